@@ -1,0 +1,246 @@
+"""Oracle restatement of ``healpy.alm2map`` on the HEALPix RING grid (scalar and spin-2).
+
+TEST INFRASTRUCTURE ONLY (see package doc).  **Parity unpinned**: healpy (>=1.17,
+``pyproject.toml:30``; libsharp / HEALPix C++ inside) is third-party, absent from
+/root/reference and not installable here, and the reference's tests hold no golden at
+this boundary.  This file restates the *published* HEALPix definitions (Gorski et al.
+2005, the HEALPix primer, and the ``alm2map``/``alm2map_pol`` facility documentation)
+that the reference's call sites rely on:
+
+* ``cora/util/hputil.py:388``      scalar ``healpy.alm2map(alm_packed, nside)``
+* ``cora/util/hputil.py:420-423``  ``healpy.alm2map([T, E, B], nside)`` (``pol=True`` default)
+* ``cora/util/hputil.py:426-430``  V through a separate scalar transform
+
+Conventions: alm packed m-major, ``idx(l, m) = m (2 lmax + 1 - m) / 2 + l``
+(``hputil.py:124-152``); ``lmax`` inferred from the packed length, ``mmax = lmax``; no beam
+or pixel window; the imaginary part of ``a_l0`` is ignored; the map value is the direct sum
+
+    T(ring, j) = sum_m w_m Re[ F_m(theta_ring) exp(i m phi_j) ],   w_0 = 1, w_{m>0} = 2,
+    F_m(theta) = sum_{l>=m} a_lm lambda_lm(cos theta)
+
+so harmonics with ``m >= nph`` alias onto ``m mod nph`` exactly as the sum dictates.
+
+It is validated analytically in ``tests/test_oracle_sht.py`` (scipy ``sph_harm_y`` direct
+sums, ``a_00`` -> constant map, spin-2 against the closed forms of ``_{+-2}Y_lm``).
+"""
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------ geometry
+def nside2npix(nside):
+    return 12 * nside * nside
+
+
+def ring_geometry(nside):
+    """Per-ring arrays for rings 1 .. 4 nside - 1 (north to south).
+
+    Returns dict with ``nph`` (pixels in ring), ``cth``/``sth`` (cos/sin of colatitude),
+    ``phi0`` (azimuth of first pixel) and ``start`` (index of first pixel, RING order).
+    """
+    n = int(nside)
+    i = np.arange(1, 4 * n, dtype=np.int64)
+    npix = 12 * n * n
+    north = np.minimum(i, 4 * n - i)  # mirror ring index for the south
+    cap = north < n
+    nph = np.where(cap, 4 * north, 4 * n)
+    nf = float(n)
+    nn = north.astype(np.float64)
+    # polar cap: cos = 1 - i^2 / (3 n^2); belt: cos = 4/3 - 2 i / (3 n)
+    cth_cap = 1.0 - nn * nn / (3.0 * nf * nf)
+    cth_belt = 4.0 / 3.0 - 2.0 * nn / (3.0 * nf)
+    cth_n = np.where(cap, cth_cap, cth_belt)
+    # sin(theta) without cancellation near the poles
+    sth_cap = np.sqrt((nn * nn / (3.0 * nf * nf)) * (1.0 + cth_cap))
+    sth_belt = np.sqrt(np.maximum((1.0 - cth_belt) * (1.0 + cth_belt), 0.0))
+    sth = np.where(cap, sth_cap, sth_belt)
+    cth = np.where(i > 2 * n, -cth_n, cth_n)
+    shifted = cap | (((north - n) & 1) == 0)
+    phi0 = np.where(shifted, np.pi / nph, 0.0)
+    start_n = np.where(cap, 2 * north * (north - 1), 2 * n * (n - 1) + 4 * n * (north - n))
+    start_s = np.where(cap, npix - 2 * north * (north + 1), 0)
+    # southern belt rings: continue the belt numbering
+    start_belt_s = 2 * n * (n - 1) + 4 * n * (i - n)
+    start = np.where(i <= 2 * n, start_n, np.where(cap, start_s, start_belt_s))
+    return {"nph": nph, "cth": cth, "sth": sth, "phi0": phi0, "start": start}
+
+
+def pix2ang_ring(nside):
+    """(theta, phi) of every pixel in RING order."""
+    g = ring_geometry(nside)
+    theta = np.empty(nside2npix(nside))
+    phi = np.empty_like(theta)
+    for r in range(len(g["nph"])):
+        s, n = g["start"][r], g["nph"][r]
+        theta[s : s + n] = np.arctan2(g["sth"][r], g["cth"][r])
+        phi[s : s + n] = g["phi0"][r] + 2.0 * np.pi * np.arange(n) / n
+    return theta, phi
+
+
+# ------------------------------------------------------------------- alm utilities
+def lmax_from_nalm(nalm):
+    lmax = int((np.sqrt(8.0 * nalm + 1.0) - 3.0) / 2.0 + 0.5)
+    if (lmax + 1) * (lmax + 2) // 2 != nalm:
+        raise ValueError("packed alm length %d is not (lmax+1)(lmax+2)/2" % nalm)
+    return lmax
+
+
+def alm_index(lmax, l, m):
+    return m * (2 * lmax + 1 - m) // 2 + l
+
+
+# ------------------------------------------------------------------- lambda_lm
+def lambda_lm(lmax, m, cth, sth):
+    """``lambda_lm(theta)`` for ``l = m .. lmax`` at every ring, shape (lmax-m+1, nring).
+
+    ``lambda_lm = sqrt((2l+1)/(4 pi) (l-m)!/(l+m)!) P_l^m(cos theta)`` with the
+    Condon-Shortley phase.  Seed ``lambda_mm`` in log space and run the standard
+    three-term recurrence on (mantissa, binary exponent) pairs so that ``sin^m theta``
+    may underflow double without harming the in-range values; the result is flushed to
+    0 only where it is below the smallest normal double.
+    """
+    cth = np.asarray(cth, dtype=np.float64)
+    sth = np.asarray(sth, dtype=np.float64)
+    nr = cth.shape[0]
+    out = np.zeros((lmax - m + 1, nr))
+    # log|lambda_mm| = 0.5 [ log((2m+1)/(4 pi)) + sum_k log((2k-1)/(2k)) ] + m log sin
+    k = np.arange(1, m + 1, dtype=np.float64)
+    logn = 0.5 * (np.log((2 * m + 1) / (4.0 * np.pi)) + np.sum(np.log1p(-1.0 / (2.0 * k))))
+    with np.errstate(divide="ignore"):
+        loglam = logn + m * np.log(sth)
+    # mantissa / exponent split (base 2)
+    e = np.floor(loglam / np.log(2.0))
+    e = np.where(np.isfinite(e), e, -1e9)
+    mant = np.exp(loglam - e * np.log(2.0)) * (-1.0 if (m & 1) else 1.0)
+    mant = np.where(sth > 0, mant, 1.0 if m == 0 else 0.0)
+    if m == 0:
+        mant = np.full(nr, np.sqrt(1.0 / (4.0 * np.pi)))
+        e = np.zeros(nr)
+    scale = e.astype(np.int64)
+    p_prev = np.zeros(nr)
+    p_cur = mant
+    out[0] = np.ldexp(p_cur, np.clip(scale, -100000, 100000).astype(np.int32))
+    a_prev = 0.0
+    for l in range(m + 1, lmax + 1):
+        a_l = np.sqrt((4.0 * l * l - 1.0) / (l * l - m * m))
+        if l == m + 1:
+            p_new = a_l * cth * p_cur
+        else:
+            p_new = a_l * (cth * p_cur - p_prev / a_prev)
+        p_prev, p_cur, a_prev = p_cur, p_new, a_l
+        big = np.abs(p_cur) > 2.0**64
+        if big.any():
+            p_cur = np.where(big, p_cur * 2.0**-64, p_cur)
+            p_prev = np.where(big, p_prev * 2.0**-64, p_prev)
+            scale = np.where(big, scale + 64, scale)
+        out[l - m] = np.ldexp(p_cur, np.clip(scale, -100000, 100000).astype(np.int32))
+    return out
+
+
+# ------------------------------------------------------------------- ring synthesis
+def _rings_from_phase(Fm, geom, ring_sel, out):
+    """Phase synthesis.  ``Fm``: complex (mmax+1, nring_sel, nchan) -> ``out[chan, pix]``.
+
+    Direct-sum definition implemented through the aliased spectrum
+    ``G_k = sum_{m = k mod nph} w_m F_m e^{i m phi0}`` and ``T_j = Re sum_k G_k e^{2 pi i jk/nph}``.
+    """
+    mmax = Fm.shape[0] - 1
+    m = np.arange(mmax + 1)
+    w = np.where(m == 0, 1.0, 2.0)
+    for a, r in enumerate(ring_sel):
+        nph = int(geom["nph"][r])
+        start = int(geom["start"][r])
+        ph = w * np.exp(1j * m * geom["phi0"][r])
+        G = np.zeros((nph, Fm.shape[2]), dtype=np.complex128)
+        np.add.at(G, m % nph, Fm[:, a, :] * ph[:, None])
+        out[:, start : start + nph] = (np.fft.ifft(G, axis=0).real * nph).T
+
+
+def alm2map(alm, nside, lmax=None):
+    """Scalar synthesis.  ``alm``: complex (nalm,) or (nchan, nalm) healpy-packed."""
+    alm = np.asarray(alm, dtype=np.complex128)
+    single = alm.ndim == 1
+    alm = np.atleast_2d(alm)
+    nchan, nalm = alm.shape
+    if lmax is None:
+        lmax = lmax_from_nalm(nalm)
+    g = ring_geometry(nside)
+    nring = 4 * nside - 1
+    Fm = np.zeros((lmax + 1, nring, nchan), dtype=np.complex128)
+    for m in range(lmax + 1):
+        lam = lambda_lm(lmax, m, g["cth"], g["sth"])  # (nl, nring)
+        a = alm[:, alm_index(lmax, m, m) : alm_index(lmax, lmax, m) + 1].copy()  # (nchan, nl)
+        if m == 0:
+            a = a.real.astype(np.complex128)
+        Fm[m] = lam.T @ a.T
+    out = np.empty((nchan, nside2npix(nside)))
+    _rings_from_phase(Fm, g, np.arange(nring), out)
+    return out[0] if single else out
+
+
+# ------------------------------------------------------------------------ spin 2
+def alm2map_spin2(almE, almB, nside, lmax=None):
+    """(E, B) -> (Q, U) in the HEALPix convention.
+
+    ``Q = -sum (aE X1 + i aB X2)``, ``U = -sum (aB X1 - i aE X2)`` with
+    ``X1 = 2 n_l [ -((l - m^2)/s^2 + l(l-1)/2) lam_lm + (c/s^2) g_lm lam_{l-1,m} ]``,
+    ``X2 = 2 n_l (m/s^2) [ -(l-1) c lam_lm + g_lm lam_{l-1,m} ]``,
+    ``n_l = ((l+2)(l+1)l(l-1))^-1/2``, ``g_lm = sqrt((2l+1)/(2l-1) (l^2-m^2))``; zero for l < 2.
+    """
+    almE = np.atleast_2d(np.asarray(almE, dtype=np.complex128))
+    almB = np.atleast_2d(np.asarray(almB, dtype=np.complex128))
+    nchan, nalm = almE.shape
+    if lmax is None:
+        lmax = lmax_from_nalm(nalm)
+    g = ring_geometry(nside)
+    c, s = g["cth"], g["sth"]
+    s2 = s * s
+    nring = 4 * nside - 1
+    FQ = np.zeros((lmax + 1, nring, nchan), dtype=np.complex128)
+    FU = np.zeros_like(FQ)
+    for m in range(lmax + 1):
+        lam = lambda_lm(lmax, m, c, s)  # l = m..lmax
+        l = np.arange(m, lmax + 1, dtype=np.float64)
+        lam_prev = np.vstack([np.zeros((1, nring)), lam[:-1]])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            nl = np.where(l >= 2, 1.0 / np.sqrt((l + 2) * (l + 1) * l * (l - 1)), 0.0)
+        glm = np.sqrt((2 * l + 1) / np.maximum(2 * l - 1, 1.0) * (l * l - m * m))
+        X1 = (2 * nl)[:, None] * (
+            -((l - m * m)[:, None] / s2[None, :] + (l * (l - 1) / 2)[:, None]) * lam
+            + (c / s2)[None, :] * glm[:, None] * lam_prev
+        )
+        X2 = (2 * nl)[:, None] * (m / s2)[None, :] * (
+            -(l - 1)[:, None] * c[None, :] * lam + glm[:, None] * lam_prev
+        )
+        sl = slice(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1)
+        aE, aB = almE[:, sl].copy(), almB[:, sl].copy()
+        if m == 0:
+            aE = aE.real.astype(np.complex128)
+            aB = aB.real.astype(np.complex128)
+        FQ[m] = -(X1.T @ aE.T + 1j * (X2.T @ aB.T))
+        FU[m] = -(X1.T @ aB.T - 1j * (X2.T @ aE.T))
+    Q = np.empty((nchan, nside2npix(nside)))
+    U = np.empty_like(Q)
+    rs = np.arange(nring)
+    _rings_from_phase(FQ, g, rs, Q)
+    _rings_from_phase(FU, g, rs, U)
+    return Q, U
+
+
+def alm2map_direct(alm, nside, lmax=None):
+    """O(npix * nalm) brute-force evaluation with scipy's Y_lm — validation only."""
+    from scipy.special import sph_harm_y
+
+    alm = np.asarray(alm, dtype=np.complex128)
+    if lmax is None:
+        lmax = lmax_from_nalm(alm.shape[-1])
+    theta, phi = pix2ang_ring(nside)
+    out = np.zeros(theta.shape)
+    for m in range(lmax + 1):
+        for l in range(m, lmax + 1):
+            a = alm[alm_index(lmax, l, m)]
+            if m == 0:
+                out += a.real * sph_harm_y(l, 0, theta, phi).real
+            else:
+                out += 2.0 * (a * sph_harm_y(l, m, theta, phi)).real
+    return out

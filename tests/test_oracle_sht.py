@@ -1,0 +1,155 @@
+"""Analytic validation of the SHT restatement (parity at this boundary is UNPINNED:
+healpy is absent; see oracle/sht.py).  Checks the HEALPix RING geometry, lambda_lm and
+the synthesis against scipy's spherical harmonics and closed forms."""
+
+import numpy as np
+import pytest
+from scipy.special import sph_harm_y
+
+from oracle import sht
+
+
+def test_ring_geometry_basic():
+    for nside in (1, 2, 4, 8, 3):
+        g = sht.ring_geometry(nside)
+        assert g["nph"].sum() == 12 * nside * nside
+        # rings tile the pixel range exactly, in order
+        assert g["start"][0] == 0
+        assert np.all(g["start"][1:] == np.cumsum(g["nph"])[:-1])
+        # equal-area: cos(theta) spacing. z of ring centres symmetric
+        np.testing.assert_allclose(g["cth"], -g["cth"][::-1], atol=1e-15)
+        np.testing.assert_allclose(g["cth"] ** 2 + g["sth"] ** 2, 1.0, rtol=1e-14)
+    # nside=1 known pixel centres: 3 rings of 4; z = 2/3, 0, -2/3; phi0 = pi/4, 0, pi/4
+    g = sht.ring_geometry(1)
+    np.testing.assert_allclose(g["cth"], [2 / 3, 0, -2 / 3], atol=1e-15)
+    np.testing.assert_allclose(g["phi0"], [np.pi / 4, 0, np.pi / 4])
+    # nside=2, published HEALPix values: ring 1 z = 1 - 1/12, ring 2 (belt, i=nside) z = 2/3
+    g = sht.ring_geometry(2)
+    np.testing.assert_allclose(g["cth"][:4], [1 - 1 / 12.0, 2 / 3.0, 1 / 3.0, 0.0], atol=1e-15)
+    np.testing.assert_allclose(g["phi0"][:4], [np.pi / 4, np.pi / 8, 0.0, np.pi / 8])
+
+
+def test_lambda_matches_scipy():
+    theta = np.array([0.05, 0.7, 1.3, np.pi / 2, 2.4, 3.1])
+    lmax = 40
+    for m in (0, 1, 2, 5, 17, 40):
+        lam = sht.lambda_lm(lmax, m, np.cos(theta), np.sin(theta))
+        for l in range(m, lmax + 1):
+            ref = sph_harm_y(l, m, theta, 0.0).real
+            np.testing.assert_allclose(lam[l - m], ref, rtol=2e-12, atol=1e-13)
+
+
+def test_lambda_scaled_start_no_underflow():
+    # sin^m underflows double: m = 1500 at theta ~ 1e-3 is ~1e-4500; values must come back
+    # in range once l ~ m / sin(theta) is reached or stay exactly 0 -- never NaN/inf.
+    theta = np.array([1e-3, 0.3, np.pi / 2])
+    lam = sht.lambda_lm(1600, 1500, np.cos(theta), np.sin(theta))
+    assert np.all(np.isfinite(lam))
+    assert np.all(lam[:, 0] == 0.0)
+    # on the equator the harmonic is O(1) near the top of the l range
+    assert np.abs(lam[:, 2]).max() > 0.1
+    # orthonormality spot check via high-order Gauss-Legendre: int lam_lm lam_l'm dcos = delta/(2 pi)
+    x, w = np.polynomial.legendre.leggauss(400)
+    lam = sht.lambda_lm(120, 100, x, np.sqrt(1 - x * x))
+    gram = (lam * w) @ lam.T * 2 * np.pi
+    np.testing.assert_allclose(gram, np.eye(gram.shape[0]), atol=5e-12)
+
+
+def test_monopole_and_single_modes():
+    nside = 4
+    lmax = 3 * nside - 1
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    alm = np.zeros(nalm, dtype=complex)
+    alm[0] = np.sqrt(4 * np.pi)
+    np.testing.assert_allclose(sht.alm2map(alm, nside), 1.0, rtol=1e-14)
+    theta, phi = sht.pix2ang_ring(nside)
+    for (l, m, val) in ((1, 0, 1.0), (2, 1, 0.3 - 0.7j), (5, 5, 1.0j), (11, 3, -2.0 + 0.5j)):
+        alm[:] = 0
+        alm[sht.alm_index(lmax, l, m)] = val
+        ref = (val.real if m == 0 else 2.0) * 1.0
+        y = sph_harm_y(l, m, theta, phi)
+        ref = val.real * y.real if m == 0 else 2.0 * (val * y).real
+        np.testing.assert_allclose(sht.alm2map(alm, nside), ref, atol=1e-13)
+
+
+def test_imag_of_m0_ignored():
+    nside, lmax = 2, 5
+    rng = np.random.default_rng(0)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    alm = rng.standard_normal(nalm) + 1j * rng.standard_normal(nalm)
+    a2 = alm.copy()
+    a2[: lmax + 1] = a2[: lmax + 1].real
+    np.testing.assert_array_equal(sht.alm2map(alm, nside), sht.alm2map(a2, nside))
+
+
+@pytest.mark.parametrize("nside,lmax", [(2, 5), (4, 11), (4, 12), (8, 23), (3, 8)])
+def test_alm2map_vs_direct_sum(nside, lmax):
+    # lmax = 3 nside - 1 and 3 nside: every ring has nph < 2 lmax + 1 -> aliasing path
+    rng = np.random.default_rng(nside * 100 + lmax)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    alm = rng.standard_normal(nalm) + 1j * rng.standard_normal(nalm)
+    fast = sht.alm2map(alm, nside)
+    slow = sht.alm2map_direct(alm, nside)
+    assert np.max(np.abs(fast - slow)) / np.max(np.abs(slow)) < 1e-13
+
+
+def test_multichannel_matches_single():
+    nside, lmax = 4, 11
+    rng = np.random.default_rng(7)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    alm = rng.standard_normal((3, nalm)) + 1j * rng.standard_normal((3, nalm))
+    m = sht.alm2map(alm, nside)
+    for c in range(3):
+        np.testing.assert_allclose(m[c], sht.alm2map(alm[c], nside), rtol=0, atol=1e-14)
+
+
+def _sylm(s, l, m, theta, phi):
+    """Spin-weighted harmonic _sY_lm by Goldberg et al.'s closed sum (validation only)."""
+    from math import comb, factorial as f
+
+    pref = (-1.0) ** m * np.sqrt(f(l + m) * f(l - m) * (2 * l + 1) / (4 * np.pi * f(l + s) * f(l - s)))
+    sh, ch = np.sin(theta / 2), np.cos(theta / 2)
+    tot = np.zeros_like(theta)
+    for r in range(0, l - s + 1):
+        k = r + s - m
+        if k < 0 or k > l + s:
+            continue
+        # sin^{2l}(t/2) cot^{2r+s-m}(t/2) = cos^{2r+s-m} sin^{2l-2r-s+m}
+        tot = tot + comb(l - s, r) * comb(l + s, k) * (-1.0) ** (l - r - s) * ch ** (2 * r + s - m) * sh ** (2 * l - 2 * r - s + m)
+    return pref * tot * np.exp(1j * m * phi)
+
+
+def test_goldberg_helper_against_known():
+    theta = np.linspace(0.1, 3.0, 7)
+    phi = np.linspace(0.0, 5.0, 7)
+    for l, m in ((0, 0), (2, 1), (3, -2), (5, 4)):
+        np.testing.assert_allclose(_sylm(0, l, m, theta, phi), sph_harm_y(l, m, theta, phi), atol=1e-13)
+    np.testing.assert_allclose(_sylm(2, 2, 2, theta, phi), np.sqrt(5 / (64 * np.pi)) * (1 - np.cos(theta)) ** 2 * np.exp(2j * phi), atol=1e-14)
+    np.testing.assert_allclose(_sylm(-2, 2, 2, theta, phi), np.sqrt(5 / (64 * np.pi)) * (1 + np.cos(theta)) ** 2 * np.exp(2j * phi), atol=1e-14)
+
+
+@pytest.mark.parametrize("nside,lmax", [(2, 5), (4, 11), (4, 12)])
+def test_spin2_vs_direct_sum(nside, lmax):
+    """Q + iU = sum_{l,m=-l..l} _2a_lm _2Y_lm with _2a_lm = -(aE + i aB) (HEALPix sign)."""
+    rng = np.random.default_rng(11 + lmax)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    aE = rng.standard_normal(nalm) + 1j * rng.standard_normal(nalm)
+    aB = rng.standard_normal(nalm) + 1j * rng.standard_normal(nalm)
+    for l in (0, 1):  # no spin-2 content below l = 2
+        for m in range(l + 1):
+            aE[sht.alm_index(lmax, l, m)] = aB[sht.alm_index(lmax, l, m)] = 0
+    theta, phi = sht.pix2ang_ring(nside)
+    P = np.zeros(theta.shape, dtype=complex)
+    for l in range(2, lmax + 1):
+        for m in range(-l, l + 1):
+            i = sht.alm_index(lmax, l, abs(m))
+            e, b = aE[i], aB[i]
+            if m == 0:
+                e, b = e.real, b.real
+            if m < 0:
+                e, b = (-1) ** m * np.conj(e), (-1) ** m * np.conj(b)
+            P += -(e + 1j * b) * _sylm(2, l, m, theta, phi)
+    Q, U = sht.alm2map_spin2(aE, aB, nside)
+    scale = np.max(np.abs(P))
+    assert np.max(np.abs(Q[0] - P.real)) / scale < 1e-12
+    assert np.max(np.abs(U[0] - P.imag)) / scale < 1e-12
