@@ -1,0 +1,72 @@
+"""Device-side plumbing shared by the host modules: buffers (torch owns the memory), SHT plan
+cache, workspace sizing."""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_plans = {}
+
+
+def torch():
+    return _lib.require_cuda()
+
+
+def device():
+    t = torch()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def to_device(a, dtype=None):
+    """numpy array / torch tensor -> contiguous CUDA tensor (a copy for host input)."""
+    t = torch()
+    if isinstance(a, t.Tensor):
+        x = a.to(device())
+        if dtype is not None and x.dtype != dtype:
+            x = x.to(dtype)
+        return x.contiguous()
+    arr = np.ascontiguousarray(a)
+    x = t.from_numpy(arr).to(device(), non_blocking=False)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x
+
+
+def empty(shape, dtype):
+    return torch().empty(shape, dtype=dtype, device=device())
+
+
+def zeros(shape, dtype):
+    return torch().zeros(shape, dtype=dtype, device=device())
+
+
+def workspace(nbytes):
+    return torch().empty(int(nbytes), dtype=torch().uint8, device=device())
+
+
+def free_bytes():
+    free, _ = torch().cuda.mem_get_info()
+    return int(free)
+
+
+def sht_plan(nside, lmax):
+    """Cached opaque SHT plan for (device, nside, lmax)."""
+    t = torch()
+    key = (t.cuda.current_device(), int(nside), int(lmax))
+    if key not in _plans:
+        h = ctypes.c_void_p()
+        _lib.call("cora_b200_sht_plan_create", int(nside), int(lmax), ctypes.byref(h))
+        _plans[key] = h
+    return _plans[key]
+
+
+def sht_workspace(plan, layout, nchan, mult=1, reserve=2 << 30):
+    """Workspace for alm2map: whole-problem size if it fits, else what is free minus a reserve."""
+    lib = _lib.load()
+    per16 = lib.cora_b200_alm2map_workspace_bytes(plan, layout, 16) * mult
+    need = lib.cora_b200_alm2map_workspace_bytes(plan, layout, int(nchan)) * mult
+    avail = free_bytes() - reserve
+    nbytes = min(need, max(per16, avail))
+    return workspace(nbytes), nbytes

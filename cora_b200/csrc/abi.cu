@@ -1,0 +1,81 @@
+// Library-level C ABI: version, error string, launch counter, FP64 peak probe.
+#include "common.cuh"
+#include "cora_b200.h"
+
+#include <cstdarg>
+
+namespace cb {
+
+static thread_local char g_err[1024] = "";
+long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// 8 independent DMMA chains per warp; 256 FMA per DMMA per warp.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c0[i] = threadIdx.x; c1[i] = i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma884(c0[i], c1[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cora_b200_version(void) { return 100; }
+extern "C" const char* cora_b200_last_error(void) { return get_error(); }
+extern "C" long long cora_b200_launch_count(void) { return g_launches; }
+
+extern "C" int cora_b200_fp64_peak(double ms_budget, double* tflops_out, void* stream) {
+    CB_REQUIRE(tflops_out, 1, "fp64_peak: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev, nsm;
+    CB_CUDA(cudaGetDevice(&dev));
+    CB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = nsm * 4, iters = 4096;
+    double* out;
+    CB_CUDA(cudaMalloc(&out, sizeof(double) * grid * 256));
+    cudaEvent_t e0, e1;
+    CB_CUDA(cudaEventCreate(&e0));
+    CB_CUDA(cudaEventCreate(&e1));
+    fp64_peak_kernel<<<grid, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);   // warm-up
+    count_launch();
+    double flop_per = 2.0 * 256 * 8 * (double)iters * 8.0 * grid;
+    int reps = 1;
+    double best = 0;
+    // one launch is ~2.1 ms on B200; repeat until the budget is used, keep the best
+    double spent = 0;
+    while (spent < ms_budget && reps < 1000) {
+        CB_CUDA(cudaEventRecord(e0, st));
+        fp64_peak_kernel<<<grid, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
+        count_launch();
+        CB_CUDA(cudaEventRecord(e1, st));
+        CB_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        CB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        spent += ms;
+        double tf = flop_per / ms * 1e-9;
+        if (tf > best) best = tf;
+        reps++;
+    }
+    CB_LAUNCH_CHECK();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_out = best;
+    return 0;
+}

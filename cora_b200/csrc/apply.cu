@@ -1,0 +1,219 @@
+// Gaussian draws + root application:  a_lm(nu) = sum_nu' M_l[nu, nu'] g_l[nu', m]   (sm_100a)
+//
+// replaces complex_std_normal + np.dot + the strided scatter of cora/core/skysim.py:119-121
+// (cora/util/nputil.py:104-125).  Draws: counter-based Philox4x32-10, one call per complex
+// variate, counter = (l, m, nu', 0), key = seed; Box-Muller in FP64.  Apply: batched FP64
+// tensor-core GEMM (DMMA.8x8x4) per l, triangular roots (Cholesky) skip the zero half of K,
+// output written straight into the PANEL layout the Legendre stage reads.
+#include "common.cuh"
+#include "cora_b200.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace cb {
+
+// --------------------------------------------------------------------------- Philox
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                              unsigned k1, unsigned out[4]) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// complex standard normal (re, im each N(0, 1/2)) for (l, m, nu')
+__device__ __forceinline__ double2 philox_cnormal(unsigned long long seed, unsigned l, unsigned m, unsigned nu) {
+    unsigned r[4];
+    philox4x32_10(l, m, nu, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+    const unsigned long long a = ((unsigned long long)r[1] << 32) | r[0];
+    const unsigned long long b = ((unsigned long long)r[3] << 32) | r[2];
+    const double u1 = ((double)(a >> 11) + 0.5) * 0x1p-53;   // (0, 1)
+    const double u2 = ((double)(b >> 11) + 0.5) * 0x1p-53;
+    const double rad = sqrt(-log(u1));                       // sqrt(-2 ln u)/sqrt(2)
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    return make_double2(rad * c, rad * s);
+}
+
+struct LDesc {
+    long long goff;   // offset (complex elements) of this l's draws in the gauss buffer
+    int l;            // global multipole
+    int ld;           // row length (complex) of the gauss buffer for this l
+};
+
+__global__ void draw_kernel(const LDesc* __restrict__ ld, int nz, unsigned long long seed, double2* __restrict__ G) {
+    const LDesc d = ld[blockIdx.z];
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nu = blockIdx.y;
+    if (m > d.l) return;
+    G[d.goff + (long long)nu * d.ld + m] = philox_cnormal(seed, (unsigned)d.l, (unsigned)m, (unsigned)nu);
+}
+
+// ---------------------------------------------------------------------------- apply
+constexpr int AP_TM = 128;   // nu rows per CTA
+constexpr int AP_TN = 64;    // real columns per CTA (32 m's)
+constexpr int AP_KC = 16;
+constexpr int AP_ALD = 20;   // As[128][20]  (g*20 + t: conflict-free per half-warp)
+constexpr int AP_BLD = 68;   // Bs[16][68]   (t*68 + g)
+
+struct ApplyParams {
+    const double* root;       // [nl][nz][nz]
+    const LDesc* ldesc;
+    const int* dense;         // per-l flag: 1 = dense root (eigh), 0 = lower triangular; may be null (all dense)
+    const double2* G;
+    double2* panel;
+    long long panel_stride;
+    int nz, lmax, chan0, nu0, nnu;
+};
+
+__global__ void __launch_bounds__(256) apply_kernel(ApplyParams P) {
+    __shared__ __align__(16) double As[AP_TM * AP_ALD];
+    __shared__ __align__(16) double Bs[AP_KC * AP_BLD];
+    const int li = blockIdx.z;
+    const LDesc d = P.ldesc[li];
+    const int m0 = blockIdx.x * (AP_TN / 2);
+    if (m0 > d.l) return;
+    const int r0 = P.nu0 + blockIdx.y * AP_TM;           // first nu row of the tile
+    const int nz = P.nz;
+    const double* M = P.root + (long long)li * nz * nz;
+    const double* Gd = (const double*)(P.G + d.goff);    // rows nu', 2*ld doubles each
+    const int gld = 2 * d.ld;
+    const bool tri = P.dense ? (P.dense[li] == 0) : false;
+    const int kend = tri ? min(nz, r0 + AP_TM) : nz;
+    const int ncols = 2 * (d.l + 1);                      // valid real columns
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int k0 = 0; k0 < kend; k0 += AP_KC) {
+        __syncthreads();
+        // A tile: 128 x 16
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int e = tid + q * 256;
+            const int rr = e >> 4, kk = e & 15;
+            const int r = r0 + rr, k = k0 + kk;
+            As[rr * AP_ALD + kk] = (r < nz && k < nz) ? M[(long long)r * nz + k] : 0.0;
+        }
+        // B tile: 16 x 64
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = tid + q * 256;
+            const int kk = e >> 6, cc = e & 63;
+            const int k = k0 + kk, col = 2 * m0 + cc;
+            Bs[kk * AP_BLD + cc] = (k < nz && col < ncols) ? Gd[(long long)k * gld + col] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < AP_KC / 4; k4++) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) af[mb] = As[(wm * 32 + 8 * mb + g) * AP_ALD + k4 * 4 + t];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) bf[nb] = Bs[(k4 * 4 + t) * AP_BLD + wn * 32 + 8 * nb + g];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+        }
+    }
+    // epilogue: C[g][2t], C[g][2t+1] = (re, im) of (nu = row g, m = col t)
+    const int lmax = P.lmax;
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) {
+        const int m = m0 + wn * 16 + 4 * nb + t;
+        if (m > d.l) continue;
+        const long long idx = (long long)m * (2 * lmax + 1 - m) / 2 + d.l;
+        double2* row = P.panel + idx * P.panel_stride + P.chan0;
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) {
+            const int nu = r0 + wm * 32 + 8 * mb + g;
+            if (nu < P.nu0 + P.nnu && nu < nz) row[nu - P.nu0] = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+        }
+    }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" long long cora_b200_draw_apply_workspace_bytes(int nz, int lmax_in_batch, int nl_batch) {
+    return 16LL * nz * (long long)(lmax_in_batch + 1) * nl_batch + 64LL * nl_batch + 1024;
+}
+
+extern "C" int cora_b200_draw_apply(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz, int lmax,
+                                    unsigned long long seed, const void* gauss, long long gauss_ld, void* alm_panel,
+                                    long long panel_stride, int chan0, int nu0, int nnu, void* workspace,
+                                    long long ws_bytes, void* stream) {
+    CB_REQUIRE(root && l_list_h && alm_panel && workspace, 1, "draw_apply: null argument");
+    CB_REQUIRE(nl >= 1 && nz >= 1 && lmax >= 0 && nnu >= 1 && nu0 >= 0 && nu0 + nnu <= nz, 1, "draw_apply: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    long long avail = (char*)workspace + ws_bytes - ws;
+    for (int i = 0; i < nl; i++)
+        CB_REQUIRE(l_list_h[i] >= 0 && l_list_h[i] <= lmax, 1, "draw_apply: l_list[%d]=%d outside [0,%d]", i, l_list_h[i], lmax);
+    if (gauss) CB_REQUIRE(gauss_ld >= lmax + 1 || nl == 0, 1, "draw_apply: gauss_ld %lld < lmax+1", gauss_ld);
+
+    int i0 = 0;
+    while (i0 < nl) {
+        // choose a batch of l's whose descriptors (+ generated draws) fit the workspace
+        std::vector<LDesc> hd;
+        long long gneed = 0;
+        int i1 = i0;
+        while (i1 < nl) {
+            LDesc d;
+            d.l = l_list_h[i1];
+            if (gauss) { d.goff = (long long)i1 * nz * gauss_ld; d.ld = (int)gauss_ld; }
+            else { d.goff = gneed; d.ld = d.l + 1; }
+            long long add = gauss ? 0 : (long long)nz * d.ld;
+            long long bytes = ((long long)(hd.size() + 1) * sizeof(LDesc) + 255) / 256 * 256 + 16 * (gneed + add) + 512;
+            if (bytes > avail && i1 > i0) break;
+            CB_REQUIRE(bytes <= avail, 4, "draw_apply: workspace too small (%lld B) for a single l (needs %lld B)", avail, bytes);
+            gneed += add;
+            hd.push_back(d);
+            i1++;
+            if (hd.size() >= 65535) break;
+        }
+        const int nb = (int)hd.size();
+        LDesc* dd = (LDesc*)ws;
+        double2* Gbuf = (double2*)(ws + ((long long)nb * sizeof(LDesc) + 255) / 256 * 256);
+        CB_CUDA(cudaMemcpyAsync(dd, hd.data(), sizeof(LDesc) * nb, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaStreamSynchronize(st));   // hd is about to go out of scope
+        int lbig = 0;
+        for (auto& d : hd) lbig = std::max(lbig, d.l);
+        const double2* Gsrc = (const double2*)gauss;
+        if (!gauss) {
+            draw_kernel<<<dim3(ceil_div(lbig + 1, 128), nz, nb), 128, 0, st>>>(dd, nz, seed, Gbuf);
+            count_launch();
+            CB_LAUNCH_CHECK();
+            Gsrc = Gbuf;
+        }
+        ApplyParams P;
+        P.root = root + (long long)i0 * nz * nz;
+        P.ldesc = dd;
+        P.dense = dense_flag ? dense_flag + i0 : nullptr;
+        P.G = Gsrc; P.panel = (double2*)alm_panel; P.panel_stride = panel_stride;
+        P.nz = nz; P.lmax = lmax; P.chan0 = chan0; P.nu0 = nu0; P.nnu = nnu;
+        dim3 grid(ceil_div(lbig + 1, AP_TN / 2), ceil_div(nnu, AP_TM), nb);
+        apply_kernel<<<grid, 256, 0, st>>>(P);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        if (i1 < nl) CB_CUDA(cudaStreamSynchronize(st));   // workspace reuse
+        i0 = i1;
+    }
+    return 0;
+}

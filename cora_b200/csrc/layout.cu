@@ -1,0 +1,79 @@
+// alm layout conversions between the library's PANEL layout and cora's dense [chan][l][m].
+#include "common.cuh"
+#include "cora_b200.h"
+
+namespace cb {
+
+// one thread per (l, m<=l... full square) x channel tile; channels contiguous in the panel,
+// m contiguous in the dense array -> stage through shared memory for coalescing on both sides.
+__global__ void panel_to_dense_kernel(const double2* __restrict__ panel, long long stride, int chan0, int nchan,
+                                      int lmax, double2* __restrict__ dense) {
+    __shared__ double2 tile[32][33];
+    const int L = lmax + 1;
+    const int l = blockIdx.z;
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int m = m0 + r, c = c0 + threadIdx.x;
+        double2 v = make_double2(0.0, 0.0);
+        if (m <= l && c < nchan) {
+            long long idx = (long long)m * (2 * lmax + 1 - m) / 2 + l;
+            v = panel[idx * stride + chan0 + c];
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, m = m0 + threadIdx.x;
+        if (c < nchan && m < L) dense[((long long)c * L + l) * L + m] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void dense_to_panel_kernel(const double2* __restrict__ dense, int nchan, int lmax,
+                                      double2* __restrict__ panel, long long stride, int chan0) {
+    __shared__ double2 tile[32][33];
+    const int L = lmax + 1;
+    const int l = blockIdx.z;
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, m = m0 + threadIdx.x;
+        double2 v = make_double2(0.0, 0.0);
+        if (c < nchan && m <= l) v = dense[((long long)c * L + l) * L + m];
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int m = m0 + r, c = c0 + threadIdx.x;
+        if (m <= l && c < nchan) {
+            long long idx = (long long)m * (2 * lmax + 1 - m) / 2 + l;
+            panel[idx * stride + chan0 + c] = tile[threadIdx.x][r];
+        }
+    }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cora_b200_alm_panel_to_dense(const void* alm_panel, long long panel_stride, int chan0, int nchan, int lmax,
+                                            void* dense, void* stream) {
+    CB_REQUIRE(alm_panel && dense && nchan >= 1 && lmax >= 0, 1, "alm_panel_to_dense: bad arguments");
+    CB_REQUIRE(lmax + 1 <= 65535, 1, "alm_panel_to_dense: lmax too large");
+    dim3 grid(ceil_div(lmax + 1, 32), ceil_div(nchan, 32), lmax + 1);
+    panel_to_dense_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const double2*)alm_panel, panel_stride, chan0, nchan,
+                                                                          lmax, (double2*)dense);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cora_b200_alm_dense_to_panel(const void* dense, int nchan, int lmax, void* alm_panel, long long panel_stride,
+                                            int chan0, void* stream) {
+    CB_REQUIRE(alm_panel && dense && nchan >= 1 && lmax >= 0, 1, "alm_dense_to_panel: bad arguments");
+    CB_REQUIRE(lmax + 1 <= 65535, 1, "alm_dense_to_panel: lmax too large");
+    dim3 grid(ceil_div(lmax + 1, 32), ceil_div(nchan, 32), lmax + 1);
+    dense_to_panel_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const double2*)dense, nchan, lmax,
+                                                                          (double2*)alm_panel, panel_stride, chan0);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}

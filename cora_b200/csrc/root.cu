@@ -1,0 +1,349 @@
+// Batched per-l matrix root with the reference's semantics (sm_100a).
+//
+//   corrm = C_l + 1e-14 max(diag C_l) I                     (cora/core/skysim.py:116-117)
+//   try Cholesky (lower); on a non-positive pivot fall back to a symmetric eigen-
+//   decomposition, zero eigenvalues < 1e-16 max, root = evecs sqrt(evals), all columns
+//   kept, ascending eigenvalue order                        (cora/util/nputil.py:51-101)
+//
+// Cholesky: one CTA per matrix, left-looking blocked (32-wide panels) on the matrix resident
+// in global/L2.  Fallback: one CTA per failed matrix, one-sided (Hestenes) Jacobi on the rows
+// of the symmetric matrix with accumulated rotations; rows end up as lambda_i v_i^T.
+#include "common.cuh"
+#include "cora_b200.h"
+
+#include <algorithm>
+
+namespace cb {
+
+constexpr int CH_NB = 32;      // panel width
+constexpr int CH_THREADS = 256;
+
+// jitter + copy lower triangle (upper zeroed); also per-matrix max(diag)
+__global__ void root_prepare_kernel(const double* __restrict__ cl, int nz, double jitter_rel, double* __restrict__ root,
+                                    double* __restrict__ dmax_out) {
+    __shared__ double red[256];
+    const long long base = (long long)blockIdx.x * nz * nz;
+    double mx = -1.0e308;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) mx = fmax(mx, cl[base + (long long)i * nz + i]);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    const double cmax = red[0] * jitter_rel;
+    if (threadIdx.x == 0) dmax_out[blockIdx.x] = red[0];
+    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
+        const int r = (int)(e / nz), c = (int)(e % nz);
+        double v = 0.0;
+        if (c <= r) v = cl[base + e] + (r == c ? cmax : 0.0);
+        root[base + e] = v;
+    }
+}
+
+// In-place lower Cholesky of root[l] (row-major, lower triangle holds the matrix).
+// fail[l] = 1 if a pivot is <= 0 or NaN (LAPACK dpotrf info > 0).
+__global__ void __launch_bounds__(CH_THREADS) cholesky_kernel(double* __restrict__ root, int nz, int* __restrict__ fail) {
+    __shared__ double Lc[CH_NB][CH_NB + 1];     // rows kb..kb+NB of the previous-columns chunk / diagonal block
+    __shared__ double Lr[64][CH_NB + 1];        // a 64-row slab of the same column chunk
+    __shared__ int s_fail;
+    double* A = root + (long long)blockIdx.x * nz * nz;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    for (int kb = 0; kb < nz; kb += CH_NB) {
+        const int nbk = min(CH_NB, nz - kb);
+        // (1) panel update: A[r, kb+c] -= sum_{p<kb} A[r,p] A[kb+c,p]   for r >= kb
+        if (kb > 0) {
+            for (int r0 = kb; r0 < nz; r0 += 64) {
+                const int c = tid & 31, rq = tid >> 5;   // 8 row groups
+                double acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = 0.0;
+                for (int p0 = 0; p0 < kb; p0 += CH_NB) {
+                    __syncthreads();
+                    for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                        const int rr = e >> 5, pp = e & 31;
+                        Lc[rr][pp] = (kb + rr < nz) ? A[(long long)(kb + rr) * nz + p0 + pp] : 0.0;
+                    }
+                    for (int e = tid; e < 64 * CH_NB; e += CH_THREADS) {
+                        const int rr = e >> 5, pp = e & 31;
+                        Lr[rr][pp] = (r0 + rr < nz) ? A[(long long)(r0 + rr) * nz + p0 + pp] : 0.0;
+                    }
+                    __syncthreads();
+#pragma unroll 8
+                    for (int pp = 0; pp < CH_NB; pp++) {
+                        const double lc = Lc[c][pp];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) acc[q] = fma(Lr[rq + 8 * q][pp], lc, acc[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int r = r0 + rq + 8 * q;
+                    if (r < nz && c < nbk && kb + c <= r) A[(long long)r * nz + kb + c] -= acc[q];
+                }
+            }
+        }
+        __syncthreads();
+        // (2) factor the diagonal block in shared memory (unblocked, column by column)
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+            const int rr = e >> 5, cc = e & 31;
+            Lc[rr][cc] = (rr < nbk && cc <= rr) ? A[(long long)(kb + rr) * nz + kb + cc] : 0.0;
+        }
+        __syncthreads();
+        for (int jj = 0; jj < nbk; jj++) {
+            if (tid == 0) {
+                const double d = Lc[jj][jj];
+                if (!(d > 0.0)) s_fail = 1;
+                Lc[jj][jj] = sqrt(d);
+            }
+            __syncthreads();
+            if (s_fail) break;
+            const double dj = Lc[jj][jj];
+            if (tid > jj && tid < nbk) Lc[tid][jj] /= dj;
+            __syncthreads();
+            // trailing update inside the block
+            for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                const int rr = e >> 5, cc = e & 31;
+                if (cc > jj && cc <= rr && rr < nbk) Lc[rr][cc] -= Lc[rr][jj] * Lc[cc][jj];
+            }
+            __syncthreads();
+        }
+        if (s_fail) break;
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+            const int rr = e >> 5, cc = e & 31;
+            if (rr < nbk && cc <= rr) A[(long long)(kb + rr) * nz + kb + cc] = Lc[rr][cc];
+        }
+        // (3) triangular solve for the rows below: X L_kk^T = B, one row per thread
+        for (int r = kb + nbk + tid; r < nz; r += CH_THREADS) {
+            double xrow[CH_NB];
+#pragma unroll
+            for (int cc = 0; cc < CH_NB; cc++) xrow[cc] = (cc < nbk) ? A[(long long)r * nz + kb + cc] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < CH_NB; cc++) {
+                if (cc < nbk) {
+                    double v = xrow[cc];
+#pragma unroll
+                    for (int pp = 0; pp < CH_NB; pp++)
+                        if (pp < cc) v -= xrow[pp] * Lc[cc][pp];
+                    xrow[cc] = v / Lc[cc][cc];
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < CH_NB; cc++)
+                if (cc < nbk) A[(long long)r * nz + kb + cc] = xrow[cc];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) fail[blockIdx.x] = s_fail;
+}
+
+// ----------------------------------------------------------------- Jacobi fallback
+// G (rows) starts as the symmetrised jittered matrix; V starts as identity.  Rotating rows
+// p,q of both by the same plane rotation until all rows of G are mutually orthogonal gives
+// G = diag(lambda) V, rows of V the eigenvectors.  Round-robin ordering, one warp per pair.
+__global__ void jacobi_init_kernel(const double* __restrict__ cl, const int* __restrict__ fail_list, int nz,
+                                   double jitter_rel, const double* __restrict__ dmax, double* __restrict__ G,
+                                   double* __restrict__ V) {
+    const int l = fail_list[blockIdx.x];
+    const long long src = (long long)l * nz * nz, dst = (long long)blockIdx.x * nz * nz;
+    const double cmax = dmax[l] * jitter_rel;
+    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
+        const int r = (int)(e / nz), c = (int)(e % nz);
+        // LAPACK eigh(lower=True) reads the lower triangle only
+        const double v = (c <= r) ? cl[src + e] : cl[src + (long long)c * nz + r];
+        G[dst + e] = v + (r == c ? cmax : 0.0);
+        V[dst + e] = (r == c) ? 1.0 : 0.0;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall, double* __restrict__ Vall, int nz,
+                                                      int max_sweeps, int* __restrict__ sweeps_out) {
+    __shared__ int s_rot;
+    double* G = Gall + (long long)blockIdx.x * nz * nz;
+    double* V = Vall + (long long)blockIdx.x * nz * nz;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int npl = nz + (nz & 1);          // players in the round-robin (pad to even)
+    const int nsteps = npl - 1, npairs = npl / 2;
+    int sweep = 0;
+    for (; sweep < max_sweeps; sweep++) {
+        if (threadIdx.x == 0) s_rot = 0;
+        __syncthreads();
+        for (int step = 0; step < nsteps; step++) {
+            for (int pi = warp; pi < npairs; pi += nwarp) {
+                // circle method: player npl-1 fixed, others rotate
+                int a = (pi == 0) ? npl - 1 : (step + pi) % (npl - 1);
+                int b = (step + npl - 1 - pi) % (npl - 1);
+                int p = min(a, b), q = max(a, b);
+                if (q >= nz) continue;   // bye
+                double* gp = G + (long long)p * nz;
+                double* gq = G + (long long)q * nz;
+                double app = 0, aqq = 0, apq = 0;
+                for (int c = lane; c < nz; c += 32) {
+                    const double x = gp[c], y = gq[c];
+                    app = fma(x, x, app); aqq = fma(y, y, aqq); apq = fma(x, y, apq);
+                }
+                app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
+                if (fabs(apq) <= 1e-15 * sqrt(app * aqq) || apq == 0.0) continue;
+                const double zeta = (aqq - app) / (2.0 * apq);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                for (int c = lane; c < nz; c += 32) {
+                    const double x = gp[c], y = gq[c];
+                    gp[c] = cs * x - sn * y;
+                    gq[c] = sn * x + cs * y;
+                }
+                double* vp = V + (long long)p * nz;
+                double* vq = V + (long long)q * nz;
+                for (int c = lane; c < nz; c += 32) {
+                    const double x = vp[c], y = vq[c];
+                    vp[c] = cs * x - sn * y;
+                    vq[c] = sn * x + cs * y;
+                }
+                if (lane == 0) s_rot = 1;
+            }
+            __syncthreads();
+        }
+        const int any = s_rot;
+        __syncthreads();
+        if (!any) break;
+    }
+    if (threadIdx.x == 0) sweeps_out[blockIdx.x] = sweep;
+}
+
+// eigenvalues lambda_i = v_i . g_i, clip, sort ascending, write root[:, rank] = v_i sqrt(lambda_i)
+__global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __restrict__ Gall, const double* __restrict__ Vall,
+                                                            const int* __restrict__ fail_list, int nz, double clip_rel,
+                                                            double* __restrict__ root, int* __restrict__ num_pos,
+                                                            double* __restrict__ evals_ws, int* __restrict__ rank_ws) {
+    __shared__ double s_max;
+    __shared__ int s_npos;
+    const int l = fail_list[blockIdx.x];
+    const double* G = Gall + (long long)blockIdx.x * nz * nz;
+    const double* V = Vall + (long long)blockIdx.x * nz * nz;
+    double* ev = evals_ws + (long long)blockIdx.x * nz;
+    int* rank = rank_ws + (long long)blockIdx.x * nz;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = warp; i < nz; i += nwarp) {
+        double s = 0.0;
+        for (int c = lane; c < nz; c += 32) s = fma(V[(long long)i * nz + c], G[(long long)i * nz + c], s);
+        s = warp_sum(s);
+        if (lane == 0) ev[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = -1.0e308;
+        for (int i = 0; i < nz; i++) mx = fmax(mx, ev[i]);
+        s_max = mx;
+        s_npos = 0;
+    }
+    __syncthreads();
+    const double thr = s_max * clip_rel;
+    // rank of each eigenvalue in ascending order (ties broken by index)
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) {
+        const double vi = ev[i];
+        int rk = 0;
+        for (int k = 0; k < nz; k++) {
+            const double vk = ev[k];
+            rk += (vk < vi) || (vk == vi && k < i);
+        }
+        rank[i] = rk;
+        if (!(vi < thr) && vi != 0.0) atomicAdd(&s_npos, 1);
+    }
+    __syncthreads();
+    double* R = root + (long long)l * nz * nz;
+    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
+        const int i = (int)(e / nz), r = (int)(e % nz);     // eigenpair i, row r of the root
+        const double lam = ev[i];
+        const double sc = (lam < thr) ? 0.0 : sqrt(fmax(lam, 0.0));
+        R[(long long)r * nz + rank[i]] = V[(long long)i * nz + r] * sc;
+    }
+    if (threadIdx.x == 0) num_pos[l] = s_npos;
+}
+
+__global__ void root_flags_kernel(const int* __restrict__ fail, int nl, int nz, int* __restrict__ used_eigh,
+                                  int* __restrict__ num_pos, int* __restrict__ fail_list, int* __restrict__ nfail) {
+    // single thread block: compact the failed indices (order preserved)
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int l = 0; l < nl; l++) {
+            used_eigh[l] = fail[l];
+            num_pos[l] = nz;
+            if (fail[l]) fail_list[n++] = l;
+        }
+        *nfail = n;
+    }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+// workspace: dmax[nl] | fail[nl] | fail_list[nl] | nfail | evals[nl*nz] | rank[nl*nz] | sweeps[nl] | G | V (eigh slots)
+static long long root_fixed_bytes(int nl, int nz) {
+    return 8LL * nl + 4LL * nl * 3 + 64 + 12LL * nl * nz + 10 * 256;
+}
+
+extern "C" long long cora_b200_root_workspace_bytes(int nl, int nz) {
+    // room for every matrix to take the eigh path (2 nz^2 doubles each); a smaller workspace is
+    // accepted and processed in waves
+    return root_fixed_bytes(nl, nz) + 16LL * nz * nz * (long long)nl;
+}
+
+extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, double clip_rel, double* root,
+                                      int* used_eigh, int* num_pos, void* workspace, long long ws_bytes, void* stream) {
+    CB_REQUIRE(cl && root && used_eigh && num_pos && workspace, 1, "root_batched: null argument");
+    CB_REQUIRE(nl >= 1 && nz >= 1, 1, "root_batched: bad sizes nl=%d nz=%d", nl, nz);
+    CB_REQUIRE(ws_bytes >= root_fixed_bytes(nl, nz) + 16LL * nz * nz, 4,
+               "root_batched: workspace too small (%lld B, need >= %lld B)", ws_bytes, root_fixed_bytes(nl, nz) + 16LL * nz * nz);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    auto take = [&](long long bytes) { char* p = ws; ws = (char*)(((uintptr_t)(ws + bytes) + 255) & ~(uintptr_t)255); return p; };
+    double* dmax = (double*)take(8LL * nl);
+    int* fail = (int*)take(4LL * nl);
+    int* fail_list = (int*)take(4LL * nl);
+    int* sweeps = (int*)take(4LL * nl);
+    int* nfail_d = (int*)take(64);
+    double* evals = (double*)take(8LL * nl * nz);
+    int* rank = (int*)take(4LL * nl * nz);
+    double* GV = (double*)ws;
+    long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
+
+    root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    cholesky_kernel<<<nl, CH_THREADS, 0, st>>>(root, nz, fail);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    root_flags_kernel<<<1, 32, 0, st>>>(fail, nl, nz, used_eigh, num_pos, fail_list, nfail_d);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    int nfail = 0;
+    CB_CUDA(cudaMemcpyAsync(&nfail, nfail_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    if (nfail == 0) return 0;
+    CB_REQUIRE(slots >= 1, 4, "root_batched: no workspace for the eigen fallback");
+    const int threads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
+    for (int f0 = 0; f0 < nfail; f0 += (int)slots) {
+        const int nb = (int)std::min<long long>(slots, nfail - f0);
+        double* G = GV;
+        double* V = GV + (long long)nb * nz * nz;
+        jacobi_init_kernel<<<nb, 256, 0, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, G, V);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, fail_list + f0, nz, clip_rel, root, num_pos, evals, rank);
+        count_launch();
+        CB_LAUNCH_CHECK();
+    }
+    return 0;
+}

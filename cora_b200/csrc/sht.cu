@@ -1,0 +1,807 @@
+// Batched inverse spherical-harmonic transform (alm -> HEALPix RING maps) for sm_100a.
+//
+// Replaces the per-channel healpy.alm2map loop of cora/util/hputil.py:500-531 (call sites
+// :388, :420, :427).  Two stages, batched over all frequency channels:
+//
+//   1. sht_legendre_kernel: for every m, F_m(ring, chan) = sum_l lambda_lm(theta_ring) a_lm(chan).
+//      lambda_lm is produced on the fly by a scaled three-term recurrence in registers (one
+//      ring per lane), handed to the FP64 tensor cores (DMMA.8x8x4) through a warp-private
+//      shared-memory tile, and contracted against a cp.async double-buffered alm tile.  North /
+//      south rings share lambda through the (l-m) parity split: two accumulator sets per warp.
+//   2. sht_phase_kernel: per ring, fold m onto m mod nph (exact aliasing of the direct sum),
+//      pair two channels into one complex transform, in-shared-memory power-of-two FFT
+//      (rings with nph = 2^k) or Bluestein chirp-z on a power-of-two FFT (all other rings),
+//      coalesced stores into map[chan][pix].
+//
+// Conventions follow SURVEY.md App. A.7-A.8 / oracle/sht.py.
+#include "common.cuh"
+#include "cora_b200.h"
+
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+namespace cb {
+
+// ------------------------------------------------------------------------------- plan
+struct RingDesc {
+    long long start;      // first pixel of the ring (RING order)
+    int nph;              // pixels in ring
+    int shifted;          // phi0 = pi/nph (1) or 0 (0)
+    int cap;              // index into the per-size Bluestein tables (cap ring number i), or -1
+};
+
+struct PhaseClass {
+    int M, logM, bluestein, P;      // FFT size, pairs per CTA
+    int nrings;
+    int* d_rings;                   // ring indices of this class
+};
+
+struct ShtPlan {
+    int nside, lmax, nrn;           // nrn = 2*nside north rings incl. equator
+    long long npix, nalm;
+    double *d_cth, *d_sth;          // [nrn]
+    double* d_nm_mant;              // [lmax+1]   N_m = mant * 2^exp
+    int* d_nm_exp;                  // [lmax+1]
+    RingDesc* d_rings;              // [4*nside-1]
+    std::vector<RingDesc> h_rings;
+    double2* d_tw;                  // exp(2 pi i j / tw_n), j < tw_n/2
+    int tw_n, log_tw;
+    double2* d_chirp;               // Bluestein chirps  c_k = exp(i pi k^2 / nph), per cap ring
+    double2* d_bhat;                // FFT_M(conj chirp)/M in bit-reversed order, per cap ring
+    long long *d_chirp_off, *d_bhat_off;   // [nside] offsets by cap ring number
+    std::vector<PhaseClass> classes;
+};
+
+static int ilog2(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// ------------------------------------------------------------------ in-smem batched FFT
+// x: [P][M] complex.  In-place radix-2.  DIT: bit-reversed in -> natural out.
+// DIF: natural in -> bit-reversed out.  sign = +1: exp(+2 pi i jk/M).
+template <bool DIT>
+__device__ __forceinline__ void fft_batch(double2* x, int M, int logM, int P, int sign,
+                                          const double2* __restrict__ tw, int log_tw) {
+    const int nb = M >> 1;
+    const int total = P * nb;
+    for (int st = 0; st < logM; st++) {
+        const int s = DIT ? st : (logM - 1 - st);
+        const int h = 1 << s;
+        for (int w = threadIdx.x; w < total; w += blockDim.x) {
+            const int p = w / nb;
+            const int b = w - p * nb;
+            const int q = b & (h - 1);
+            const int i0 = ((b >> s) << (s + 1)) + q;
+            const int i1 = i0 + h;
+            double2 wv = tw[(size_t)q << (log_tw - 1 - s)];
+            if (sign < 0) wv.y = -wv.y;
+            double2* xp = x + (size_t)p * M;
+            double2 u = xp[i0], v = xp[i1];
+            if (DIT) {
+                v = cmul(v, wv);
+                xp[i0] = make_double2(u.x + v.x, u.y + v.y);
+                xp[i1] = make_double2(u.x - v.x, u.y - v.y);
+            } else {
+                xp[i0] = make_double2(u.x + v.x, u.y + v.y);
+                xp[i1] = cmul(make_double2(u.x - v.x, u.y - v.y), wv);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void twiddle_kernel(double2* tw, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n / 2) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)n, &s, &c);
+        tw[j] = make_double2(c, s);
+    }
+}
+
+// chirp c_k = exp(+i pi k^2 / n) with k^2 reduced mod 2n exactly.
+__device__ __forceinline__ double2 chirp_val(long long k, int n) {
+    long long r = (k * k) % (2LL * n);
+    double s, c;
+    sincospi((double)r / (double)n, &s, &c);
+    return make_double2(c, s);
+}
+
+// One CTA per cap ring size: chirp table and bhat = DIF-FFT_M(b)/M with b_d = conj(c_d), d = -(n-1)..(n-1).
+__global__ void bluestein_setup_kernel(int nside, const long long* chirp_off, const long long* bhat_off,
+                                       double2* chirp, double2* bhat, const double2* tw, int log_tw) {
+    extern __shared__ __align__(16) double2 xs[];
+    const int i = blockIdx.x + 1;  // cap ring number
+    const int n = 4 * i;
+    if ((n & (n - 1)) == 0) return;  // power of two: direct FFT, no tables
+    int M = 1, logM = 0;
+    while (M < 2 * n - 1) { M <<= 1; logM++; }
+    for (int k = threadIdx.x; k < M; k += blockDim.x) xs[k] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double2 c = chirp_val(k, n);
+        chirp[chirp_off[i] + k] = c;
+        double2 b = cconj(c);
+        xs[k] = b;
+        if (k > 0) xs[M - k] = b;
+    }
+    __syncthreads();
+    fft_batch<false>(xs, M, logM, 1, -1, tw, log_tw);
+    const double inv = 1.0 / (double)M;
+    for (int k = threadIdx.x; k < M; k += blockDim.x)
+        bhat[bhat_off[i] + k] = make_double2(xs[k].x * inv, xs[k].y * inv);
+}
+
+// --------------------------------------------------------------------- layout transpose
+// healpy-packed channel-major alm[chan][idx] -> panel layout almT[idx][chan_batch].
+__global__ void alm_transpose_kernel(const double2* __restrict__ in, long long in_stride, int nchan,
+                                     long long nalm, double2* __restrict__ out, int out_stride) {
+    __shared__ double2 tile[32][33];
+    const long long i0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r;
+        long long i = i0 + threadIdx.x;
+        if (c < nchan && i < nalm) tile[r][threadIdx.x] = in[(long long)c * in_stride + i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        long long i = i0 + r;
+        int c = c0 + threadIdx.x;
+        if (c < nchan && i < nalm) out[i * out_stride + c] = tile[threadIdx.x][r];
+    }
+}
+
+// ------------------------------------------------------------------------ Legendre stage
+constexpr int LEG_THREADS = 256;
+constexpr int LEG_WARPS = 8;
+constexpr int LEG_RT = 256;   // north rings per CTA (one per thread)
+constexpr int LEG_NCH = 16;   // complex channels per CTA  (32 real columns = 4 n8 blocks)
+constexpr int LEG_KC = 32;    // l's per alm chunk
+constexpr int LEG_ALD = 36;   // As[8][36]: (par*4+t)*36 + ring -> conflict-free LDS.64 per half-warp
+constexpr int LEG_BLD = 34;   // Bs[KC][34]: (2t+par)*34 + col
+
+struct LegParams {
+    const double2* almT;      // [nalm][alm_stride] panel layout (spin 2: the E panel)
+    const double2* almB;      // spin 2 only: the B panel (same strides)
+    long long alm_stride;     // in double2
+    int chan0;                // first channel of this batch inside almT rows
+    int nb;                   // channels in this batch ( = width of F rows)
+    double2* F;               // [4*nside-1][lmax+1][nb]   (spin 2: Q)
+    double2* F2;              // spin 2 only: U
+    const double *cth, *sth;  // [nrn]
+    const double* nm_mant;
+    const int* nm_exp;
+    int nside, lmax, nrn, nrb, ncb, Lpad;
+};
+
+__device__ __forceinline__ void norm_frexp(double& m, long long& e) {
+    int ee;
+    m = frexp(m, &ee);
+    e += ee;
+}
+
+// SPIN = 0: scalar synthesis, 16 complex channels per CTA (32 real GEMM columns).
+// SPIN = 2: (E,B) -> (Q,U) with the HEALPix X1/X2 functions, 8 channels per
+//   CTA; GEMM columns per channel are (Q_re, Q_im, U_re, U_im) and the K dimension is the
+//   concatenation [X1 | X2] against B1 = (aE_re, aE_im, aB_re, aB_im), B2 = (-aB_im, aB_re,
+//   aE_im, -aE_re), so Q = -(X1 aE + i X2 aB), U = -(X1 aB - i X2 aE) accumulate in place.
+//   X2 has the opposite theta-parity of X1, so it feeds the other parity accumulator.
+template <int SPIN>
+__global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams P) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NCH = (SPIN == 0) ? LEG_NCH : LEG_NCH / 2;   // channels per CTA
+    constexpr int AROWS = (SPIN == 0) ? 8 : 16;
+    double* c1 = smem;                         // [Lpad]  a_l
+    double* c2 = c1 + P.Lpad;                  // [Lpad]  a_l / a_{l-1}
+    double* cn = c2 + P.Lpad;                  // [Lpad]  spin 2: 2 n_l
+    double* cg = cn + (SPIN ? P.Lpad : 0);     // [Lpad]  spin 2: 2 n_l g_lm
+    double* Bs = cg + (SPIN ? P.Lpad : 0);     // [2][KC][BLD]
+    double* As = Bs + 2 * LEG_KC * LEG_BLD;    // [WARPS][AROWS][ALD]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bid = blockIdx.x;
+    const int cb = bid % P.ncb; bid /= P.ncb;
+    const int rb = bid % P.nrb;
+    const int m = bid / P.nrb;
+    const int lmax = P.lmax;
+    const int nk = lmax - m + 1;               // number of l's
+
+    // recurrence coefficients for this m:  lam_k = c1[k] x lam_{k-1} - c2[k] lam_{k-2},  k = l - m
+    for (int k = tid; k < P.Lpad; k += LEG_THREADS) {
+        double a = 0.0, r = 0.0;
+        const double l = (double)(m + k), mm = (double)m;
+        if (k >= 1 && k < nk) {
+            a = sqrt((4.0 * l * l - 1.0) / (l * l - mm * mm));
+            if (k >= 2) {
+                double lp = l - 1.0;
+                double ap = sqrt((4.0 * lp * lp - 1.0) / (lp * lp - mm * mm));
+                r = a / ap;
+            }
+        }
+        c1[k] = a;
+        c2[k] = r;
+        if (SPIN) {
+            double tn = 0.0, tg = 0.0;
+            if (k < nk && m + k >= 2) {
+                tn = 2.0 / sqrt((l + 2.0) * (l + 1.0) * l * (l - 1.0));
+                tg = tn * sqrt((2.0 * l + 1.0) / (2.0 * l - 1.0) * (l * l - mm * mm));
+            }
+            cn[k] = tn;
+            cg[k] = tg;
+        }
+    }
+
+    // ring owned by this lane
+    const int rn = rb * LEG_RT + warp * 32 + lane;   // north ring index (ring number rn+1)
+    const bool ring_ok = rn < P.nrn;
+    double x = 0.0, p_cur = 0.0, p_prev = 0.0;
+    double is2 = 0.0, cs2 = 0.0;   // spin 2: 1/sin^2, cos/sin^2
+    int e = -(1 << 20);  // scale exponent (multiple of 256, <= 0); true value = p * 2^e
+    if (ring_ok) {
+        x = P.cth[rn];
+        // seed lambda_mm = (-1)^m N_m sin^m(theta) as (mantissa, exponent)
+        double bm = P.sth[rn];
+        if (SPIN) { is2 = 1.0 / (bm * bm); cs2 = x * is2; }
+        long long be = 0;
+        norm_frexp(bm, be);
+        double rm = 1.0;
+        long long re = 0;
+        int n = m;
+        while (n) {
+            if (n & 1) { rm *= bm; re += be; norm_frexp(rm, re); }
+            bm *= bm; be *= 2; norm_frexp(bm, be);
+            n >>= 1;
+        }
+        rm *= P.nm_mant[m];
+        re += P.nm_exp[m];
+        norm_frexp(rm, re);
+        if (m & 1) rm = -rm;
+        // e = 256*ceil(re/256) clipped to <= 0
+        long long q = (re >= 0) ? 0 : -((-re) / 256);
+        e = (int)(q * 256);
+        long long sh = re - (long long)e;   // in (-256, 0] when e < 0, = re when e == 0
+        p_cur = ldexp(rm, (int)sh);
+    }
+
+    double acc[2][4][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[a][b][c][0] = acc[a][b][c][1] = 0.0;
+
+    // alm chunk loader: rows l = m + kc + j (j < KC); 16 x 16-byte pieces per row
+    const long long row0 = (long long)m * (2 * lmax + 1 - m) / 2 + m;   // idx(l=m, m)
+    const int nchunk = (nk + LEG_KC - 1) / LEG_KC;
+    auto load_chunk = [&](int ck, int buf) {
+#pragma unroll
+        for (int qd = 0; qd < 2; qd++) {
+            int el = tid + qd * LEG_THREADS;
+            int j = el >> 4, c = el & 15;
+            int k = ck * LEG_KC + j;
+            int ch;
+            const double2* base;
+            if (SPIN == 0) { ch = cb * NCH + c; base = P.almT; }
+            else { ch = cb * NCH + (c >> 1); base = (c & 1) ? P.almB : P.almT; }
+            bool ok = (k < nk) && (ch < P.nb);
+            const double2* src = base + (ok ? ((row0 + k) * P.alm_stride + P.chan0 + ch) : 0);
+            cp_async16(Bs + (size_t)buf * LEG_KC * LEG_BLD + j * LEG_BLD + 2 * c, src, ok);
+        }
+        cp_async_commit();
+    };
+
+    double* Aw = As + warp * AROWS * LEG_ALD;
+    load_chunk(0, 0);
+    __syncthreads();   // coefficient arrays visible
+
+    // spin 2: B2 fragment = +-B1 at a permuted column inside each group of four
+    const int gperm = (g & 4) + 3 - (g & 3);
+    const double gsign = ((g & 3) == 0 || (g & 3) == 3) ? -1.0 : 1.0;
+
+    int k = 0;   // next k to emit
+    for (int ck = 0; ck < nchunk; ck++) {
+        const int buf = ck & 1;
+        cp_async_wait<0>();
+        __syncthreads();
+        if (ck + 1 < nchunk) load_chunk(ck + 1, buf ^ 1);
+        const double* Bb = Bs + (size_t)buf * LEG_KC * LEG_BLD;
+#pragma unroll 1
+        for (int grp = 0; grp < LEG_KC / 8; grp++) {
+            // ---- 8 recurrence steps, emit into the warp-private tile (parity-split rows)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool live = (e == 0);
+                const int arow = (j & 1) * 4 + (j >> 1);
+                if (SPIN == 0) {
+                    Aw[arow * LEG_ALD + lane] = live ? p_cur : 0.0;
+                } else {
+                    const double l = (double)(m + k), mm = (double)m;
+                    const double tn = cn[k], tg = cg[k];
+                    const double al = tn * (l - mm * mm), be = 0.5 * tn * l * (l - 1.0), de = tn * mm * (l - 1.0);
+                    const double x1 = -(al * is2 + be) * p_cur + tg * cs2 * p_prev;
+                    const double x2 = -de * cs2 * p_cur + mm * tg * is2 * p_prev;
+                    Aw[arow * LEG_ALD + lane] = live ? x1 : 0.0;
+                    Aw[(8 + arow) * LEG_ALD + lane] = live ? x2 : 0.0;
+                }
+                double cc1 = c1[k + 1], cc2 = c2[k + 1];
+                double pn = fma(cc1 * x, p_cur, -cc2 * p_prev);
+                p_prev = p_cur;
+                p_cur = pn;
+                if (e < 0 && fabs(p_cur) > 0x1p128) {
+                    p_cur *= 0x1p-256;
+                    p_prev *= 0x1p-256;
+                    e += 256;
+                }
+                k++;
+            }
+            const bool active = __any_sync(0xffffffffu, e == 0);
+            __syncwarp();
+            if (active) {
+#pragma unroll
+                for (int par = 0; par < 2; par++) {
+                    double af[4], bf[4];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++) af[mb] = Aw[(par * 4 + t) * LEG_ALD + 8 * mb + g];
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) bf[nb] = Bb[(grp * 8 + 2 * t + par) * LEG_BLD + 8 * nb + g];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                        for (int nb = 0; nb < 4; nb++)
+                            dmma884(acc[par][mb][nb][0], acc[par][mb][nb][1], af[mb], bf[nb]);
+                    if (SPIN) {
+                        // X2 rows of l-parity `par` have theta-parity 1-par
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++) af[mb] = Aw[(8 + par * 4 + t) * LEG_ALD + 8 * mb + g];
+#pragma unroll
+                        for (int nb = 0; nb < 4; nb++)
+                            bf[nb] = gsign * Bb[(grp * 8 + 2 * t + par) * LEG_BLD + 8 * nb + gperm];
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++)
+                                dmma884(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[mb], bf[nb]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: north = even + odd, south = even - odd;  F[ring][m][chan]
+    const int L = lmax + 1;
+    const int nring_tot = 4 * P.nside - 1;
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++) {
+        const int rr = rb * LEG_RT + warp * 32 + 8 * mb + g;   // north ring index
+        if (rr >= P.nrn) continue;
+        const int r_n = rr;                       // ring array index of the north ring
+        const int r_s = nring_tot - 1 - rr;       // mirror ring
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            double er = acc[0][mb][nb][0], ei = acc[0][mb][nb][1];
+            double orr = acc[1][mb][nb][0], oi = acc[1][mb][nb][1];
+            if (SPIN == 0) {
+                const int ch = cb * NCH + 4 * nb + t;
+                if (ch >= P.nb) continue;
+                P.F[((long long)r_n * L + m) * P.nb + ch] = make_double2(er + orr, ei + oi);
+                if (r_s != r_n) P.F[((long long)r_s * L + m) * P.nb + ch] = make_double2(er - orr, ei - oi);
+            } else {
+                const int ch = cb * NCH + 2 * nb + (t >> 1);
+                if (ch >= P.nb) continue;
+                double2* Fo = (t & 1) ? P.F2 : P.F;   // even t: Q, odd t: U
+                Fo[((long long)r_n * L + m) * P.nb + ch] = make_double2(-(er + orr), -(ei + oi));
+                if (r_s != r_n) Fo[((long long)r_s * L + m) * P.nb + ch] = make_double2(-(er - orr), -(ei - oi));
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- phase stage
+struct PhaseParams {
+    const double2* F;        // [nring][L][nb]
+    double* map;             // [nchan][npix] (pointer already offset to the batch's first channel)
+    long long npix;
+    const RingDesc* rings;
+    const int* ring_list;
+    const double2* tw;
+    const double2* chirp;
+    const double2* bhat;
+    const long long *chirp_off, *bhat_off;
+    int lmax, nb, M, logM, P, bluestein, log_tw;
+};
+
+__device__ __forceinline__ int bitrev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - bits)); }
+
+__global__ void __launch_bounds__(256) sht_phase_kernel(PhaseParams Q) {
+    extern __shared__ __align__(16) double2 xs[];   // [P][M]
+    const int r = Q.ring_list[blockIdx.x];
+    const RingDesc rd = Q.rings[r];
+    const int n = rd.nph, M = Q.M, Pp = Q.P;
+    const int c0 = blockIdx.y * 2 * Pp;
+    const int L = Q.lmax + 1;
+    const double2* Fr = Q.F + (long long)r * L * Q.nb;
+    const int half = n >> 1;
+    const double2* chirp = Q.bluestein ? Q.chirp + Q.chirp_off[rd.cap] : nullptr;
+
+    if (Q.bluestein) {
+        for (int w = threadIdx.x; w < Pp * (M - n); w += blockDim.x) {
+            int p = w / (M - n), k = n + (w - p * (M - n));
+            xs[(size_t)p * M + k] = make_double2(0.0, 0.0);
+        }
+    }
+    // ---- fold m -> m mod nph, Hermitian part, two channels per complex series
+    for (int w = threadIdx.x; w < (half + 1) * Pp; w += blockDim.x) {
+        const int pair = w % Pp, k = w / Pp;
+        const int ch = c0 + 2 * pair;
+        const bool has1 = ch < Q.nb, has2 = ch + 1 < Q.nb;
+        double2 a1 = make_double2(0, 0), a2 = a1, b1 = a1, b2 = a1;
+        if (has1) {
+            double sg = 1.0;
+            for (int m = k; m <= Q.lmax; m += n) {
+                const double wgt = (m == 0) ? 1.0 : 2.0;
+                double2 f1 = Fr[(long long)m * Q.nb + ch];
+                double2 f2 = has2 ? Fr[(long long)m * Q.nb + ch + 1] : make_double2(0, 0);
+                if (m == 0) { f1.y = 0.0; f2.y = 0.0; }
+                const double s = sg * wgt;
+                a1.x += s * f1.x; a1.y += s * f1.y;
+                a2.x += s * f2.x; a2.y += s * f2.y;
+                if (rd.shifted) sg = -sg;
+            }
+            const int kk = n - k;
+            if (k != 0 && kk != k) {
+                sg = 1.0;
+                for (int m = kk; m <= Q.lmax; m += n) {
+                    double2 f1 = Fr[(long long)m * Q.nb + ch];
+                    double2 f2 = has2 ? Fr[(long long)m * Q.nb + ch + 1] : make_double2(0, 0);
+                    const double s = sg * 2.0;
+                    b1.x += s * f1.x; b1.y += s * f1.y;
+                    b2.x += s * f2.x; b2.y += s * f2.y;
+                    if (rd.shifted) sg = -sg;
+                }
+                if (rd.shifted) {
+                    // e^{i pi k/n} on bin k;  e^{i pi (n-k)/n} = -conj(e^{i pi k/n}) on bin n-k
+                    double sn, cs;
+                    sincospi((double)k / (double)n, &sn, &cs);
+                    const double2 ph = make_double2(cs, sn), phb = make_double2(-cs, sn);
+                    a1 = cmul(a1, ph); a2 = cmul(a2, ph);
+                    b1 = cmul(b1, phb); b2 = cmul(b2, phb);
+                }
+            } else {
+                if (rd.shifted && k != 0) {   // k == n/2: phase e^{i pi/2} = i
+                    a1 = make_double2(-a1.y, a1.x);
+                    a2 = make_double2(-a2.y, a2.x);
+                }
+                b1 = a1; b2 = a2;
+            }
+        }
+        // H = (G_k + conj(G_{n-k}))/2
+        const double2 h1 = make_double2(0.5 * (a1.x + b1.x), 0.5 * (a1.y - b1.y));
+        const double2 h2 = make_double2(0.5 * (a2.x + b2.x), 0.5 * (a2.y - b2.y));
+        double2 zk = make_double2(h1.x - h2.y, h1.y + h2.x);
+        double2 zn = make_double2(h1.x + h2.y, -h1.y + h2.x);
+        double2* xp = xs + (size_t)pair * M;
+        const int kk = n - k;
+        if (Q.bluestein) {
+            xp[k] = cmul(zk, chirp[k]);
+            if (k != 0 && kk != k) xp[kk] = cmul(zn, chirp[kk]);
+        } else {
+            xp[bitrev(k, Q.logM)] = zk;
+            if (k != 0 && kk != k) xp[bitrev(kk, Q.logM)] = zn;
+        }
+    }
+    __syncthreads();
+
+    if (Q.bluestein) {
+        fft_batch<false>(xs, M, Q.logM, Pp, -1, Q.tw, Q.log_tw);
+        const double2* bh = Q.bhat + Q.bhat_off[rd.cap];
+        for (int w = threadIdx.x; w < Pp * M; w += blockDim.x) {
+            int k = w % M;
+            xs[w] = cmul(xs[w], bh[k]);
+        }
+        __syncthreads();
+        fft_batch<true>(xs, M, Q.logM, Pp, +1, Q.tw, Q.log_tw);
+    } else {
+        fft_batch<true>(xs, M, Q.logM, Pp, +1, Q.tw, Q.log_tw);
+    }
+
+    // ---- store: real part -> first channel of the pair, imaginary part -> second
+    for (int w = threadIdx.x; w < n * Pp; w += blockDim.x) {
+        const int pair = w / n, j = w - pair * n;
+        const int ch = c0 + 2 * pair;
+        if (ch >= Q.nb) continue;
+        double2 v = xs[(size_t)pair * M + j];
+        if (Q.bluestein) v = cmul(v, chirp[j]);
+        Q.map[(long long)ch * Q.npix + rd.start + j] = v.x;
+        if (ch + 1 < Q.nb) Q.map[(long long)(ch + 1) * Q.npix + rd.start + j] = v.y;
+    }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+// =============================================================================== C ABI
+extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
+    CB_REQUIRE(nside >= 1 && lmax >= 0 && plan_out, 1, "sht_plan_create: bad arguments (nside=%d lmax=%d)", nside, lmax);
+    ShtPlan* pl = new ShtPlan();
+    pl->nside = nside; pl->lmax = lmax; pl->nrn = 2 * nside;
+    pl->npix = 12LL * nside * nside;
+    pl->nalm = (long long)(lmax + 1) * (lmax + 2) / 2;
+    const int nring = 4 * nside - 1;
+
+    // ring geometry
+    std::vector<double> cth(pl->nrn), sth(pl->nrn);
+    pl->h_rings.resize(nring);
+    const double nf = (double)nside;
+    for (int i = 1; i <= 2 * nside; i++) {
+        double c, s;
+        if (i < nside) {
+            double om = (double)i * (double)i / (3.0 * nf * nf);   // 1 - cos(theta)
+            c = 1.0 - om;
+            s = std::sqrt(om * (1.0 + c));
+        } else {
+            c = 4.0 / 3.0 - 2.0 * (double)i / (3.0 * nf);
+            s = std::sqrt((1.0 - c) * (1.0 + c));
+        }
+        cth[i - 1] = c; sth[i - 1] = s;
+    }
+    for (int i = 1; i <= nring; i++) {
+        int north = std::min(i, 4 * nside - i);
+        bool cap = north < nside;
+        RingDesc rd;
+        rd.nph = cap ? 4 * north : 4 * nside;
+        rd.shifted = (cap || (((north - nside) & 1) == 0)) ? 1 : 0;
+        rd.cap = cap ? north : -1;
+        if (i <= 2 * nside || !cap) {
+            rd.start = cap ? 2LL * north * (north - 1) : 2LL * nside * (nside - 1) + 4LL * nside * (i - nside);
+        } else {
+            rd.start = pl->npix - 2LL * north * (north + 1);
+        }
+        pl->h_rings[i - 1] = rd;
+    }
+
+    // N_m = sqrt((2m+1)/(4 pi) prod_{k<=m} (2k-1)/(2k)) as mantissa/exponent, long double product
+    std::vector<double> nm_mant(lmax + 1);
+    std::vector<int> nm_exp(lmax + 1);
+    {
+        long double pm = 1.0L; long long pe = 0;
+        const long double four_pi = 4.0L * 3.14159265358979323846264338327950288L;
+        for (int m = 0; m <= lmax; m++) {
+            if (m > 0) {
+                pm *= (long double)(2 * m - 1) / (long double)(2 * m);
+                int ee; pm = frexpl(pm, &ee); pe += ee;
+            }
+            long double v = pm * (long double)(2 * m + 1) / four_pi;
+            long long ve = pe; int ee;
+            v = frexpl(v, &ee); ve += ee;
+            if (ve & 1) { v *= 2.0L; ve -= 1; }
+            long double sq = sqrtl(v);
+            long long se = ve / 2;
+            sq = frexpl(sq, &ee); se += ee;
+            nm_mant[m] = (double)sq; nm_exp[m] = (int)se;
+        }
+    }
+
+    CB_CUDA(cudaMalloc(&pl->d_cth, sizeof(double) * pl->nrn));
+    CB_CUDA(cudaMalloc(&pl->d_sth, sizeof(double) * pl->nrn));
+    CB_CUDA(cudaMalloc(&pl->d_nm_mant, sizeof(double) * (lmax + 1)));
+    CB_CUDA(cudaMalloc(&pl->d_nm_exp, sizeof(int) * (lmax + 1)));
+    CB_CUDA(cudaMalloc(&pl->d_rings, sizeof(RingDesc) * nring));
+    CB_CUDA(cudaMemcpy(pl->d_cth, cth.data(), sizeof(double) * pl->nrn, cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(pl->d_sth, sth.data(), sizeof(double) * pl->nrn, cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(pl->d_nm_mant, nm_mant.data(), sizeof(double) * (lmax + 1), cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(pl->d_nm_exp, nm_exp.data(), sizeof(int) * (lmax + 1), cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(pl->d_rings, pl->h_rings.data(), sizeof(RingDesc) * nring, cudaMemcpyHostToDevice));
+
+    // FFT classes
+    int maxM = 4;
+    std::vector<long long> chirp_off(nside + 1, 0), bhat_off(nside + 1, 0);
+    long long nchirp = 0, nbhat = 0;
+    for (int i = 1; i < nside; i++) {
+        int n = 4 * i;
+        if (is_pow2(n)) { maxM = std::max(maxM, n); continue; }
+        int M = 1; while (M < 2 * n - 1) M <<= 1;
+        chirp_off[i] = nchirp; nchirp += n;
+        bhat_off[i] = nbhat; nbhat += M;
+        maxM = std::max(maxM, M);
+    }
+    maxM = std::max(maxM, 4 * nside);
+    int belt_M = 4 * nside;
+    bool belt_pow2 = is_pow2(belt_M);
+    // a non-power-of-two nside makes the belt rings Bluestein rings too: give them table slot `nside`
+    if (!belt_pow2) {
+        int n = belt_M; int M = 1; while (M < 2 * n - 1) M <<= 1;
+        chirp_off[nside] = nchirp; nchirp += n;
+        bhat_off[nside] = nbhat; nbhat += M;
+        maxM = std::max(maxM, M);
+        for (auto& rd : pl->h_rings) if (rd.cap < 0) rd.cap = nside;
+        CB_CUDA(cudaMemcpy(pl->d_rings, pl->h_rings.data(), sizeof(RingDesc) * nring, cudaMemcpyHostToDevice));
+    }
+    CB_REQUIRE(maxM <= 8192, 2, "sht_plan_create: ring FFT size %d exceeds the 8192-point shared-memory FFT (nside too large)", maxM);
+    pl->tw_n = maxM; pl->log_tw = ilog2(maxM);
+    CB_CUDA(cudaMalloc(&pl->d_tw, sizeof(double2) * std::max(1, maxM / 2)));
+    twiddle_kernel<<<ceil_div(maxM / 2, 256), 256>>>(pl->d_tw, maxM); count_launch();
+    CB_LAUNCH_CHECK();
+    CB_CUDA(cudaMalloc(&pl->d_chirp, sizeof(double2) * std::max(1LL, nchirp)));
+    CB_CUDA(cudaMalloc(&pl->d_bhat, sizeof(double2) * std::max(1LL, nbhat)));
+    CB_CUDA(cudaMalloc(&pl->d_chirp_off, sizeof(long long) * (nside + 1)));
+    CB_CUDA(cudaMalloc(&pl->d_bhat_off, sizeof(long long) * (nside + 1)));
+    CB_CUDA(cudaMemcpy(pl->d_chirp_off, chirp_off.data(), sizeof(long long) * (nside + 1), cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(pl->d_bhat_off, bhat_off.data(), sizeof(long long) * (nside + 1), cudaMemcpyHostToDevice));
+    if (nbhat > 0) {
+        CB_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+        bluestein_setup_kernel<<<nside, 256, (size_t)maxM * 16>>>(nside, pl->d_chirp_off, pl->d_bhat_off, pl->d_chirp,
+                                                                  pl->d_bhat, pl->d_tw, pl->log_tw);
+        count_launch();
+        CB_LAUNCH_CHECK();
+    }
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+
+    // group rings into (bluestein, M) classes
+    std::vector<std::vector<int>> byclass(2 * 16);
+    for (int r = 0; r < nring; r++) {
+        int n = pl->h_rings[r].nph;
+        int bl = is_pow2(n) ? 0 : 1;
+        int M = n; if (bl) { M = 1; while (M < 2 * n - 1) M <<= 1; }
+        byclass[bl * 16 + ilog2(M)].push_back(r);
+    }
+    for (int bl = 0; bl < 2; bl++)
+        for (int lg = 0; lg < 16; lg++) {
+            auto& v = byclass[bl * 16 + lg];
+            if (v.empty()) continue;
+            PhaseClass pc;
+            pc.M = 1 << lg; pc.logM = lg; pc.bluestein = bl; pc.nrings = (int)v.size();
+            pc.P = std::max(1, std::min(8, 4096 / pc.M));
+            CB_CUDA(cudaMalloc(&pc.d_rings, sizeof(int) * v.size()));
+            CB_CUDA(cudaMemcpy(pc.d_rings, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
+            pl->classes.push_back(pc);
+        }
+    CB_CUDA(cudaDeviceSynchronize());
+    *plan_out = pl;
+    return 0;
+}
+
+extern "C" int cora_b200_sht_plan_destroy(void* plan) {
+    if (!plan) return 0;
+    ShtPlan* pl = (ShtPlan*)plan;
+    cudaFree(pl->d_cth); cudaFree(pl->d_sth); cudaFree(pl->d_nm_mant); cudaFree(pl->d_nm_exp);
+    cudaFree(pl->d_rings); cudaFree(pl->d_tw); cudaFree(pl->d_chirp); cudaFree(pl->d_bhat);
+    cudaFree(pl->d_chirp_off); cudaFree(pl->d_bhat_off);
+    for (auto& pc : pl->classes) cudaFree(pc.d_rings);
+    delete pl;
+    return 0;
+}
+
+// bytes of workspace needed per channel of a batch
+static long long ws_per_chan(const ShtPlan* pl, int layout) {
+    long long f = (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16;
+    long long a = (layout == CORA_B200_ALM_PACKED) ? pl->nalm * 16 : 0;
+    return f + a;
+}
+
+extern "C" long long cora_b200_alm2map_workspace_bytes(void* plan, int layout, int nchan_batch) {
+    if (!plan) return -1;
+    return ws_per_chan((ShtPlan*)plan, layout) * (long long)nchan_batch + 256;
+}
+
+template <int SPIN>
+static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* almB, long long alm_stride, int chan0, int nb,
+                        double2* F, double2* F2, cudaStream_t st) {
+    LegParams P;
+    P.almT = almT; P.almB = almB; P.alm_stride = alm_stride; P.chan0 = chan0; P.nb = nb; P.F = F; P.F2 = F2;
+    P.cth = pl->d_cth; P.sth = pl->d_sth; P.nm_mant = pl->d_nm_mant; P.nm_exp = pl->d_nm_exp;
+    P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
+    P.nrb = ceil_div(pl->nrn, LEG_RT);
+    P.ncb = ceil_div(nb, SPIN ? LEG_NCH / 2 : LEG_NCH);
+    P.Lpad = ((pl->lmax + 1 + LEG_KC) / LEG_KC + 1) * LEG_KC + 8;
+    size_t smem = sizeof(double) * ((SPIN ? 4 : 2) * (size_t)P.Lpad + 2 * LEG_KC * LEG_BLD + LEG_WARPS * (SPIN ? 16 : 8) * LEG_ALD);
+    CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
+    CB_CUDA(cudaFuncSetAttribute(sht_legendre_kernel<SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
+    CB_REQUIRE(grid < 2147483647LL, 3, "alm2map: Legendre grid too large (%lld)", grid);
+    sht_legendre_kernel<SPIN><<<(unsigned)grid, LEG_THREADS, smem, st>>>(P);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, cudaStream_t st) {
+    for (const auto& pc : pl->classes) {
+        PhaseParams Q;
+        Q.F = F; Q.map = map; Q.npix = pl->npix; Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
+        Q.tw = pl->d_tw; Q.chirp = pl->d_chirp; Q.bhat = pl->d_bhat;
+        Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
+        Q.lmax = pl->lmax; Q.nb = nb; Q.M = pc.M; Q.logM = pc.logM; Q.bluestein = pc.bluestein; Q.log_tw = pl->log_tw;
+        int npairs = (nb + 1) / 2;
+        Q.P = std::min(pc.P, npairs);
+        dim3 grid(pc.nrings, ceil_div(npairs, Q.P));
+        size_t smem = (size_t)Q.P * pc.M * 16;
+        sht_phase_kernel<<<grid, 256, smem, st>>>(Q);
+        count_launch();
+        CB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int cora_b200_alm2map(void* plan, const void* alm, int layout, long long alm_stride, int nchan, double* map,
+                                 void* workspace, long long ws_bytes, void* stream) {
+    CB_REQUIRE(plan && alm && map && workspace, 1, "alm2map: null argument");
+    CB_REQUIRE(layout == CORA_B200_ALM_PACKED || layout == CORA_B200_ALM_PANEL, 1, "alm2map: unknown alm layout %d", layout);
+    CB_REQUIRE(nchan >= 1, 1, "alm2map: nchan must be >= 1");
+    ShtPlan* pl = (ShtPlan*)plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long per = ws_per_chan(pl, layout);
+    long long cap = (ws_bytes - 256) / per;
+    CB_REQUIRE(cap >= 1, 4, "alm2map: workspace too small (%lld B; need %lld B per channel)", ws_bytes, per);
+    int nbmax = (int)std::min<long long>(cap, nchan);
+    if (nbmax >= 16) nbmax -= nbmax % 16; else if (nbmax >= 2) nbmax -= nbmax % 2;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    for (int c0 = 0; c0 < nchan; c0 += nbmax) {
+        int nb = std::min(nbmax, nchan - c0);
+        double2* F = (double2*)ws;
+        const double2* almT; long long stride; int chan0;
+        if (layout == CORA_B200_ALM_PACKED) {
+            double2* T = (double2*)(ws + (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16 * nbmax);
+            dim3 grid(ceil_div(pl->nalm, 32), ceil_div(nb, 32));
+            alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)alm + (long long)c0 * alm_stride, alm_stride, nb,
+                                                                pl->nalm, T, nb);
+            count_launch();
+            CB_LAUNCH_CHECK();
+            almT = T; stride = nb; chan0 = 0;
+        } else {
+            almT = (const double2*)alm; stride = alm_stride; chan0 = c0;
+        }
+        int rc = run_legendre<0>(pl, almT, nullptr, stride, chan0, nb, F, nullptr, st);
+        if (rc) return rc;
+        rc = run_phase(pl, F, nb, map + (long long)c0 * pl->npix, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int cora_b200_alm2map_spin2(void* plan, const void* almE, const void* almB, int layout, long long alm_stride, int nchan,
+                                       double* mapQ, double* mapU, void* workspace, long long ws_bytes, void* stream) {
+    CB_REQUIRE(plan && almE && almB && mapQ && mapU && workspace, 1, "alm2map_spin2: null argument");
+    CB_REQUIRE(layout == CORA_B200_ALM_PACKED || layout == CORA_B200_ALM_PANEL, 1, "alm2map_spin2: unknown alm layout %d", layout);
+    CB_REQUIRE(nchan >= 1, 1, "alm2map_spin2: nchan must be >= 1");
+    ShtPlan* pl = (ShtPlan*)plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long fbytes = (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16;
+    const long long per = 2 * fbytes + ((layout == CORA_B200_ALM_PACKED) ? 2 * pl->nalm * 16 : 0);
+    long long cap = (ws_bytes - 256) / per;
+    CB_REQUIRE(cap >= 1, 4, "alm2map_spin2: workspace too small (%lld B; need %lld B per channel)", ws_bytes, per);
+    int nbmax = (int)std::min<long long>(cap, nchan);
+    if (nbmax >= 8) nbmax -= nbmax % 8; else if (nbmax >= 2) nbmax -= nbmax % 2;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    for (int c0 = 0; c0 < nchan; c0 += nbmax) {
+        int nb = std::min(nbmax, nchan - c0);
+        double2* FQ = (double2*)ws;
+        double2* FU = (double2*)(ws + fbytes * nbmax);
+        const double2 *pE, *pB; long long stride; int chan0;
+        if (layout == CORA_B200_ALM_PACKED) {
+            double2* TE = (double2*)(ws + 2 * fbytes * nbmax);
+            double2* TB = TE + pl->nalm * nbmax;
+            dim3 grid(ceil_div(pl->nalm, 32), ceil_div(nb, 32));
+            alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)almE + (long long)c0 * alm_stride, alm_stride, nb,
+                                                                pl->nalm, TE, nb);
+            alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)almB + (long long)c0 * alm_stride, alm_stride, nb,
+                                                                pl->nalm, TB, nb);
+            count_launch(2);
+            CB_LAUNCH_CHECK();
+            pE = TE; pB = TB; stride = nb; chan0 = 0;
+        } else {
+            pE = (const double2*)almE; pB = (const double2*)almB; stride = alm_stride; chan0 = c0;
+        }
+        int rc = run_legendre<2>(pl, pE, pB, stride, chan0, nb, FQ, FU, st);
+        if (rc) return rc;
+        rc = run_phase(pl, FQ, nb, mapQ + (long long)c0 * pl->npix, st);
+        if (rc) return rc;
+        rc = run_phase(pl, FU, nb, mapU + (long long)c0 * pl->npix, st);
+        if (rc) return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,126 @@
+"""Drivers of record for the path: ``cora-makesky 21cm`` and ``cora-makesky gaussianfg``.
+
+Mirrors ``cora/scripts/makesky.py``: ``FreqState`` (``:44-92``), the ``21cm`` command
+(``:313-344``) and the ``gaussianfg`` command (``:347-390``).  The click CLI and the HDF5 writer
+(``write_map``, ``:412-450``; h5py is not available here) are outside the hot path; the functions
+below return the ``(nfreq, npol, npix)`` arrays the commands would write.
+
+    python -m cora_b200.makesky 21cm --nside 64 --freq 800 400 32 --pol none out.npy
+"""
+
+import numpy as np
+
+
+class FreqState(object):
+    """Process and store the frequency spec (``makesky.py:44-92``)."""
+
+    def __init__(self):
+        self.freq = (800.0, 400.0, 1025)
+        self.channel_range = None
+        self.channel_list = None
+        self.channel_bin = 1
+        self.freq_mode = "centre"
+
+    @property
+    def frequencies(self):
+        """The frequency centres in MHz."""
+        return self._calculate()[0]
+
+    @property
+    def freq_width(self):
+        """The frequency width in MHz."""
+        return self._calculate()[1]
+
+    def _calculate(self):
+        sf, ef, nf = self.freq
+        if self.freq_mode == "centre":
+            df = abs(ef - sf) / nf
+            frequencies = np.linspace(sf, ef, nf, endpoint=False)
+        elif self.freq_mode == "centre_nyquist":
+            df = abs((ef - sf) / (nf - 1))
+            frequencies = np.linspace(sf, ef, nf, endpoint=True)
+        else:
+            df = (ef - sf) / nf
+            frequencies = sf + df * (np.arange(nf) + 0.5)
+        if self.channel_bin > 1:
+            frequencies = frequencies.reshape(-1, self.channel_bin).mean(axis=1)
+            df = df * self.channel_bin
+        if self.channel_list is not None:
+            frequencies = frequencies[self.channel_list]
+        elif self.channel_range is not None:
+            frequencies = frequencies[self.channel_range[0] : self.channel_range[1]]
+        return frequencies, df
+
+
+def make_21cm(fstate, nside, pol="full", eor=False, oversample=None):
+    """Gaussian simulation of the unresolved 21cm background (``makesky.py:325-344``).
+
+    Returns ``float64[nfreq, npix]`` for ``pol == "none"``/``"zero"`` or ``[nfreq, 4, npix]``
+    (Q = U = V = 0) for ``pol == "full"``."""
+    from . import corr21cm
+
+    cr = corr21cm.EoR21cm() if eor else corr21cm.Corr21cm()
+    cr.nside = nside
+    cr.frequencies = fstate.frequencies
+    cr.oversample = oversample if oversample is not None else 3
+    return cr.getpolsky() if pol == "full" else cr.getsky()
+
+
+def make_gaussianfg(fstate, nside, pol="full", rng=None, seed=None):
+    """Full-sky Gaussian random field for synchrotron emission (``makesky.py:349-390``).
+
+    The polarised case builds the block-diagonal ``(npol*nfreq)^2`` covariance exactly as the
+    reference does (T = FullSkySynchrotron, E = B = FullSkyPolarisedSynchrotron, V = 0,
+    ``lmax = 3*nside``) so that the global jitter / eigenvalue clip of the root acts on the whole
+    matrix.  Returns ``float64[nfreq, npol, npix]``."""
+    from . import _dev, galaxy, hputil, skysim
+
+    t = _dev.torch()
+    fsyn = galaxy.FullSkySynchrotron()
+    fpol = galaxy.FullSkyPolarisedSynchrotron()
+    fsyn.frequencies = fstate.frequencies
+    nfreq = len(fsyn.frequencies)
+    lmax = 3 * nside
+    npol = 4 if pol == "full" else 1
+
+    cv_fg = _dev.zeros((lmax + 1, npol, nfreq, npol, nfreq), t.float64)
+    cv_fg[:, 0, :, 0, :] = skysim.clarray(fsyn.angular_powerspectrum, lmax, fsyn.nu_pixels, device_out=True)
+    if pol == "full":
+        cpol = skysim.clarray(fpol.angular_powerspectrum, lmax, fsyn.nu_pixels, device_out=True)
+        cv_fg[:, 1, :, 1, :] = cpol
+        cv_fg[:, 2, :, 2, :] = cpol
+    cv_fg = cv_fg.reshape(lmax + 1, npol * nfreq, npol * nfreq)
+
+    alms = skysim.mkfullsky(cv_fg, nside, alms=True, rng=rng, seed=seed, device_out=True)
+    alms = alms.reshape(npol, nfreq, lmax + 1, lmax + 1).permute(1, 0, 2, 3).contiguous()
+    return hputil.sphtrans_inv_sky(alms, nside)
+
+
+def main(argv=None):
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="cora_b200.makesky", description=__doc__.split("\n")[0])
+    ap.add_argument("command", choices=["21cm", "gaussianfg"])
+    ap.add_argument("--nside", type=int, default=128)
+    ap.add_argument("--freq", type=float, nargs=3, default=(800.0, 400.0, 1024), metavar=("START", "STOP", "NUM"))
+    ap.add_argument("--freq-mode", choices=["centre", "centre_nyquist", "edge"], default="centre")
+    ap.add_argument("--pol", choices=["full", "zero", "none"], default="full")
+    ap.add_argument("--eor", action="store_true")
+    ap.add_argument("--oversample", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("filename")
+    a = ap.parse_args(argv)
+    fs = FreqState()
+    fs.freq = (a.freq[0], a.freq[1], int(a.freq[2]))
+    fs.freq_mode = a.freq_mode
+    if a.seed is not None:
+        np.random.seed(a.seed)
+    if a.command == "21cm":
+        m = make_21cm(fs, a.nside, a.pol, a.eor, a.oversample)
+    else:
+        m = make_gaussianfg(fs, a.nside, a.pol, seed=a.seed)
+    np.save(a.filename, m)
+
+
+if __name__ == "__main__":
+    main()

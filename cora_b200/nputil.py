@@ -1,0 +1,80 @@
+"""numpy-facing helpers of the path (mirrors ``cora/util/nputil.py:51-125``), computed on the GPU."""
+
+import ctypes
+
+import numpy as np
+
+from . import _dev, _lib
+
+
+def root_batched_device(cl_dev, jitter_rel=0.0, clip_rel=1e-16, stream=None):
+    """Batched root on device: ``cl_dev`` CUDA float64 [nl, nz, nz] -> (root, used_eigh, num_pos).
+
+    Semantics of ``skysim.py:116-119`` + ``nputil.py:51-101`` (``truncate=False``): jitter on the
+    diagonal, Cholesky, eigen-decomposition with clipping where Cholesky meets a non-positive pivot.
+    """
+    t = _dev.torch()
+    nl, nz = int(cl_dev.shape[0]), int(cl_dev.shape[1])
+    root = _dev.empty((nl, nz, nz), t.float64)
+    used = _dev.empty((nl,), t.int32)
+    npos = _dev.empty((nl,), t.int32)
+    lib = _lib.load()
+    full = lib.cora_b200_root_workspace_bytes(nl, nz)
+    one = lib.cora_b200_root_workspace_bytes(nl, nz) - 16 * nz * nz * (nl - 1)
+    nbytes = min(full, max(one, _dev.free_bytes() - (2 << 30)))
+    ws = _dev.workspace(nbytes)
+    _lib.call("cora_b200_root_batched", _lib.ptr(cl_dev), nl, nz, float(jitter_rel), float(clip_rel), _lib.ptr(root),
+              _lib.ptr(used), _lib.ptr(npos), _lib.ptr(ws), int(nbytes), _lib.stream_ptr(stream))
+    return root, used, npos
+
+
+def matrix_root_manynull(mat, threshold=1e-16, truncate=True):
+    """Square root a matrix: Cholesky, else eigen-decomposition with small/negative eigenvalues
+    set to zero (``nputil.py:51-101``).  Returns ``root`` or ``(root, num_pos)`` if ``truncate``.
+
+    The eigen branch returns columns in ascending-eigenvalue order; with ``truncate`` only the
+    last ``num_pos`` columns are kept and -- reference quirk preserved -- the array then has
+    shape ``(1, N, num_pos)`` (``nputil.py:92-96``).
+    """
+    t = _dev.torch()
+    mat = np.asarray(mat, dtype=np.float64)
+    cl = _dev.to_device(mat[np.newaxis], t.float64)
+    root, used, npos = root_batched_device(cl, 0.0, threshold)
+    r = root[0].cpu().numpy()
+    eigh = bool(used[0].item())
+    num_pos = int(npos[0].item()) if eigh else mat.shape[0]
+    if not truncate:
+        return r
+    if eigh:
+        r = r[:, -num_pos:][np.newaxis] if num_pos else r[np.newaxis]
+    return r, num_pos
+
+
+def complex_std_normal(shape, rng=None, seed=None):
+    """Complex standard normal variates ``(N(0,1) + i N(0,1)) / sqrt(2)`` (``nputil.py:104-125``).
+
+    With ``rng`` (a numpy Generator) the caller's stream is consumed exactly as the reference
+    does -- real block, then imaginary block -- which is the identical-draw parity path.  With
+    ``rng=None`` the variates come from the device Philox4x32-10 generator (``seed`` or a seed
+    taken from numpy's legacy global state, which is what the reference would have consumed).
+    """
+    if rng is not None:
+        return (rng.standard_normal(shape) + 1.0j * rng.standard_normal(shape)) / 2**0.5
+    t = _dev.torch()
+    shape = tuple(np.atleast_1d(shape).astype(int))
+    n = int(np.prod(shape))
+    if seed is None:
+        seed = int(np.random.randint(0, 2**31 - 1))
+    # one "l" with a 1 x 1 identity root: alm[idx(l=n-1, m)] = g[m]
+    lmax = n - 1
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    panel = _dev.zeros((nalm, 1), t.complex128)
+    root = _dev.to_device(np.ones((1, 1, 1)), t.float64)
+    llist = np.array([lmax], dtype=np.int32)
+    nbytes = _lib.load().cora_b200_draw_apply_workspace_bytes(1, lmax, 1)
+    ws = _dev.workspace(nbytes)
+    _lib.call("cora_b200_draw_apply", _lib.ptr(root), _lib.ptr(llist), None, 1, 1, lmax, ctypes.c_ulonglong(seed), None, 0,
+              _lib.ptr(panel), 1, 0, 0, 1, _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+    m = np.arange(n)
+    idx = m * (2 * lmax + 1 - m) // 2 + lmax
+    return panel[:, 0].cpu().numpy()[idx].reshape(shape)

@@ -1,0 +1,180 @@
+"""Full-sky correlated Gaussian fields: ``clarray`` and ``mkfullsky``.
+
+Mirrors ``cora/core/skysim.py:10-136`` (same names, argument meaning, return layouts and
+error behaviour); the arithmetic runs in the CUDA kernels of ``csrc/`` through the C ABI.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _dev, _lib, hputil, nputil
+
+
+def romberg_weights(zromb):
+    """Normalised Romberg weights ``w`` (sum 1) for ``2**zromb + 1`` equally spaced samples:
+    ``romb(y, dx) / (2 h) == w . y``.  Built from the Richardson tableau of the trapezoid rule
+    (what ``scipy.integrate.romb`` evaluates, ``skysim.py:64-65``)."""
+    n = 2**zromb + 1
+    if zromb == 0:
+        return np.ones(1)
+    rows = []
+    for k in range(zromb + 1):  # trapezoid with 2^k intervals, as weights on the n samples
+        step = 2 ** (zromb - k)
+        w = np.zeros(n)
+        w[::step] = 1.0
+        w[0] = w[-1] = 0.5
+        rows.append(w * step)
+    R = [rows]
+    for j in range(1, zromb + 1):
+        prev = R[-1]
+        R.append([(4**j * prev[i + 1] - prev[i]) / (4**j - 1) for i in range(len(prev) - 1)])
+    return R[-1][0] / (n - 1)
+
+
+def _sample_frequencies(zarray, zromb, zwidth):
+    zarray = np.asarray(zarray, dtype=np.float64)
+    if zromb == 0:
+        return zarray.copy(), 1
+    zsort = np.sort(zarray)
+    zhalf = np.abs(zsort[1] - zsort[0]) / 2.0 if zwidth is None else zwidth / 2.0
+    zint = 2**zromb + 1
+    za = (zarray[:, np.newaxis] + np.linspace(-zhalf, zhalf, zint)[np.newaxis, :]).flatten()
+    return za, zint
+
+
+def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
+    """Calculate an array of C_l(z, z') averaged over each frequency channel.
+
+    Same contract as ``cora/core/skysim.py:10-69``: ``aps(l, z1, z2)`` is the angular power
+    spectrum, channels are sampled at ``2**zromb + 1`` points and Romberg-integrated in both
+    arguments; returns ``float64[lmax+1, len(zarray), len(zarray)]``.
+
+    If ``aps`` is the bound ``angular_powerspectrum`` of one of this package's spectrum
+    classes (SCK foregrounds, ``Corr21cm``) the whole table is filled by one fused CUDA kernel.
+    Any other callable is evaluated in l-sections (the reference's chunking) and the Romberg
+    average runs on the GPU.
+    """
+    t = _dev.torch()
+    zarray = np.asarray(zarray, dtype=np.float64)
+    nz = zarray.size
+    owner = getattr(aps, "__self__", None)
+    fused = getattr(owner, "_b200_fill", None) if getattr(aps, "__name__", "") == "angular_powerspectrum" else None
+
+    if zromb != 0 and lmax < 5:
+        # the reference dies in np.array_split(..., 0) (skysim.py:51); keep the error type
+        raise ValueError("number sections must be larger than 0.")
+
+    za, zint = _sample_frequencies(zarray, zromb, zwidth)
+    w = romberg_weights(zromb)
+
+    if fused is not None:
+        out = _dev.empty((lmax + 1, nz, nz), t.float64)
+        fused(za, w, 0, lmax + 1, nz, zint, out)
+        return out if device_out else out.cpu().numpy()
+
+    if zromb == 0:
+        res = aps(np.arange(lmax + 1)[:, np.newaxis, np.newaxis], zarray[np.newaxis, :, np.newaxis],
+                  zarray[np.newaxis, np.newaxis, :])
+        return _dev.to_device(res, t.float64) if device_out else res
+
+    out = _dev.empty((lmax + 1, nz, nz), t.float64)
+    wd = _dev.to_device(w, t.float64)
+    for lsec in np.array_split(np.arange(lmax + 1), lmax // 5):
+        l_first = int(lsec[0])  # before the call: reference-style callables may mutate lsec
+        clt = aps(lsec[:, np.newaxis, np.newaxis], za[np.newaxis, :, np.newaxis], za[np.newaxis, np.newaxis, :])
+        blk = _dev.to_device(np.ascontiguousarray(np.broadcast_to(clt, (len(lsec), nz * zint, nz * zint))), t.float64)
+        _lib.call("cora_b200_cl_romberg_reduce", _lib.ptr(blk), _lib.ptr(wd), len(lsec), nz, zint,
+                  _lib.ptr(out[l_first:]), _lib.stream_ptr())
+    t.cuda.current_stream().synchronize()
+    return out if device_out else out.cpu().numpy()
+
+
+def draw_apply_device(root, l_list, dense_flag, nz, lmax, panel, seed=0, gauss=None, chan0=0, nu0=0, nnu=None,
+                      stream=None):
+    """Draw + apply on device buffers (see ``cora_b200_draw_apply`` in include/cora_b200.h)."""
+    t = _dev.torch()
+    lib = _lib.load()
+    l_list = np.ascontiguousarray(l_list, dtype=np.int32)
+    nl = len(l_list)
+    nnu = nz if nnu is None else nnu
+    if gauss is None:
+        full = lib.cora_b200_draw_apply_workspace_bytes(nz, int(l_list.max()), nl)
+        one = lib.cora_b200_draw_apply_workspace_bytes(nz, int(l_list.max()), 1)
+        nbytes = min(full, max(one, _dev.free_bytes() - (2 << 30)))
+        gauss_ld = 0
+    else:
+        nbytes = 64 * nl + 4096
+        gauss_ld = int(gauss.shape[-1])
+    ws = _dev.workspace(nbytes)
+    _lib.call("cora_b200_draw_apply", _lib.ptr(root), _lib.ptr(l_list), _lib.ptr(dense_flag), nl, int(nz), int(lmax),
+              ctypes.c_ulonglong(int(seed)), _lib.ptr(gauss), gauss_ld, _lib.ptr(panel), int(panel.shape[1]), int(chan0),
+              int(nu0), int(nnu), _lib.ptr(ws), int(nbytes), _lib.stream_ptr(stream))
+    return panel
+
+
+def mkfullsky(corr, nside, alms=False, rng=None, *, seed=None, roots=None, gauss=None, device_out=False):
+    """Construct a set of correlated Healpix maps (``cora/core/skysim.py:72-136``).
+
+    Parameters
+    ----------
+    corr : np.ndarray or CUDA tensor (lmax+1, numz, numz)
+        The correlation matrix C_l(z, z').
+    nside : integer
+        The resolution of the Healpix maps.
+    alms : boolean, optional
+        If True return the alms ``complex128[numz, 1, lmax+1, lmax+1]`` instead of the maps.
+    rng : numpy Generator, optional
+        If given, the Gaussian draws are taken from it exactly as the reference does (per l,
+        ascending: real block then imaginary block of shape (numz, l+1)) and applied on the GPU
+        -- the identical-draw parity path.  If None, draws come from the device Philox
+        generator (the reference would use numpy's legacy global state).
+
+    Keyword-only extensions (not in the reference signature): ``seed`` for the Philox path;
+    ``roots`` (float64[L, numz, numz]) / ``gauss`` (complex128[L, numz, L]) to inject the
+    reference's own matrix roots / draws; ``device_out`` to get CUDA tensors back.
+
+    Returns
+    -------
+    hpmaps : np.ndarray (numz, npix)   -- or the alm array if ``alms``.
+    """
+    t = _dev.torch()
+    if hasattr(corr, "local_array"):
+        raise Exception("MPIArray input: use cora_b200.dist.mkfullsky_sharded for the multi-GPU path.")
+    numz = corr.shape[1]
+    maxl = corr.shape[0] - 1
+    if corr.shape[2] != numz:
+        raise Exception("Correlation matrix is incorrect shape.")
+    L = maxl + 1
+    nalm = L * (L + 1) // 2
+
+    if roots is None:
+        cl = _dev.to_device(corr, t.float64)
+        root, used, _ = nputil.root_batched_device(cl, jitter_rel=1e-14, clip_rel=1e-16)
+        del cl
+    else:
+        root = _dev.to_device(roots, t.float64)
+        used = None  # injected roots: treat as dense
+
+    gdev = None
+    if gauss is not None:
+        gdev = _dev.to_device(gauss, t.complex128)
+    elif rng is not None:
+        g = np.zeros((L, numz, L), dtype=np.complex128)
+        for l in range(L):
+            g[l, :, : l + 1] = nputil.complex_std_normal((numz, l + 1), rng=rng)
+        gdev = _dev.to_device(g, t.complex128)
+    elif seed is None:
+        seed = int(np.random.randint(0, 2**31 - 1))
+
+    panel = _dev.empty((nalm, numz), t.complex128)
+    draw_apply_device(root, np.arange(L), used, numz, maxl, panel, seed=seed or 0, gauss=gdev)
+    del root, gdev
+
+    if alms:
+        dense = hputil.panel_to_dense(panel, maxl, numz)  # [numz, L, L]
+        out = dense.reshape(numz, 1, L, L)
+        return out if device_out else out.cpu().numpy()
+
+    sky = hputil.alm2map_device(panel, nside, maxl, _lib.ALM_PANEL, numz, numz)
+    return sky if device_out else sky.cpu().numpy()

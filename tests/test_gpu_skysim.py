@@ -1,0 +1,248 @@
+"""GPU parity for the root / draw / apply stages and the end-to-end mkfullsky
+(csrc/root.cu, csrc/apply.cu, csrc/sht.cu through the C ABI)."""
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import hputil as ohp
+from oracle import nputil as onp
+from oracle import skysim as osk
+
+pytestmark = pytest.mark.gpu
+
+
+def _mmt_err(root, c):
+    return np.max(np.abs(root @ root.T - c)) / np.max(np.abs(c))
+
+
+def test_matrix_root_manynull_cases():
+    from cora_b200 import nputil
+
+    g = golden("root_cases.npz")
+    r = nputil.matrix_root_manynull(g["spd"].copy(), truncate=False)
+    np.testing.assert_allclose(r, g["root_spd"], rtol=1e-12, atol=1e-14)
+    assert np.all(np.triu(r, 1) == 0)
+    r2, npos = nputil.matrix_root_manynull(g["spd"].copy())
+    assert npos == 12 and r2.shape == (12, 12)
+    # eigh branch
+    low = g["lowrank"]
+    r = nputil.matrix_root_manynull(low.copy(), truncate=False)
+    assert r.shape == (12, 12)
+    assert _mmt_err(r, low) < 1e-12
+    assert np.all(r[:, :8] == 0)  # clipped columns first, kept as zeros
+    np.testing.assert_allclose(np.abs(r[:, 8:]), np.abs(g["root_lowrank"][:, 8:]), atol=1e-11)
+    rt, npos = nputil.matrix_root_manynull(low.copy())
+    assert npos == int(g["num_pos"]) == 4
+    assert rt.shape == g["root_lowrank_trunc"].shape == (1, 12, 4)  # reference shape quirk
+
+
+def test_root_batched_random_and_degenerate():
+    import torch
+    from cora_b200 import nputil
+
+    rng = np.random.default_rng(0)
+    nz = 70  # not a multiple of the panel width
+    mats = []
+    for k in range(6):
+        a = rng.standard_normal((nz, nz if k % 2 == 0 else 9))
+        mats.append(a @ a.T)
+    mats.append(np.zeros((nz, nz)))  # zero matrix (SCK l = 0): Cholesky fails -> eigh -> root 0
+    mats = np.array(mats)
+    root, used, npos = nputil.root_batched_device(torch.from_numpy(mats).cuda(), jitter_rel=1e-14, clip_rel=1e-16)
+    root, used, npos = root.cpu().numpy(), used.cpu().numpy(), npos.cpu().numpy()
+    for k in range(6):
+        ref = onp.matrix_root_manynull(mats[k] + np.eye(nz) * mats[k].diagonal().max() * 1e-14, truncate=False)
+        ref_eigh = not np.all(np.triu(ref, 1) == 0)
+        assert bool(used[k]) == ref_eigh
+        assert _mmt_err(root[k], mats[k]) < 1e-12
+        if not ref_eigh:
+            np.testing.assert_allclose(root[k], ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
+        else:
+            assert npos[k] == np.count_nonzero(np.abs(ref).sum(axis=0))
+    assert used[6] == 1 and npos[6] == 0 and np.all(root[6] == 0)
+
+
+def test_root_256_channels_21cm_like():
+    """Config-2-sized matrices (256 x 256): Cholesky path against LAPACK."""
+    import torch
+    from cora_b200 import nputil
+
+    rng = np.random.default_rng(1)
+    nz = 256
+    x = np.linspace(0, 1, nz)
+    base = np.exp(-0.5 * ((x[:, None] - x[None, :]) / 0.02) ** 2)
+    mats = np.array([base * (1 + 0.1 * k) + 1e-6 * np.eye(nz) for k in range(5)])
+    root, used, _ = nputil.root_batched_device(torch.from_numpy(mats).cuda(), jitter_rel=1e-14)
+    root = root.cpu().numpy()
+    assert not used.cpu().numpy().any()
+    for k in range(5):
+        ref = onp.matrix_root_manynull(mats[k] + np.eye(nz) * mats[k].diagonal().max() * 1e-14, truncate=False)
+        assert _mmt_err(root[k], mats[k]) < 1e-12
+        np.testing.assert_allclose(root[k], ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
+def test_complex_std_normal():
+    from cora_b200 import nputil
+
+    g = golden("root_cases.npz")
+    v = nputil.complex_std_normal((5, 7), rng=np.random.default_rng(11))
+    np.testing.assert_array_equal(v, g["cstd_seed11"])  # identical-draw path: the caller's stream, bit for bit
+    a = nputil.complex_std_normal((200, 500), seed=1)
+    b = nputil.complex_std_normal((200, 500), seed=1)
+    c = nputil.complex_std_normal((200, 500), seed=2)
+    assert a.shape == (200, 500) and a.dtype == np.complex128
+    np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(a, c)
+    n = a.size
+    assert abs(a.real.mean()) < 5 / np.sqrt(2 * n) and abs(a.imag.mean()) < 5 / np.sqrt(2 * n)
+    assert abs(a.real.var() - 0.5) < 5 * 0.5 * np.sqrt(2.0 / n)
+    assert abs(a.imag.var() - 0.5) < 5 * 0.5 * np.sqrt(2.0 / n)
+    assert abs(np.mean(a.real * a.imag)) < 5 * 0.5 / np.sqrt(n)
+    # kurtosis of a Gaussian
+    x = a.real / np.sqrt(0.5)
+    assert abs(np.mean(x**4) - 3.0) < 5 * np.sqrt(96.0 / n)
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 counter (l, m, nu', 0), key = seed, against a numpy restatement of the
+    published Random123 algorithm + the same Box-Muller mapping."""
+    from cora_b200 import nputil
+
+    def philox(c, k):
+        M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+        c = [int(v) for v in c]
+        k = [int(v) for v in k]
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF,
+                 p0 & 0xFFFFFFFF]
+            k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+        return c
+
+    # Random123 known-answer test vectors for philox4x32-10
+    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    seed = 0x123456789
+    n = 40
+    v = nputil.complex_std_normal((n,), seed=seed)  # l = n-1, nu' = 0, m = 0..n-1
+    for m in (0, 1, 7, 39):
+        r = philox([n - 1, m, 0, 0], [seed & 0xFFFFFFFF, seed >> 32])
+        a = (r[1] << 32) | r[0]
+        b = (r[3] << 32) | r[2]
+        u1 = ((a >> 11) + 0.5) * 2.0**-53
+        u2 = ((b >> 11) + 0.5) * 2.0**-53
+        rad = np.sqrt(-np.log(u1))
+        ref = rad * np.cos(2 * np.pi * u2) + 1j * rad * np.sin(2 * np.pi * u2)
+        assert abs(v[m] - ref) < 1e-14
+
+
+def _check_alms(name, seed):
+    from cora_b200 import skysim
+
+    g = golden(name)
+    cl, nside = g["cl"], int(g["nside"])
+    # (1) identical draws, own roots
+    alm = skysim.mkfullsky(cl, nside, alms=True, rng=np.random.default_rng(seed))
+    assert alm.shape == g["alm"].shape and alm.dtype == np.complex128
+    scale = np.abs(g["alm"]).max()
+    assert np.max(np.abs(alm - g["alm"])) / scale < 1e-10
+    L = cl.shape[0]
+    for l in range(L):
+        assert np.all(alm[:, 0, l, l + 1 :] == 0)
+    # (2) the reference's own roots and draws injected
+    alm2 = skysim.mkfullsky(cl, nside, alms=True, roots=g["roots"], gauss=g["gauss"])
+    assert np.max(np.abs(alm2 - g["alm"])) / scale < 1e-12
+    return g
+
+
+def test_mkfullsky_alms_vs_reference_fixture_sck():
+    _check_alms("mkfullsky_sck.npz", 0)
+
+
+def test_mkfullsky_alms_vs_reference_fixture_21cm():
+    _check_alms("mkfullsky_21cm.npz", 0)
+
+
+def test_mkfullsky_alms_polarised_block_fixture():
+    from cora_b200 import skysim
+
+    g = golden("mkfullsky_pol.npz")
+    alm = skysim.mkfullsky(g["cl"], 4, alms=True, rng=np.random.default_rng(3))
+    scale = np.abs(g["alm"]).max()
+    assert np.max(np.abs(alm - g["alm"])) / scale < 1e-10
+
+
+def test_mkfullsky_maps_identical_draws():
+    """North-star check 1: fed the reference's draws and roots, maps match to <= 1e-10 (max-abs
+    over pixels, relative).  Reference alm fixture -> oracle SHT restatement vs the GPU path."""
+    from cora_b200 import skysim
+
+    for name in ("mkfullsky_sck.npz", "mkfullsky_21cm.npz"):
+        g = golden(name)
+        nside = int(g["nside"])
+        ref = ohp.sphtrans_inv_sky(g["alm"], nside)[:, 0]
+        sky = skysim.mkfullsky(g["cl"], nside, roots=g["roots"], gauss=g["gauss"])
+        assert sky.shape == ref.shape == (g["cl"].shape[1], 12 * nside**2)
+        assert np.max(np.abs(sky - ref)) / np.max(np.abs(ref)) < 1e-10
+        sky2 = skysim.mkfullsky(g["cl"], nside, rng=np.random.default_rng(0))
+        assert np.max(np.abs(sky2 - ref)) / np.max(np.abs(ref)) < 1e-9
+
+
+def test_mkfullsky_errors():
+    from cora_b200 import skysim
+
+    with pytest.raises(Exception, match="incorrect shape"):
+        skysim.mkfullsky(np.zeros((4, 3, 2)), 2)
+
+
+def test_mkfullsky_config1_end_to_end_statistics():
+    """Config 1 (gaussianfg nside 64, 32 channels, lmax 192) with the device Philox draws:
+    alm second moments reproduce C_l within cosmic variance (north-star check 2, in alm space),
+    and the root satisfies M M^T = C_l to 1e-12."""
+    import torch
+    from cora_b200 import galaxy, nputil, skysim
+
+    nside, nfreq = 64, 32
+    lmax = 3 * nside
+    freq = np.linspace(800.0, 400.0, nfreq, endpoint=False)
+    cl = skysim.clarray(galaxy.FullSkySynchrotron().angular_powerspectrum, lmax, freq)
+    root, used, _ = nputil.root_batched_device(torch.from_numpy(cl).cuda(), jitter_rel=1e-14)
+    root = root.cpu().numpy()
+    for l in (1, 2, 50, 192):
+        assert np.max(np.abs(root[l] @ root[l].T - cl[l])) / np.max(np.abs(cl[l])) < 1e-12
+    alm = skysim.mkfullsky(cl, nside, alms=True, seed=42)[:, 0]
+    # estimator over m >= 1 (m = 0 carries C_l / 2 in its real part)
+    for l in (20, 100, 192):
+        a = alm[:, l, 1 : l + 1]
+        est = (a @ a.conj().T).real / l
+        sig = np.sqrt((cl[l].diagonal()[:, None] * cl[l].diagonal()[None, :] + cl[l] ** 2) / (2 * l))
+        assert np.all(np.abs(est - cl[l]) < 6 * sig)
+    sky = skysim.mkfullsky(cl, nside, seed=42)
+    assert sky.shape == (nfreq, 12 * nside**2)
+    # same seed -> same alm -> the map is the SHT of those alm
+    ref = ohp.sphtrans_inv_sky(skysim.mkfullsky(cl, nside, alms=True, seed=42)[:2], nside)[:, 0]
+    assert np.max(np.abs(sky[:2] - ref)) / np.max(np.abs(ref)) < 1e-10
+
+
+def test_getsky_and_makesky_drivers():
+    from cora_b200 import corr21cm, makesky
+
+    fs = makesky.FreqState()
+    fs.freq = (800.0, 700.0, 4)
+    np.random.seed(0)
+    m = makesky.make_21cm(fs, 8, pol="full")
+    assert m.shape == (4, 4, 12 * 64) and np.all(m[:, 1:] == 0) and np.all(np.isfinite(m))
+    m = makesky.make_21cm(fs, 8, pol="none")
+    assert m.shape == (4, 12 * 64)
+    m = makesky.make_gaussianfg(fs, 8, pol="full", seed=1)
+    assert m.shape == (4, 4, 12 * 64)
+    assert np.abs(m[:, 1]).max() > 0 and np.abs(m[:, 2]).max() > 0
+    # few channels -> Cholesky path -> V = sqrt(cmax) g, tiny but non-zero
+    assert 0 < np.abs(m[:, 3]).max() < 1e-4 * np.abs(m[:, 0]).max()
+    m1 = makesky.make_gaussianfg(fs, 8, pol="none", seed=1)
+    assert m1.shape == (4, 1, 12 * 64)
+    cr = corr21cm.Corr21cm()
+    cr.nside, cr.frequencies = 8, fs.frequencies
+    a = cr.getalms(23)
+    assert a.shape == (4, 1, 24, 24)
