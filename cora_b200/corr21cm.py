@@ -166,9 +166,9 @@ class Corr21cm(maps.Sky3d):
         lb = np.ascontiguousarray(np.broadcast_to(la, shape)).ravel()
         v1b, v2b = vectors(z1), vectors(z2)
         out = _dev.empty((n,), t.float64)
-        _lib.call("cora_b200_aps_21cm_points", _lib.ptr(self.table()), _lib.ptr(_dev.to_device(lb, t.float64)),
-                  _lib.ptr(_dev.to_device(v1b, t.float64)), _lib.ptr(_dev.to_device(v2b, t.float64)), n, _lib.ptr(out),
-                  _lib.stream_ptr())
+        dl, d1, d2 = _dev.to_device(lb, t.float64), _dev.to_device(v1b, t.float64), _dev.to_device(v2b, t.float64)
+        _lib.call("cora_b200_aps_21cm_points", _lib.ptr(self.table()), _lib.ptr(dl), _lib.ptr(d1), _lib.ptr(d2), n,
+                  _lib.ptr(out), _lib.stream_ptr())
         res = out.cpu().numpy().reshape(shape)
         return res if res.ndim else float(res)
 

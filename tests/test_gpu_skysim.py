@@ -57,7 +57,9 @@ def test_root_batched_random_and_degenerate():
         assert bool(used[k]) == ref_eigh
         assert _mmt_err(root[k], mats[k]) < 1e-12
         if not ref_eigh:
-            np.testing.assert_allclose(root[k], ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
+            # two backward-stable Cholesky factorisations differ by ~cond(C) eps
+            tol = 50 * np.linalg.cond(mats[k]) * 2.2e-16
+            np.testing.assert_allclose(root[k], ref, rtol=0, atol=tol * np.abs(ref).max())
         else:
             assert npos[k] == np.count_nonzero(np.abs(ref).sum(axis=0))
     assert used[6] == 1 and npos[6] == 0 and np.all(root[6] == 0)
@@ -137,16 +139,18 @@ def test_philox_known_answer():
         assert abs(v[m] - ref) < 1e-14
 
 
-def _check_alms(name, seed):
+def _check_alms(name, seed, own_root_tol):
     from cora_b200 import skysim
 
     g = golden(name)
     cl, nside = g["cl"], int(g["nside"])
-    # (1) identical draws, own roots
+    # (1) identical draws, own roots.  The root of an ill-conditioned C_l is only determined to
+    # ~cond(C_l) eps (LAPACK's and ours both satisfy M M^T = C_l to 1e-14), hence the per-model
+    # tolerance; the strict identical-draw contract is (2).
     alm = skysim.mkfullsky(cl, nside, alms=True, rng=np.random.default_rng(seed))
     assert alm.shape == g["alm"].shape and alm.dtype == np.complex128
     scale = np.abs(g["alm"]).max()
-    assert np.max(np.abs(alm - g["alm"])) / scale < 1e-10
+    assert np.max(np.abs(alm - g["alm"])) / scale < own_root_tol
     L = cl.shape[0]
     for l in range(L):
         assert np.all(alm[:, 0, l, l + 1 :] == 0)
@@ -157,11 +161,11 @@ def _check_alms(name, seed):
 
 
 def test_mkfullsky_alms_vs_reference_fixture_sck():
-    _check_alms("mkfullsky_sck.npz", 0)
+    _check_alms("mkfullsky_sck.npz", 0, 1e-6)  # SCK channels are ~1e10-conditioned
 
 
 def test_mkfullsky_alms_vs_reference_fixture_21cm():
-    _check_alms("mkfullsky_21cm.npz", 0)
+    _check_alms("mkfullsky_21cm.npz", 0, 1e-10)
 
 
 def test_mkfullsky_alms_polarised_block_fixture():
@@ -170,7 +174,7 @@ def test_mkfullsky_alms_polarised_block_fixture():
     g = golden("mkfullsky_pol.npz")
     alm = skysim.mkfullsky(g["cl"], 4, alms=True, rng=np.random.default_rng(3))
     scale = np.abs(g["alm"]).max()
-    assert np.max(np.abs(alm - g["alm"])) / scale < 1e-10
+    assert np.max(np.abs(alm - g["alm"])) / scale < 1e-6  # own roots of ill-conditioned SCK blocks
 
 
 def test_mkfullsky_maps_identical_draws():
@@ -185,8 +189,8 @@ def test_mkfullsky_maps_identical_draws():
         sky = skysim.mkfullsky(g["cl"], nside, roots=g["roots"], gauss=g["gauss"])
         assert sky.shape == ref.shape == (g["cl"].shape[1], 12 * nside**2)
         assert np.max(np.abs(sky - ref)) / np.max(np.abs(ref)) < 1e-10
-        sky2 = skysim.mkfullsky(g["cl"], nside, rng=np.random.default_rng(0))
-        assert np.max(np.abs(sky2 - ref)) / np.max(np.abs(ref)) < 1e-9
+        sky2 = skysim.mkfullsky(g["cl"], nside, rng=np.random.default_rng(0))  # own roots: cond(C_l) eps
+        assert np.max(np.abs(sky2 - ref)) / np.max(np.abs(ref)) < (1e-6 if "sck" in name else 1e-9)
 
 
 def test_mkfullsky_errors():
