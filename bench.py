@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""Benchmark of the full-sky Gaussian field path (BASELINE.json: map voxels/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+One "step" = one pass of the hot path over the workload: C_l(nu,nu') fill -> batched root ->
+Philox draws + apply -> (N > 1: all-to-all) -> inverse SHT -> maps resident in HBM.  The
+one-off 21cm P(k) DCT table (the reference's ``_aps_cache``, corr.py:915-942) is built once
+before the timed region in both arms and reported separately.
+
+``--impl reference`` times the CPU restatement of the reference path (``oracle/``; numpy/scipy,
+all host cores through a fork pool + BLAS threads) on a bounded sample of the same workload
+and extrapolates to the whole workload (the sample is described in ``cpu_baseline.sample``).
+healpy cannot be installed here, so the SHT leg is the restatement, not healpy.
+
+Prints ONE JSON line (rank 0).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, nside, nchan, f_start, f_stop)   (BASELINE.json configs; frequencies = makesky "centre" mode)
+    "c1": ("gaussianfg", 64, 32, 800.0, 400.0),
+    "c2": ("21cm", 256, 256, 800.0, 400.0),
+    "c3": ("21cm", 512, 1024, 800.0, 400.0),
+    "c5": ("21cm", 1024, 2048, 800.0, 400.0),
+}
+WORKLOAD_TEXT = {
+    "c1": "cora-makesky gaussianfg nside=64, 32 channels 400-800 MHz, unpolarised",
+    "c2": "cora-makesky 21cm (Corr21cm) nside=256, 256 channels 400-800 MHz",
+    "c3": "cora-makesky 21cm nside=512, 1024 channels 400-800 MHz",
+    "c5": "cora-makesky 21cm nside=1024, 2048 channels 400-800 MHz",
+}
+METRIC = "full-sky map voxels/sec (pixels x channels)"
+UNIT = "voxels/s"
+
+
+def workload_params(name):
+    model, nside, nchan, f0, f1 = WORKLOADS[name]
+    lmax = 3 * nside if model == "gaussianfg" else 3 * nside - 1
+    freq = np.linspace(f0, f1, nchan, endpoint=False)
+    return dict(model=model, nside=nside, nchan=nchan, lmax=lmax, freq=freq, npix=12 * nside * nside, zromb=3)
+
+
+def sht_flops(nside, lmax, nchan):
+    """2 real FMAs per (ring pair, l, m, channel) = 4 flop x ceil((4 nside - 1)/2) x nalm x nchan."""
+    L = lmax + 1
+    return 4.0 * ((4 * nside - 1 + 1) // 2) * (L * (L + 1) / 2.0) * nchan
+
+
+# =============================================================================== CPU arm
+def _cpu_fill_one(args):
+    """worker: C_l for one l (aps evaluation at all (9 nz)^2 sample pairs + both Romberg passes)."""
+    import scipy.integrate as si
+
+    l, za, nz, zint, dx, h = args
+    clt = _CPU["aps"](np.array([l])[:, None, None], za[None, :, None], za[None, None, :])
+    clt = np.broadcast_to(clt, (1, nz * zint, nz * zint)).reshape(1, nz, zint, nz, zint)
+    clt = si.romb(clt, dx=dx, axis=4)
+    clt = si.romb(clt, dx=dx, axis=2)
+    return clt[0] / (2 * h) ** 2
+
+
+def _cpu_leg_one(args):
+    """worker: Legendre stage of one m for all channels (lambda recursion + contraction)."""
+    from oracle import sht as osht
+
+    m, lmax, nchan, seed = args
+    g = _CPU["geom"]
+    lam = osht.lambda_lm(lmax, m, g["cth"], g["sth"])
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((nchan, lmax - m + 1)) + 1j * rng.standard_normal((nchan, lmax - m + 1))
+    return (lam.T @ a.T).shape[0]
+
+
+_CPU = {}
+
+
+def cpu_reference_setup(wp):
+    """One-off state of the CPU arm (21cm: the P(k) DCT tables, like the reference's cache)."""
+    from oracle import sht as osht
+    from oracle import spectra as osp
+
+    t0 = time.time()
+    if wp["model"] == "21cm":
+        c = osp.Corr21cm()
+        c.tables()
+        _CPU["aps"] = c.angular_powerspectrum
+    else:
+        _CPU["aps"] = osp.full_sky_synchrotron().angular_powerspectrum
+    _CPU["geom"] = osht.ring_geometry(wp["nside"])
+    return time.time() - t0
+
+
+def cpu_reference_step(wp, pool, ncores, scale=1):
+    """Time a bounded sample of the path on the host and extrapolate to the whole workload.
+
+    Returns (extrapolated seconds for the whole workload, per-stage dict, sample description)."""
+    import scipy.linalg as la
+
+    from oracle import nputil as onp
+    from oracle import sht as osht
+
+    nz, lmax, nside, npix = wp["nchan"], wp["lmax"], wp["nside"], wp["npix"]
+    L = lmax + 1
+    freq = wp["freq"]
+    zs = np.sort(freq)
+    h = abs(zs[1] - zs[0]) / 2.0
+    zint = 2 ** wp["zromb"] + 1
+    dx = 2.0 * h / 2 ** wp["zromb"]
+    za = (freq[:, None] + np.linspace(-h, h, zint)[None, :]).flatten()
+
+    # --- stage 1: C_l fill, one l per worker, ls spread over the range
+    n_l = max(1, ncores * scale)
+    ls = np.unique(np.linspace(1, lmax, n_l).astype(int))
+    t0 = time.time()
+    cls = pool.map(_cpu_fill_one, [(int(l), za, nz, zint, dx, h) for l in ls])
+    t_fill_s = time.time() - t0
+    t_fill = t_fill_s * L / len(ls)
+
+    # --- stages 2-4: root, draws, apply for the same l's (BLAS threads)
+    rng = np.random.default_rng(0)
+    t_root_s = t_draw_s = t_apply_s = 0.0
+    for l, c in zip(ls, cls):
+        t0 = time.time()
+        cm = c + np.identity(nz) * c.diagonal().max() * 1e-14
+        tr = onp.matrix_root_manynull(cm, truncate=False)
+        t1 = time.time()
+        g = onp.complex_std_normal((nz, l + 1), rng=rng)
+        t2 = time.time()
+        _ = np.dot(tr, g)
+        t3 = time.time()
+        t_root_s += t1 - t0
+        t_draw_s += t2 - t1
+        t_apply_s += t3 - t2
+    wsum = float(np.sum(ls + 1))
+    wall = L * (L + 1) / 2.0
+    t_root = t_root_s * L / len(ls)
+    t_draw = t_draw_s * wall / wsum
+    t_apply = t_apply_s * wall / wsum
+
+    # --- stage 5: inverse SHT (restatement of healpy.alm2map): Legendre over sampled m, phase over sampled rings
+    n_m = max(2, 2 * ncores * scale)
+    ms = np.unique(np.linspace(0, lmax, n_m).astype(int))
+    t0 = time.time()
+    pool.map(_cpu_leg_one, [(int(m), lmax, nz, 7 + int(m)) for m in ms])
+    t_leg_s = time.time() - t0
+    t_leg = t_leg_s * wall / float(np.sum(lmax - ms + 1))
+    nring = 4 * nside - 1
+    rs = np.unique(np.linspace(0, nring - 1, max(2, 2 * ncores * scale)).astype(int))
+    Fm = (rng.standard_normal((L, len(rs), nz)) + 1j * rng.standard_normal((L, len(rs), nz)))
+    out = np.empty((nz, npix))
+    t0 = time.time()
+    osht._rings_from_phase(Fm, _CPU["geom"], rs, out)
+    t_ph_s = time.time() - t0
+    t_phase = t_ph_s * nring / len(rs)
+
+    stages = {"cl_fill_s": t_fill, "root_s": t_root, "draws_s": t_draw, "apply_s": t_apply, "sht_legendre_s": t_leg,
+              "sht_phase_s": t_phase}
+    total = sum(stages.values())
+    sample = ("oracle port (numpy/scipy), %d-process fork pool + BLAS threads; per step: C_l fill + root/draw/apply for "
+              "%d of %d l (extrapolated x l-count / x sum(l+1)), SHT Legendre for %d of %d m and phase synthesis for "
+              "%d of %d rings, all %d channels (extrapolated by work); SHT leg is the restatement, not healpy; "
+              "sample wall %.1f s" % (ncores, len(ls), L, len(ms), L, len(rs), nring, nz,
+                                      t_fill_s + t_root_s + t_draw_s + t_apply_s + t_leg_s + t_ph_s))
+    return total, stages, sample
+
+
+def run_reference(args):
+    """``--impl reference``: rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+
+    wp = workload_params(args.workload)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ncores = min(ncores, 32)
+    oneoff = cpu_reference_setup(wp)
+    pool = mp.get_context("fork").Pool(ncores)
+    try:
+        for _ in range(args.warmup):
+            cpu_reference_step(wp, pool, ncores)
+        totals, stages, sample = [], None, ""
+        t_start = time.time()
+        for _ in range(args.steps):
+            tot, stages, sample = cpu_reference_step(wp, pool, ncores)
+            totals.append(tot)
+        wall = time.time() - t_start
+    finally:
+        pool.close()
+        pool.join()
+    total = float(np.median(totals))
+    voxels = wp["npix"] * wp["nchan"]
+    value = voxels / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "nside": wp["nside"], "channels": wp["nchan"],
+                   "lmax": wp["lmax"], "zromb": wp["zromb"],
+                   "note": "value = voxels / extrapolated whole-workload CPU seconds (%.1f s); each step times a bounded "
+                           "sample; one-off P(k) table build %.1f s excluded (as in the GPU arm)" % (total, oneoff)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample,
+                         "stages_extrapolated_s": stages},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================== clocks
+class ClockSampler(object):
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =============================================================================== GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from cora_b200 import _dev, _lib, build
+    from cora_b200 import dist as cdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0 and build.needs_build():
+        build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+
+    wp = workload_params(args.workload)
+    nside, nchan, lmax, npix = wp["nside"], wp["nchan"], wp["lmax"], wp["npix"]
+    if wp["model"] == "21cm":
+        from cora_b200 import corr21cm
+
+        model = corr21cm.Corr21cm()
+        t0 = time.time()
+        model.table()
+        torch.cuda.synchronize()
+        table_s = time.time() - t0
+    else:
+        from cora_b200 import galaxy
+
+        model = galaxy.FullSkySynchrotron()
+        table_s = 0.0
+    model.nside = nside
+    model.frequencies = wp["freq"]
+    model.oversample = wp["zromb"]
+
+    sh = cdist.ShardedSky(model, nside, wp["freq"], lmax=lmax, zromb=wp["zromb"], rank=rank, size=world)
+    out = torch.empty((sh.cb, npix), dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for i in range(args.warmup):
+        sh.step(seed=1000 + i, out=out)
+    barrier()
+    lib.cora_b200_timing_enable(1)
+    n0 = lib.cora_b200_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        sh.step(seed=i, out=out)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = lib.cora_b200_launch_count() - n0
+    nk = lib.cora_b200_timing_kinds()
+    kms = (ctypes_double * nk)()
+    kcnt = (ctypes_ll * nk)()
+    lib.cora_b200_timing_read(kms, kcnt, nk)
+    lib.cora_b200_timing_enable(0)
+    kernels = {lib.cora_b200_timing_name(i).decode(): (kms[i], kcnt[i]) for i in range(nk)}
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    voxels = float(npix) * nchan
+    value = voxels * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API, host buffers in / host maps out ("e2e")
+    e2e_steps = max(1, min(args.steps, 5))
+    _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
+
+    def e2e_once(seed):
+        if world == 1:
+            np.random.seed(seed)
+            return model.getsky()  # Sky3d.getsky(): clarray + mkfullsky -> numpy float64[nfreq, npix]
+        sh2 = cdist.ShardedSky(model, nside, wp["freq"], lmax=lmax, zromb=wp["zromb"], rank=rank, size=world)
+        return _dev.to_host(sh2.step(seed=seed))
+
+    e2e_once(99)  # warm the pinned-buffer cache
+    _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        res = e2e_once(i)
+        assert res.shape == (sh.cb if world > 1 else nchan, npix)
+        del res
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s, _dev.traffic["h2d"], _dev.traffic["d2h"]], dtype=torch.float64, device="cuda")
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        e2e_s, h2d, d2h = float(mx[0].item()), float(tt[1].item()), float(tt[2].item())
+    else:
+        h2d, d2h = _dev.traffic["h2d"], _dev.traffic["d2h"]
+    e2e_value = voxels * e2e_steps / e2e_s
+
+    # ---- roofline of the dominant kernel (rank 0's view): the Legendre stage of the inverse SHT
+    peak = (ctypes_double * 1)()
+    _lib.call("cora_b200_fp64_peak", 50.0, peak, _lib.stream_ptr())
+    leg_ms, leg_n = kernels["sht_legendre"]
+    flops_per_launch = sht_flops(nside, lmax, sh.cb) * args.steps / max(1, leg_n)
+    achieved = flops_per_launch / (leg_ms / max(1, leg_n) * 1e-3) / 1e12 if leg_ms > 0 else 0.0
+    step_ms = ms / args.steps
+    stage_share = {k: round(v[0] / args.steps, 4) for k, v in kernels.items() if v[1]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup",
+                                "0", "--workload", args.workload], capture_output=True, text=True, timeout=900)
+            ref = json.loads(p.stdout.strip().splitlines()[-1])
+            cpu_baseline = ref["cpu_baseline"]
+        except Exception as exc:  # the GPU numbers stand on their own
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % (exc,)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "nside": nside, "channels": nchan, "lmax": lmax,
+                   "zromb": wp["zromb"], "parallelism": "l-sharded root/apply + channel-sharded SHT x%d" % world,
+                   "l2": "per-step working set (C_l %.0f MB, alm %.0f MB, maps %.0f MB per GPU) exceeds the 126 MB L2; no flush needed"
+                         % (8e-6 * sh.nl * nchan * nchan, 16e-6 * (lmax + 1) * (lmax + 2) / 2 * sh.cb, 8e-6 * sh.cb * npix),
+                   "one_off_table_build_s": round(table_s, 3),
+                   "stage_ms_per_step": stage_share},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
+                "steps": e2e_steps, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "sht_legendre_kernel<0> (FP64 DMMA)", "achieved": achieved,
+                     "peak": float(peak[0]), "unit": "TFLOP/s", "frac": achieved / float(peak[0]) if peak[0] else None,
+                     "traffic": None,
+                     "peak_source": "FP64 DMMA peak measured in this run by cora_b200_fp64_peak (MEASURED_PEAKS.json "
+                                    "has no FP64 entry; 37.1 TFLOP/s recorded in profiles/microbench/)",
+                     "flops_per_launch": flops_per_launch, "launch_ms": leg_ms / max(1, leg_n)},
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+import ctypes  # noqa: E402
+
+ctypes_double = ctypes.c_double
+ctypes_ll = ctypes.c_longlong
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                                  str(args.gpus), "--master-addr", "127.0.0.1", "--master-port", "29533",
+                                  os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

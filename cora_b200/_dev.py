@@ -9,6 +9,9 @@ from . import _lib
 
 _plans = {}
 
+# bytes moved across PCIe by this package (bench.py reports them as h2d/d2h_bytes_per_step)
+traffic = {"h2d": 0, "d2h": 0}
+
 
 def torch():
     return _lib.require_cuda()
@@ -28,10 +31,23 @@ def to_device(a, dtype=None):
             x = x.to(dtype)
         return x.contiguous()
     arr = np.ascontiguousarray(a)
+    traffic["h2d"] += arr.nbytes
     x = t.from_numpy(arr).to(device(), non_blocking=False)
     if dtype is not None and x.dtype != dtype:
         x = x.to(dtype)
     return x
+
+
+def to_host(x):
+    """CUDA tensor -> numpy array through a pinned host buffer (torch's pinned-memory cache owns
+    the block; the returned array keeps it alive and hands it back when it is dropped)."""
+    t = torch()
+    x = x.contiguous()
+    h = t.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    h.copy_(x, non_blocking=True)
+    t.cuda.current_stream().synchronize()
+    traffic["d2h"] += h.numel() * h.element_size()
+    return h.numpy()
 
 
 def empty(shape, dtype):

@@ -22,6 +22,10 @@ SIGNATURES = {
     "cora_b200_last_error": (_c.c_char_p, []),
     "cora_b200_launch_count": (_ll, []),
     "cora_b200_fp64_peak": (_i, [_d, _c.POINTER(_d), _vp]),
+    "cora_b200_timing_enable": (_i, [_i]),
+    "cora_b200_timing_kinds": (_i, []),
+    "cora_b200_timing_name": (_c.c_char_p, [_i]),
+    "cora_b200_timing_read": (_i, [_c.POINTER(_d), _c.POINTER(_ll), _i]),
     "cora_b200_sht_plan_create": (_i, [_i, _i, _c.POINTER(_vp)]),
     "cora_b200_sht_plan_destroy": (_i, [_vp]),
     "cora_b200_alm2map_workspace_bytes": (_ll, [_vp, _i, _i]),
@@ -29,11 +33,11 @@ SIGNATURES = {
     "cora_b200_alm2map_spin2": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _vp, _ll, _vp]),
     "cora_b200_alm_panel_to_dense": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
     "cora_b200_alm_dense_to_panel": (_i, [_vp, _i, _i, _vp, _ll, _i, _vp]),
-    "cora_b200_cl_fill_sck": (_i, [_d, _d, _d, _d, _d, _d, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "cora_b200_cl_fill_sck": (_i, [_d, _d, _d, _d, _d, _d, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "cora_b200_ps_table_21cm": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp, _ll, _vp]),
     "cora_b200_ps_table_21cm_bytes": (_ll, []),
     "cora_b200_ps_table_21cm_workspace_bytes": (_ll, []),
-    "cora_b200_cl_fill_21cm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "cora_b200_cl_fill_21cm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "cora_b200_cl_romberg_reduce": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "cora_b200_aps_sck_points": (_i, [_d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _ll, _vp, _vp]),
     "cora_b200_aps_21cm_points": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp]),
@@ -42,6 +46,8 @@ SIGNATURES = {
     "cora_b200_root_batched": (_i, [_vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _ll, _vp]),
     "cora_b200_draw_apply_workspace_bytes": (_ll, [_i, _i, _i]),
     "cora_b200_draw_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _ull, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _vp]),
+    "cora_b200_draw_apply_slabs": (_i, [_vp, _vp, _vp, _i, _i, _i, _ull, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "cora_b200_alm_slabs_to_panel": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _vp]),
 }
 
 _lib = None

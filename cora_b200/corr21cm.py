@@ -173,15 +173,19 @@ class Corr21cm(maps.Sky3d):
         return res if res.ndim else float(res)
 
     # fused clarray path (skysim.clarray looks this up); samples are frequencies (skysim.py:41-49)
-    def _b200_fill(self, nu_samples, w, l0, nl, nz, zint, out):
+    def _b200_fill_inputs(self, nu_samples, w):
+        """Device-resident inputs of the fill kernel: the DCT table (built once), the per-sample
+        vectors chi, b, f, pf, D (host cosmology, ``corr.py:944-951``) and the Romberg weights."""
         t = _dev.torch()
         z = NU21 / np.asarray(nu_samples, dtype=np.float64) - 1.0
         vec = _dev.to_device(self._sample_vectors(z), t.float64)  # [5, nz*zint]
-        wd = _dev.to_device(w, t.float64)
-        _lib.call("cora_b200_cl_fill_21cm", _lib.ptr(self.table()), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
-                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(l0), int(nl), int(nz), int(zint), _lib.ptr(out),
-                  _lib.stream_ptr())
-        t.cuda.current_stream().synchronize()
+        return self.table(), vec, _dev.to_device(w, t.float64)
+
+    def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None):
+        tab, vec, wd = inputs
+        _lib.call("cora_b200_cl_fill_21cm", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
+                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(l0), int(l_step), int(nl), int(nz), int(zint),
+                  _lib.ptr(out), _lib.stream_ptr(stream))
 
 
 class EoR21cm(Corr21cm):

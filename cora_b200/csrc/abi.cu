@@ -3,6 +3,8 @@
 #include "cora_b200.h"
 
 #include <cstdarg>
+#include <utility>
+#include <vector>
 
 namespace cb {
 
@@ -16,6 +18,35 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+// ---- per-kernel timing -----------------------------------------------------------------------
+bool g_timing_on = false;
+struct TimedSpan { int id; cudaEvent_t e0, e1; };
+static std::vector<TimedSpan> g_spans;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_free_events;
+static int g_open = -1;
+
+void timing_begin(int id, cudaStream_t st) {
+    TimedSpan s;
+    s.id = id;
+    if (!g_free_events.empty()) {
+        s.e0 = g_free_events.back().first; s.e1 = g_free_events.back().second;
+        g_free_events.pop_back();
+    } else {
+        cudaEventCreate(&s.e0);
+        cudaEventCreate(&s.e1);
+    }
+    cudaEventRecord(s.e0, st);
+    g_spans.push_back(s);
+    g_open = (int)g_spans.size() - 1;
+}
+void timing_end(cudaStream_t st) {
+    if (g_open >= 0) cudaEventRecord(g_spans[g_open].e1, st);
+    g_open = -1;
+}
+
+static const char* const g_kernel_names[K_COUNT] = {
+    "cl_fill", "root_prepare", "cholesky", "eigh_jacobi", "draw", "apply", "alm_layout", "sht_legendre", "sht_phase", "ps_table"};
 
 // 8 independent DMMA chains per warp; 256 FMA per DMMA per warp.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
@@ -39,6 +70,31 @@ using namespace cb;
 extern "C" int cora_b200_version(void) { return 100; }
 extern "C" const char* cora_b200_last_error(void) { return get_error(); }
 extern "C" long long cora_b200_launch_count(void) { return g_launches; }
+
+extern "C" int cora_b200_timing_enable(int on) {
+    // drop whatever was recorded and (re)arm
+    for (auto& s : g_spans) g_free_events.push_back({s.e0, s.e1});
+    g_spans.clear();
+    g_open = -1;
+    g_timing_on = on != 0;
+    return 0;
+}
+extern "C" int cora_b200_timing_kinds(void) { return K_COUNT; }
+extern "C" const char* cora_b200_timing_name(int id) { return (id >= 0 && id < K_COUNT) ? g_kernel_names[id] : ""; }
+extern "C" int cora_b200_timing_read(double* ms_out, long long* launches_out, int n) {
+    CB_REQUIRE(ms_out && launches_out && n >= K_COUNT, 1, "timing_read: need arrays of >= %d entries", (int)K_COUNT);
+    for (int i = 0; i < n; i++) { ms_out[i] = 0.0; launches_out[i] = 0; }
+    for (auto& s : g_spans) {
+        CB_CUDA(cudaEventSynchronize(s.e1));
+        float ms = 0.f;
+        CB_CUDA(cudaEventElapsedTime(&ms, s.e0, s.e1));
+        ms_out[s.id] += ms;
+        launches_out[s.id] += 1;
+        g_free_events.push_back({s.e0, s.e1});
+    }
+    g_spans.clear();
+    return 0;
+}
 
 extern "C" int cora_b200_fp64_peak(double ms_budget, double* tflops_out, void* stream) {
     CB_REQUIRE(tflops_out, 1, "fp64_peak: null output");

@@ -44,6 +44,7 @@ __device__ __forceinline__ double2 philox_cnormal(unsigned long long seed, unsig
 
 struct LDesc {
     long long goff;   // offset (complex elements) of this l's draws in the gauss buffer
+    long long orow;   // slab output: row of (l, m = 0); rows of one l are consecutive in m
     int l;            // global multipole
     int ld;           // row length (complex) of the gauss buffer for this l
 };
@@ -70,6 +71,10 @@ struct ApplyParams {
     const double2* G;
     double2* panel;
     long long panel_stride;
+    // slab output (multi-GPU send buffer): element (row, nu) at nu_base[nu] + row * nu_width[nu];
+    // null -> PANEL output
+    const long long* nu_base;
+    const int* nu_width;
     int nz, lmax, chan0, nu0, nnu;
 };
 
@@ -137,6 +142,15 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyParams P) {
     for (int nb = 0; nb < 4; nb++) {
         const int m = m0 + wn * 16 + 4 * nb + t;
         if (m > d.l) continue;
+        if (P.nu_base) {
+            const long long orow = d.orow + m;
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                const int nu = r0 + wm * 32 + 8 * mb + g;
+                if (nu < nz) P.panel[P.nu_base[nu] + orow * P.nu_width[nu]] = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            }
+            continue;
+        }
         const long long idx = (long long)m * (2 * lmax + 1 - m) / 2 + d.l;
         double2* row = P.panel + idx * P.panel_stride + P.chan0;
 #pragma unroll
@@ -155,10 +169,11 @@ extern "C" long long cora_b200_draw_apply_workspace_bytes(int nz, int lmax_in_ba
     return 16LL * nz * (long long)(lmax_in_batch + 1) * nl_batch + 64LL * nl_batch + 1024;
 }
 
-extern "C" int cora_b200_draw_apply(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz, int lmax,
-                                    unsigned long long seed, const void* gauss, long long gauss_ld, void* alm_panel,
-                                    long long panel_stride, int chan0, int nu0, int nnu, void* workspace,
-                                    long long ws_bytes, void* stream) {
+static int draw_apply_impl(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz, int lmax,
+                           unsigned long long seed, const void* gauss, long long gauss_ld, void* alm_panel,
+                           long long panel_stride, int chan0, int nu0, int nnu, const long long* row0_h,
+                           const long long* nu_base, const int* nu_width, void* workspace, long long ws_bytes,
+                           void* stream) {
     CB_REQUIRE(root && l_list_h && alm_panel && workspace, 1, "draw_apply: null argument");
     CB_REQUIRE(nl >= 1 && nz >= 1 && lmax >= 0 && nnu >= 1 && nu0 >= 0 && nu0 + nnu <= nz, 1, "draw_apply: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -177,6 +192,7 @@ extern "C" int cora_b200_draw_apply(const double* root, const int* l_list_h, con
         while (i1 < nl) {
             LDesc d;
             d.l = l_list_h[i1];
+            d.orow = row0_h ? row0_h[i1] : 0;
             if (gauss) { d.goff = (long long)i1 * nz * gauss_ld; d.ld = (int)gauss_ld; }
             else { d.goff = gneed; d.ld = d.l + 1; }
             long long add = gauss ? 0 : (long long)nz * d.ld;
@@ -197,7 +213,7 @@ extern "C" int cora_b200_draw_apply(const double* root, const int* l_list_h, con
         for (auto& d : hd) lbig = std::max(lbig, d.l);
         const double2* Gsrc = (const double2*)gauss;
         if (!gauss) {
-            draw_kernel<<<dim3(ceil_div(lbig + 1, 128), nz, nb), 128, 0, st>>>(dd, nz, seed, Gbuf);
+            { KTimer kt(K_DRAW, st); draw_kernel<<<dim3(ceil_div(lbig + 1, 128), nz, nb), 128, 0, st>>>(dd, nz, seed, Gbuf); }
             count_launch();
             CB_LAUNCH_CHECK();
             Gsrc = Gbuf;
@@ -207,13 +223,31 @@ extern "C" int cora_b200_draw_apply(const double* root, const int* l_list_h, con
         P.ldesc = dd;
         P.dense = dense_flag ? dense_flag + i0 : nullptr;
         P.G = Gsrc; P.panel = (double2*)alm_panel; P.panel_stride = panel_stride;
+        P.nu_base = nu_base; P.nu_width = nu_width;
         P.nz = nz; P.lmax = lmax; P.chan0 = chan0; P.nu0 = nu0; P.nnu = nnu;
         dim3 grid(ceil_div(lbig + 1, AP_TN / 2), ceil_div(nnu, AP_TM), nb);
-        apply_kernel<<<grid, 256, 0, st>>>(P);
+        { KTimer kt(K_APPLY, st); apply_kernel<<<grid, 256, 0, st>>>(P); }
         count_launch();
         CB_LAUNCH_CHECK();
         if (i1 < nl) CB_CUDA(cudaStreamSynchronize(st));   // workspace reuse
         i0 = i1;
     }
     return 0;
+}
+
+extern "C" int cora_b200_draw_apply(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz, int lmax,
+                                    unsigned long long seed, const void* gauss, long long gauss_ld, void* alm_panel,
+                                    long long panel_stride, int chan0, int nu0, int nnu, void* workspace,
+                                    long long ws_bytes, void* stream) {
+    return draw_apply_impl(root, l_list_h, dense_flag, nl, nz, lmax, seed, gauss, gauss_ld, alm_panel, panel_stride, chan0,
+                           nu0, nnu, nullptr, nullptr, nullptr, workspace, ws_bytes, stream);
+}
+
+extern "C" int cora_b200_draw_apply_slabs(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
+                                          int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
+                                          const long long* row0_h, const long long* nu_base, const int* nu_width,
+                                          void* send, void* workspace, long long ws_bytes, void* stream) {
+    CB_REQUIRE(row0_h && nu_base && nu_width, 1, "draw_apply_slabs: null slab description");
+    return draw_apply_impl(root, l_list_h, dense_flag, nl, nz, lmax, seed, gauss, gauss_ld, send, 0, 0, 0, nz, row0_h,
+                           nu_base, nu_width, workspace, ws_bytes, stream);
 }

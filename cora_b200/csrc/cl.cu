@@ -35,12 +35,12 @@ __global__ void sck_bbar_kernel(double alpha, double nu_ref, double zeta, const 
     bbar[(long long)i * nz + j] = acc;
 }
 
-__global__ void sck_scale_kernel(double A, double beta, double l_ref, const double* __restrict__ bbar, int l0, int nl,
-                                 long long nz2, double* __restrict__ out) {
+__global__ void sck_scale_kernel(double A, double beta, double l_ref, const double* __restrict__ bbar, int l0, int l_step,
+                                 int nl, long long nz2, double* __restrict__ out) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int li = blockIdx.y;
     if (e >= nz2) return;
-    const int l = l0 + li;
+    const int l = l0 + li * l_step;
     const double al = (l == 0) ? 0.0 : A * pow((double)l / l_ref, -beta);
     out[(long long)li * nz2 + e] = al * bbar[e];
 }
@@ -164,8 +164,8 @@ struct PairPre {
 __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict__ tab, const double* __restrict__ chi,
                                                         const double* __restrict__ bb, const double* __restrict__ ff,
                                                         const double* __restrict__ pf, const double* __restrict__ DD,
-                                                        const double* __restrict__ w, int l0, int nl, int nz, int zint,
-                                                        double* __restrict__ out) {
+                                                        const double* __restrict__ w, int l0, int l_step, int nl, int nz,
+                                                        int zint, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smraw[];
     PairPre* pre = (PairPre*)smraw;
     // decode lower-triangle pair index
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
     const double xscale = (double)(NKPERP - 1) / log10(KPERP_MAX / KPERP_MIN);
     const long long nz2 = (long long)nz * nz;
     for (int li = threadIdx.x; li < nl; li += blockDim.x) {
-        const int l = l0 + li;
+        const int l = l0 + li * l_step;
         const double lx = log10(l == 0 ? 1e-10 : (double)l);
         double acc = 0.0;
         for (int e = 0; e < npair; e++) {
@@ -305,18 +305,19 @@ __global__ void ps21_gather_kernel(const double* __restrict__ tab, const int* __
 using namespace cb;
 
 extern "C" int cora_b200_cl_fill_sck(double A, double beta, double l_ref, double alpha, double nu_ref, double zeta,
-                                     const double* nu_samples, const double* w, int l0, int nl, int nz, int zint,
-                                     double* out_cl, void* stream) {
+                                     const double* nu_samples, const double* w, int l0, int l_step, int nl, int nz,
+                                     int zint, double* out_cl, void* stream) {
     CB_REQUIRE(nu_samples && w && out_cl, 1, "cl_fill_sck: null argument");
-    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT, 1, "cl_fill_sck: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
+    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_sck: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
     cudaStream_t st = (cudaStream_t)stream;
+    KTimer kt(K_CL_FILL, st);
     double* bbar;
     CB_CUDA(cudaMallocAsync(&bbar, sizeof(double) * (size_t)nz * nz, st));
     sck_bbar_kernel<<<dim3(ceil_div(nz, 128), nz), 128, 0, st>>>(alpha, nu_ref, zeta, nu_samples, w, nz, zint, bbar);
     count_launch();
     CB_LAUNCH_CHECK();
     const long long nz2 = (long long)nz * nz;
-    sck_scale_kernel<<<dim3(ceil_div(nz2, 256), nl), 256, 0, st>>>(A, beta, l_ref, bbar, l0, nl, nz2, out_cl);
+    sck_scale_kernel<<<dim3(ceil_div(nz2, 256), nl), 256, 0, st>>>(A, beta, l_ref, bbar, l0, l_step, nl, nz2, out_cl);
     count_launch();
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaFreeAsync(bbar, st));
@@ -336,6 +337,7 @@ extern "C" int cora_b200_ps_table_21cm(const double* lnk_h, const double* lnp_h,
     CB_REQUIRE((NKPERP * 3) % DCT_ROWS == 0 && NKPAR % 256 == 0, 9, "ps_table_21cm: internal tiling");
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    KTimer kt(K_TABLE, st);
     double* pk = (double*)ws;
     double* ctab = pk + (long long)NKPERP * NKPAR * 3;
     double* knots = ctab + 2 * NKPAR;
@@ -355,15 +357,16 @@ extern "C" int cora_b200_ps_table_21cm(const double* lnk_h, const double* lnp_h,
 }
 
 extern "C" int cora_b200_cl_fill_21cm(const double* tab, const double* chi, const double* b, const double* f, const double* pf,
-                                      const double* D, const double* w, int l0, int nl, int nz, int zint, double* out_cl,
-                                      void* stream) {
+                                      const double* D, const double* w, int l0, int l_step, int nl, int nz, int zint,
+                                      double* out_cl, void* stream) {
     CB_REQUIRE(tab && chi && b && f && pf && D && w && out_cl, 1, "cl_fill_21cm: null argument");
-    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT, 1, "cl_fill_21cm: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
+    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_21cm: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
     const long long npairs = (long long)nz * (nz + 1) / 2;
     CB_REQUIRE(npairs < 2147483647LL, 3, "cl_fill_21cm: too many channel pairs");
     size_t smem = sizeof(PairPre) * (size_t)zint * zint;
     CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, l0, nl, nz, zint, out_cl);
+    KTimer kt(K_CL_FILL, (cudaStream_t)stream);
+    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl);
     count_launch();
     CB_LAUNCH_CHECK();
     return 0;

@@ -44,6 +44,21 @@ const char* get_error();
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
+// ---- per-kernel device timing (cora_b200_timing_*): CUDA events recorded on the launching
+// stream around each kernel while enabled; bench.py derives roofline.achieved from these.
+enum KernelId {
+    K_CL_FILL = 0, K_ROOT_PREP, K_CHOLESKY, K_EIGH, K_DRAW, K_APPLY, K_LAYOUT, K_LEGENDRE, K_PHASE, K_TABLE, K_COUNT
+};
+extern bool g_timing_on;
+void timing_begin(int id, cudaStream_t st);
+void timing_end(cudaStream_t st);
+struct KTimer {
+    cudaStream_t st;
+    bool on;
+    KTimer(int id, cudaStream_t s) : st(s), on(g_timing_on) { if (on) timing_begin(id, st); }
+    ~KTimer() { if (on) timing_end(st); }
+};
+
 // ---- device helpers -----------------------------------------------------------------------
 // FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
 // Fragment ownership (lane = 4*g + t): A[g][t], B[t][g], C[g][2t], C[g][2t+1].

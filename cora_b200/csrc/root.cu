@@ -316,10 +316,10 @@ extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double j
     double* GV = (double*)ws;
     long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
 
-    root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax);
+    { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax); }
     count_launch();
     CB_LAUNCH_CHECK();
-    cholesky_kernel<<<nl, CH_THREADS, 0, st>>>(root, nz, fail);
+    { KTimer kt(K_CHOLESKY, st); cholesky_kernel<<<nl, CH_THREADS, 0, st>>>(root, nz, fail); }
     count_launch();
     CB_LAUNCH_CHECK();
     root_flags_kernel<<<1, 32, 0, st>>>(fail, nl, nz, used_eigh, num_pos, fail_list, nfail_d);
@@ -335,6 +335,7 @@ extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double j
         const int nb = (int)std::min<long long>(slots, nfail - f0);
         double* G = GV;
         double* V = GV + (long long)nb * nz * nz;
+        KTimer kt(K_EIGH, st);
         jacobi_init_kernel<<<nb, 256, 0, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, G, V);
         count_launch();
         CB_LAUNCH_CHECK();

@@ -703,13 +703,14 @@ static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* a
     CB_CUDA(cudaFuncSetAttribute(sht_legendre_kernel<SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
     CB_REQUIRE(grid < 2147483647LL, 3, "alm2map: Legendre grid too large (%lld)", grid);
-    sht_legendre_kernel<SPIN><<<(unsigned)grid, LEG_THREADS, smem, st>>>(P);
+    { KTimer kt(K_LEGENDRE, st); sht_legendre_kernel<SPIN><<<(unsigned)grid, LEG_THREADS, smem, st>>>(P); }
     count_launch();
     CB_LAUNCH_CHECK();
     return 0;
 }
 
 static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, cudaStream_t st) {
+    KTimer kt(K_PHASE, st);
     for (const auto& pc : pl->classes) {
         PhaseParams Q;
         Q.F = F; Q.map = map; Q.npix = pl->npix; Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
@@ -747,8 +748,9 @@ extern "C" int cora_b200_alm2map(void* plan, const void* alm, int layout, long l
         if (layout == CORA_B200_ALM_PACKED) {
             double2* T = (double2*)(ws + (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16 * nbmax);
             dim3 grid(ceil_div(pl->nalm, 32), ceil_div(nb, 32));
-            alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)alm + (long long)c0 * alm_stride, alm_stride, nb,
-                                                                pl->nalm, T, nb);
+            { KTimer kt(K_LAYOUT, st);
+              alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)alm + (long long)c0 * alm_stride, alm_stride, nb,
+                                                                pl->nalm, T, nb); }
             count_launch();
             CB_LAUNCH_CHECK();
             almT = T; stride = nb; chan0 = 0;
@@ -786,10 +788,11 @@ extern "C" int cora_b200_alm2map_spin2(void* plan, const void* almE, const void*
             double2* TE = (double2*)(ws + 2 * fbytes * nbmax);
             double2* TB = TE + pl->nalm * nbmax;
             dim3 grid(ceil_div(pl->nalm, 32), ceil_div(nb, 32));
-            alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)almE + (long long)c0 * alm_stride, alm_stride, nb,
+            { KTimer kt(K_LAYOUT, st);
+              alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)almE + (long long)c0 * alm_stride, alm_stride, nb,
                                                                 pl->nalm, TE, nb);
-            alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)almB + (long long)c0 * alm_stride, alm_stride, nb,
-                                                                pl->nalm, TB, nb);
+              alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)almB + (long long)c0 * alm_stride, alm_stride, nb,
+                                                                pl->nalm, TB, nb); }
             count_launch(2);
             CB_LAUNCH_CHECK();
             pE = TE; pB = TB; stride = nb; chan0 = 0;

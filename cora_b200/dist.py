@@ -1,0 +1,236 @@
+"""Multi-GPU ``mkfullsky``: l-sharded fill / root / draw+apply, one all-to-all, channel-sharded SHT.
+
+This is the reference's own MPI design (``cora/core/skysim.py:97-134`` over ``caput.mpiarray``):
+``alm_array`` is distributed over l (``:108-110``), each rank roots and applies its local l's
+(``:114-121``), ``redistribute(axis=0)`` transposes to a frequency distribution (``:128``) and
+every rank transforms its own channels (``:130-134``).  Here: one process per GPU,
+``torch.distributed`` (NCCL over NVLink; gloo in the CPU tests) for the single exchange step,
+and no other data-path collective.
+
+Differences from the reference, by design:
+
+* l is dealt to ranks **interleaved** (``l mod G``) by default, not in contiguous blocks: the
+  apply cost grows like ``l + 1`` so caput's block split is 1.9x imbalanced at G = 8
+  (``partition="block"`` reproduces caput's split).
+* the exchanged alm are triangular-packed rows ``(l, m <= l)`` -- half the bytes of the
+  reference's dense ``L x L`` squares -- and the apply kernel writes them straight into the
+  per-destination send slabs (``cora_b200_draw_apply_slabs``).
+* Philox draws are keyed by ``(l, m, nu)``, so the maps do not depend on G (the reference's
+  pipeline caller seeds every rank identically).
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _dev, _lib, hputil, nputil
+
+
+def block_partition(n, size, rank):
+    """caput.mpiarray's contiguous split: the first ``n % size`` ranks get one extra item."""
+    base, rem = divmod(n, size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class ShardPlan(object):
+    """Who owns which l and which channel, and where every alm row sits in the exchange buffers.
+
+    Send buffer of rank r (complex elements): one slab per destination s, slab s =
+    ``[rows_r][cb_s]`` at offset ``rows_r * chan_lo[s]``; ``rows_r = sum_{l in l_list[r]} (l + 1)``,
+    rows ordered by (position of l in ``l_list[r]``, m).  Receive buffer of rank s: one slab per
+    source r, ``[rows_r][cb_s]`` at offset ``cb_s * sum_{r' < r} rows_r'``.
+    """
+
+    def __init__(self, lmax, nz, size, partition="interleaved"):
+        self.lmax, self.nz, self.size, self.partition = int(lmax), int(nz), int(size), partition
+        L = self.lmax + 1
+        if partition == "interleaved":
+            self.l_lists = [np.arange(r, L, size, dtype=np.int32) for r in range(size)]
+        elif partition == "block":
+            self.l_lists = [np.arange(*block_partition(L, size, r), dtype=np.int32) for r in range(size)]
+        else:
+            raise ValueError("partition must be 'interleaved' or 'block'")
+        bounds = [block_partition(self.nz, size, s) for s in range(size)]
+        self.chan_lo = np.array([b[0] for b in bounds], dtype=np.int64)
+        self.chan_hi = np.array([b[1] for b in bounds], dtype=np.int64)
+        self.cb = self.chan_hi - self.chan_lo
+        self.rows = np.array([int((ll.astype(np.int64) + 1).sum()) for ll in self.l_lists], dtype=np.int64)
+        self.owner = np.empty(L, dtype=np.int64)      # rank owning l
+        self.row0 = np.empty(L, dtype=np.int64)       # row of (l, m=0) inside its owner's slabs
+        for r, ll in enumerate(self.l_lists):
+            self.owner[ll] = r
+            self.row0[ll] = np.concatenate([[0], np.cumsum(ll.astype(np.int64) + 1)[:-1]]) if len(ll) else []
+
+    # ---- sender side (rank r) -------------------------------------------------------
+    def send_splits(self, r):
+        """Complex elements sent to each destination."""
+        return [int(self.rows[r] * c) for c in self.cb]
+
+    def nu_tables(self, r):
+        """(nu_base[nz], nu_width[nz]) for ``cora_b200_draw_apply_slabs`` on rank r."""
+        base = np.empty(self.nz, dtype=np.int64)
+        width = np.empty(self.nz, dtype=np.int32)
+        for s in range(self.size):
+            lo, hi = int(self.chan_lo[s]), int(self.chan_hi[s])
+            base[lo:hi] = self.rows[r] * lo + np.arange(hi - lo)
+            width[lo:hi] = hi - lo
+        return base, width
+
+    def send_row0(self, r):
+        return np.ascontiguousarray(self.row0[self.l_lists[r]], dtype=np.int64)
+
+    # ---- receiver side (rank s) -----------------------------------------------------
+    def recv_splits(self, s):
+        return [int(self.rows[r] * self.cb[s]) for r in range(self.size)]
+
+    def l_offsets(self, s):
+        """Complex offset of row (l, m=0) in rank s's receive buffer, for every l."""
+        src_base = np.concatenate([[0], np.cumsum(self.rows)[:-1]]) * int(self.cb[s])
+        return np.ascontiguousarray(src_base[self.owner] + self.row0 * int(self.cb[s]), dtype=np.int64)
+
+    def nalm_total(self):
+        return int(self.rows.sum())
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def exchange(send, plan, rank, group=None):
+    """The one collective of the path: l-major slabs -> channel-major slabs
+    (``alm_array.redistribute(axis=0)``, ``skysim.py:128``).  ``send``: complex128 tensor
+    (CUDA under NCCL, CPU under gloo).  Returns the receive buffer."""
+    import torch
+
+    dist = _dist()
+    recv = torch.empty(sum(plan.recv_splits(rank)), dtype=send.dtype, device=send.device)
+    if plan.size == 1:
+        recv.copy_(send)
+        return recv
+    s_r, r_r = torch.view_as_real(send).reshape(-1), torch.view_as_real(recv).reshape(-1)
+    dist.all_to_all_single(r_r, s_r, output_split_sizes=[2 * n for n in plan.recv_splits(rank)],
+                           input_split_sizes=[2 * n for n in plan.send_splits(rank)], group=group)
+    return recv
+
+
+class ShardedSky(object):
+    """Per-rank state of the sharded generator: plan, device tables, fill inputs.
+
+    ``step()`` runs one full pass (fill -> root -> draw/apply -> all-to-all -> SHT) and returns
+    this rank's channels ``float64[cb, npix]`` as a CUDA tensor."""
+
+    def __init__(self, model, nside, frequencies, lmax=None, zromb=3, group=None, partition="interleaved",
+                 rank=None, size=None):
+        from . import skysim
+
+        t = _dev.torch()
+        dist = _dist()
+        self.group = group
+        if size is None:
+            size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if size > 1 else 0
+        self.rank, self.size = rank, size
+        self.model, self.nside = model, int(nside)
+        self.freq = np.asarray(frequencies, dtype=np.float64)
+        self.nz = len(self.freq)
+        self.lmax = 3 * self.nside - 1 if lmax is None else int(lmax)
+        self.plan = ShardPlan(self.lmax, self.nz, size, partition)
+        self.l_list = self.plan.l_lists[rank]
+        self.nl = len(self.l_list)
+        self.cb = int(self.plan.cb[rank])
+        self.npix = 12 * self.nside**2
+        za, self.zint = skysim._sample_frequencies(self.freq, zromb, None)
+        self.fill_inputs = model._b200_fill_inputs(za, skysim.romberg_weights(zromb))
+        base, width = self.plan.nu_tables(rank)
+        self.nu_base, self.nu_width = _dev.to_device(base, t.int64), _dev.to_device(width, t.int32)
+        self.l_off = _dev.to_device(self.plan.l_offsets(rank), t.int64)
+        self.row0 = self.plan.send_row0(rank)
+
+    def fill(self, out=None):
+        """This rank's C_l(nu, nu') rows, ``float64[nl, nz, nz]`` (``skysim.clarray`` for the local l's)."""
+        t = _dev.torch()
+        if out is None:
+            out = _dev.empty((self.nl, self.nz, self.nz), t.float64)
+        if self.plan.partition == "interleaved":
+            self.model._b200_fill(self.fill_inputs, int(self.l_list[0]) if self.nl else 0, self.size, self.nl, self.nz,
+                                  self.zint, out)
+        else:
+            self.model._b200_fill(self.fill_inputs, int(self.l_list[0]) if self.nl else 0, 1, self.nl, self.nz, self.zint, out)
+        return out
+
+    def alm_local(self, cla, seed=0, gauss=None, roots=None):
+        """root + draw/apply for the local l's -> send buffer (complex128, one slab per destination)."""
+        t = _dev.torch()
+        lib = _lib.load()
+        if roots is None:
+            root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16)
+        else:
+            root, used = _dev.to_device(roots, t.float64), None
+        send = _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128)
+        lmax_loc = int(self.l_list.max())
+        if gauss is None:
+            full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
+            one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
+            nbytes = min(full, max(one, _dev.free_bytes() - (2 << 30)))
+            gptr, gld = None, 0
+        else:
+            gauss = _dev.to_device(gauss, t.complex128)
+            nbytes = 64 * self.nl + 4096
+            gptr, gld = _lib.ptr(gauss), int(gauss.shape[-1])
+        ws = _dev.workspace(nbytes)
+        _lib.call("cora_b200_draw_apply_slabs", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
+                  self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(self.row0), _lib.ptr(self.nu_base),
+                  _lib.ptr(self.nu_width), _lib.ptr(send), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+        return send
+
+    def synthesize(self, recv, out=None):
+        """received slabs -> PANEL -> maps of this rank's channels."""
+        t = _dev.torch()
+        nalm = (self.lmax + 1) * (self.lmax + 2) // 2
+        panel = _dev.empty((nalm, self.cb), t.complex128)
+        _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(recv), _lib.ptr(self.l_off), self.lmax, self.cb, _lib.ptr(panel),
+                  self.cb, 0, _lib.stream_ptr())
+        return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out)
+
+    def step(self, seed=0, out=None):
+        cla = self.fill()
+        send = self.alm_local(cla, seed=seed)
+        del cla
+        recv = exchange(send, self.plan, self.rank, self.group)
+        del send
+        return self.synthesize(recv, out=out)
+
+
+def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, partition="interleaved", seed=0, gauss=None,
+                      roots=None, device_out=True):
+    """``mkfullsky`` for an l-distributed ``corr`` (the MPIArray branch of ``skysim.py:97-134``).
+
+    ``corr_local``: this rank's ``float64[nl_local, nz, nz]`` rows, for the l's of
+    ``ShardPlan(lmax, nz, G, partition).l_lists[rank]``.  Returns this rank's channels
+    ``float64[cb, npix]`` (the reference returns the frequency-distributed ``MPIArray``)."""
+    t = _dev.torch()
+    dist = _dist()
+    size = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if size > 1 else 0
+    nz = corr_local.shape[1]
+    if corr_local.shape[2] != nz:
+        raise Exception("Correlation matrix is incorrect shape.")
+
+    class _NoModel(object):
+        def _b200_fill_inputs(self, za, w):
+            return None
+
+    sh = ShardedSky(_NoModel(), nside, np.zeros(nz), lmax=lmax, zromb=0, group=group, partition=partition, rank=rank, size=size)
+    if l_list is not None and not np.array_equal(np.asarray(l_list), sh.l_list):
+        raise Exception("l_list does not match the %s partition of rank %d" % (partition, rank))
+    if corr_local.shape[0] != sh.nl:
+        raise Exception("Correlation matrix is incorrect shape.")
+    cla = _dev.to_device(corr_local, t.float64)
+    send = sh.alm_local(cla, seed=seed, gauss=gauss, roots=roots)
+    recv = exchange(send, sh.plan, rank, group)
+    sky = sh.synthesize(recv)
+    return sky if device_out else _dev.to_host(sky)

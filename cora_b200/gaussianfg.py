@@ -58,13 +58,15 @@ class ForegroundSCK(ForegroundMap):
         return self.angular_powerspectrum(self.l_0, nu1, nu2) / self.A
 
     # fused clarray path (skysim.clarray looks this up)
-    def _b200_fill(self, nu_samples, w, l0, nl, nz, zint, out):
+    def _b200_fill_inputs(self, nu_samples, w):
+        """Device-resident inputs of the fill kernel (sample frequencies, Romberg weights)."""
         t = _dev.torch()
-        ns = _dev.to_device(nu_samples, t.float64)
-        wd = _dev.to_device(w, t.float64)
-        _lib.call("cora_b200_cl_fill_sck", *self._params(), _lib.ptr(ns), _lib.ptr(wd), int(l0), int(nl), int(nz),
-                  int(zint), _lib.ptr(out), _lib.stream_ptr())
-        t.cuda.current_stream().synchronize()
+        return _dev.to_device(nu_samples, t.float64), _dev.to_device(w, t.float64)
+
+    def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None):
+        ns, wd = inputs
+        _lib.call("cora_b200_cl_fill_sck", *self._params(), _lib.ptr(ns), _lib.ptr(wd), int(l0), int(l_step), int(nl),
+                  int(nz), int(zint), _lib.ptr(out), _lib.stream_ptr(stream))
 
 
 class Synchrotron(ForegroundSCK):

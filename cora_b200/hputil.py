@@ -160,4 +160,4 @@ def sphtrans_inv_sky(alm, nside, device_out=False):
         sky[:, 2] = u
     if device_out:
         return sky
-    return sky.cpu().numpy()
+    return _dev.to_host(sky)

@@ -62,7 +62,14 @@ class Sky3d(Map3d):
         """Create a map of the unpolarised sky, ``float64[nfreq, npix]``."""
         lmax = 3 * self.nside - 1
         cla = skysim.clarray(self.angular_powerspectrum, lmax, self.nu_pixels, zromb=self.oversample, device_out=True)
-        return self.mean_nu(self.nu_pixels)[:, np.newaxis] + skysim.mkfullsky(cla, self.nside)
+        mean = np.asarray(self.mean_nu(np.asarray(self.nu_pixels, dtype=np.float64)), dtype=np.float64)
+        if not mean.any():
+            return skysim.mkfullsky(cla, self.nside)
+        from . import _dev
+
+        sky = skysim.mkfullsky(cla, self.nside, device_out=True)
+        sky += _dev.to_device(mean, sky.dtype)[:, None]  # the reference's host-side broadcast add (maps.py:235)
+        return _dev.to_host(sky)
 
     def getpolsky(self):
         """Stokes I, Q, U, V maps ``[nfreq, 4, npix]`` (Q = U = V = 0 for an unpolarised model)."""

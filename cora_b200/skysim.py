@@ -70,8 +70,8 @@ def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
 
     if fused is not None:
         out = _dev.empty((lmax + 1, nz, nz), t.float64)
-        fused(za, w, 0, lmax + 1, nz, zint, out)
-        return out if device_out else out.cpu().numpy()
+        fused(owner._b200_fill_inputs(za, w), 0, 1, lmax + 1, nz, zint, out)
+        return out if device_out else _dev.to_host(out)
 
     if zromb == 0:
         res = aps(np.arange(lmax + 1)[:, np.newaxis, np.newaxis], zarray[np.newaxis, :, np.newaxis],
@@ -87,7 +87,7 @@ def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
         _lib.call("cora_b200_cl_romberg_reduce", _lib.ptr(blk), _lib.ptr(wd), len(lsec), nz, zint,
                   _lib.ptr(out[l_first:]), _lib.stream_ptr())
     t.cuda.current_stream().synchronize()
-    return out if device_out else out.cpu().numpy()
+    return out if device_out else _dev.to_host(out)
 
 
 def draw_apply_device(root, l_list, dense_flag, nz, lmax, panel, seed=0, gauss=None, chan0=0, nu0=0, nnu=None,
@@ -174,7 +174,7 @@ def mkfullsky(corr, nside, alms=False, rng=None, *, seed=None, roots=None, gauss
     if alms:
         dense = hputil.panel_to_dense(panel, maxl, numz)  # [numz, L, L]
         out = dense.reshape(numz, 1, L, L)
-        return out if device_out else out.cpu().numpy()
+        return out if device_out else _dev.to_host(out)
 
     sky = hputil.alm2map_device(panel, nside, maxl, _lib.ALM_PANEL, numz, numz)
-    return sky if device_out else sky.cpu().numpy()
+    return sky if device_out else _dev.to_host(sky)

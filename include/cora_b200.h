@@ -32,6 +32,16 @@ long long cora_b200_launch_count(void);
  * FP64 entry).  `ms_budget`: approximate run time of the probe. */
 int cora_b200_fp64_peak(double ms_budget, double* tflops_out, void* stream);
 
+/* Per-kernel device timing.  While enabled, every kernel family the library launches is
+ * bracketed by CUDA events on its launching stream; timing_read synchronises, returns the
+ * summed milliseconds and launch counts per family (arrays of >= cora_b200_timing_kinds()
+ * entries, names from cora_b200_timing_name) and clears the record.  bench.py computes
+ * roofline.achieved from these. */
+int cora_b200_timing_enable(int on);
+int cora_b200_timing_kinds(void);
+const char* cora_b200_timing_name(int id);
+int cora_b200_timing_read(double* ms_out_h, long long* launches_out_h, int n);
+
 /* ------------------------------------------------------------------ alm layouts -- */
 /* PACKED: healpy order per channel, alm[chan * stride + idx(l,m)],
  *         idx(l,m) = m (2 lmax + 1 - m)/2 + l          (cora/util/hputil.py:124-152)
@@ -76,9 +86,10 @@ int cora_b200_alm_dense_to_panel(const void* dense, int nchan, int lmax, void* a
  * replaces: skysim.clarray(ForegroundSCK.angular_powerspectrum, ...)
  * (cora/core/skysim.py:10-69 + cora/foreground/gaussianfg.py:107-130).
  * nu_samples[nz * zint]: per-channel sample frequencies; w[zint]: Romberg weights already
- * divided so that sum_ab w_a w_b = 1; out_cl[nl][nz][nz] for l = l0 .. l0+nl-1.          */
+ * divided so that sum_ab w_a w_b = 1; out_cl[nl][nz][nz] for l = l0 + i * l_step, i < nl
+ * (l_step = 1: a contiguous block; l_step = G: the interleaved l-shard of one of G GPUs). */
 int cora_b200_cl_fill_sck(double A, double beta, double l_ref, double alpha, double nu_ref, double zeta,
-                          const double* nu_samples, const double* w, int l0, int nl, int nz, int zint,
+                          const double* nu_samples, const double* w, int l0, int l_step, int nl, int nz, int zint,
                           double* out_cl, void* stream);
 
 /* 21cm: one-off P(k_perp, k_par) table -> three DCT-I tables (dd, dv, vv), stored
@@ -98,8 +109,8 @@ long long cora_b200_ps_table_21cm_workspace_bytes(void);
  * Per-sample vectors (length nz*zint, host-computed exactly as the reference does):
  * chi (comoving distance), b, f, pf, D.                                                  */
 int cora_b200_cl_fill_21cm(const double* tab, const double* chi, const double* b, const double* f,
-                           const double* pf, const double* D, const double* w, int l0, int nl, int nz,
-                           int zint, double* out_cl, void* stream);
+                           const double* pf, const double* D, const double* w, int l0, int l_step, int nl,
+                           int nz, int zint, double* out_cl, void* stream);
 
 /* Romberg average of a block evaluated by a generic host callable:
  * in[nl][nz][zint][nz][zint] -> out[nl][nz][nz]  (the two scipy.integrate.romb calls and the
@@ -151,6 +162,26 @@ int cora_b200_draw_apply(const double* root, const int* l_list_h, const int* den
                          int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
                          void* alm_panel, long long panel_stride, int chan0, int nu0, int nnu,
                          void* workspace, long long ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU --- */
+/* The l-sharded half of mkfullsky on one GPU of G (cora/core/skysim.py:108-121 for the local
+ * l's of alm_array.enumerate(axis=2)), writing straight into the send buffer of the l -> nu
+ * all-to-all (alm_array.redistribute(axis=0), cora/core/skysim.py:128): element (l, m, nu)
+ * goes to send[nu_base[nu] + (row0_h[i] + m) * nu_width[nu]] (complex elements), i = position
+ * of l in l_list_h.  With nu_base[nu] = slab_offset(dest(nu)) + (nu - first_nu(dest)) and
+ * nu_width[nu] = channels owned by dest(nu), the buffer is one contiguous [rows][channels]
+ * slab per destination GPU.  nu_base / nu_width: device arrays [nz]; row0_h: host [nl].      */
+int cora_b200_draw_apply_slabs(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
+                               int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
+                               const long long* row0_h, const long long* nu_base, const int* nu_width,
+                               void* send, void* workspace, long long ws_bytes, void* stream);
+
+/* After the all-to-all: receive buffer -> PANEL rows idx(l, m) of this GPU's `nchan` channels.
+ * l_off[lmax+1] (device): complex offset of row (l, m = 0) in `recv`; the rows m = 0..l of one
+ * l are consecutive, nchan channels each (the unpack half of redistribute + pack_alm,
+ * cora/core/skysim.py:128 + cora/util/hputil.py:124-152).                                   */
+int cora_b200_alm_slabs_to_panel(const void* recv, const long long* l_off, int lmax, int nchan, void* alm_panel,
+                                 long long panel_stride, int chan0, void* stream);
 
 #ifdef __cplusplus
 }
