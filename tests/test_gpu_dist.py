@@ -49,7 +49,10 @@ def test_sharded_equals_single(size, partition):
         sky = sh.synthesize(recvs[s])
         lo, hi = int(sh.plan.chan_lo[s]), int(sh.plan.chan_hi[s])
         assert sky.shape == (hi - lo, 12 * nside**2)
-        np.testing.assert_array_equal(sky.cpu().numpy(), ref[lo:hi].cpu().numpy())
+        # not bit-equal: the phase stage transforms channels in pairs, and the pairing follows the
+        # channel offset inside each rank's block
+        want = ref[lo:hi].cpu().numpy()
+        np.testing.assert_allclose(sky.cpu().numpy(), want, rtol=0, atol=1e-13 * np.abs(want).max())
 
 
 def test_sharded_injected_draws_match_oracle():
