@@ -157,8 +157,9 @@ constexpr int LEG_THREADS = 256;
 constexpr int LEG_WARPS = 8;
 constexpr int LEG_RT = 256;   // north rings per CTA (one per thread)
 constexpr int LEG_NCH = 16;   // complex channels per CTA  (32 real columns = 4 n8 blocks)
-constexpr int LEG_KC = 32;    // l's per alm chunk
-constexpr int LEG_ALD = 36;   // As[8][36]: (par*4+t)*36 + ring -> conflict-free LDS.64 per half-warp
+constexpr int LEG_KC = 64;    // l's per alm chunk
+constexpr int LEG_GPC = LEG_KC / 8;   // 8-l groups per chunk
+constexpr int LEG_ALD = 36;   // A tile [8][36]: (par*4+t)*36 + ring -> conflict-free LDS.64 per half-warp
 constexpr int LEG_BLD = 34;   // Bs[KC][34]: (2t+par)*34 + col
 
 struct LegParams {
@@ -181,23 +182,37 @@ __device__ __forceinline__ void norm_frexp(double& m, long long& e) {
     e += ee;
 }
 
+// warp-uniformly predicated DMMA: a dead 8-ring block costs an issue slot, not pipe time
+__device__ __forceinline__ void dmma884_p(double& c0, double& c1, double a, double b, int pred) {
+    asm("{\n .reg .pred p;\n setp.ne.s32 p, %4, 0;\n"
+        " @p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n}\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b), "r"(pred));
+}
+
 // SPIN = 0: scalar synthesis, 16 complex channels per CTA (32 real GEMM columns).
 // SPIN = 2: (E,B) -> (Q,U) with the HEALPix X1/X2 functions, 8 channels per
 //   CTA; GEMM columns per channel are (Q_re, Q_im, U_re, U_im) and the K dimension is the
 //   concatenation [X1 | X2] against B1 = (aE_re, aE_im, aB_re, aB_im), B2 = (-aB_im, aB_re,
 //   aE_im, -aE_re), so Q = -(X1 aE + i X2 aB), U = -(X1 aB - i X2 aE) accumulate in place.
 //   X2 has the opposite theta-parity of X1, so it feeds the other parity accumulator.
+//
+// Schedule.  The l range of one m is walked in groups of 8.  Each warp owns 32 rings (four
+// octets dealt round-robin over the warps so that the polar, late-starting rings are spread
+// evenly) and is software-pipelined: while the DMMAs of group g run from A-tile buffer g&1,
+// the lane's recurrence for group g+1 fills buffer (g+1)&1 in the same basic block, so the
+// dependent FP64 chain hides in the DMMA issue gaps.  The scale exponent is examined once per
+// group; a lane is "live" for a whole group, and 8-ring blocks with no live lane are predicated
+// off (whole warps: branched over).
 template <int SPIN>
 __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams P) {
     extern __shared__ __align__(16) double smem[];
     constexpr int NCH = (SPIN == 0) ? LEG_NCH : LEG_NCH / 2;   // channels per CTA
     constexpr int AROWS = (SPIN == 0) ? 8 : 16;
-    double* c1 = smem;                         // [Lpad]  a_l
-    double* c2 = c1 + P.Lpad;                  // [Lpad]  a_l / a_{l-1}
-    double* cn = c2 + P.Lpad;                  // [Lpad]  spin 2: 2 n_l
-    double* cg = cn + (SPIN ? P.Lpad : 0);     // [Lpad]  spin 2: 2 n_l g_lm
-    double* Bs = cg + (SPIN ? P.Lpad : 0);     // [2][KC][BLD]
-    double* As = Bs + 2 * LEG_KC * LEG_BLD;    // [WARPS][AROWS][ALD]
+    double2* cc = (double2*)smem;                              // [Lpad]  (a_l, a_l / a_{l-1})
+    double2* cs = cc + P.Lpad;                                 // [Lpad]  spin 2: (2 n_l, 2 n_l g_lm)
+    double* Bs = (double*)(cs + (SPIN ? P.Lpad : 0));          // [2][KC][BLD]
+    double* As = Bs + 2 * LEG_KC * LEG_BLD;                    // [WARPS][2][AROWS][ALD]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -220,21 +235,19 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
                 r = a / ap;
             }
         }
-        c1[k] = a;
-        c2[k] = r;
+        cc[k] = make_double2(a, r);
         if (SPIN) {
             double tn = 0.0, tg = 0.0;
             if (k < nk && m + k >= 2) {
                 tn = 2.0 / sqrt((l + 2.0) * (l + 1.0) * l * (l - 1.0));
                 tg = tn * sqrt((2.0 * l + 1.0) / (2.0 * l - 1.0) * (l * l - mm * mm));
             }
-            cn[k] = tn;
-            cg[k] = tg;
+            cs[k] = make_double2(tn, tg);
         }
     }
 
-    // ring owned by this lane
-    const int rn = rb * LEG_RT + warp * 32 + lane;   // north ring index (ring number rn+1)
+    // ring owned by this lane: octet (lane/8)*8 + warp of the CTA's 32 octets
+    const int rn = rb * LEG_RT + (((lane >> 3) * 8 + warp) << 3) + (lane & 7);   // north ring index (ring number rn+1)
     const bool ring_ok = rn < P.nrn;
     double x = 0.0, p_cur = 0.0, p_prev = 0.0;
     double is2 = 0.0, cs2 = 0.0;   // spin 2: 1/sin^2, cos/sin^2
@@ -276,9 +289,10 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
     // alm chunk loader: rows l = m + kc + j (j < KC); 16 x 16-byte pieces per row
     const long long row0 = (long long)m * (2 * lmax + 1 - m) / 2 + m;   // idx(l=m, m)
     const int nchunk = (nk + LEG_KC - 1) / LEG_KC;
+    const int ngroups = (nk + 7) / 8;
     auto load_chunk = [&](int ck, int buf) {
 #pragma unroll
-        for (int qd = 0; qd < 2; qd++) {
+        for (int qd = 0; qd < LEG_KC * 16 / LEG_THREADS; qd++) {
             int el = tid + qd * LEG_THREADS;
             int j = el >> 4, c = el & 15;
             int k = ck * LEG_KC + j;
@@ -293,81 +307,105 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
         cp_async_commit();
     };
 
-    double* Aw = As + warp * AROWS * LEG_ALD;
+    // 8 recurrence steps starting at k = kbase, emitted into A-tile buffer Ab (rows split by l parity).
+    // Returns the ballot of lanes that are live (unscaled) for this group.
+    auto recur8 = [&](double* Ab, int kbase) -> unsigned {
+        const bool live = (e == 0);
+        double2 c[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[j] = cc[kbase + 1 + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int arow = (j & 1) * 4 + (j >> 1);
+            if (SPIN == 0) {
+                Ab[arow * LEG_ALD + lane] = live ? p_cur : 0.0;
+            } else {
+                const double2 sc = cs[kbase + j];
+                const double l = (double)(m + kbase + j), mm = (double)m;
+                const double tn = sc.x, tg = sc.y;
+                const double al = tn * (l - mm * mm), be = 0.5 * tn * l * (l - 1.0), de = tn * mm * (l - 1.0);
+                const double x1 = -(al * is2 + be) * p_cur + tg * cs2 * p_prev;
+                const double x2 = -de * cs2 * p_cur + mm * tg * is2 * p_prev;
+                Ab[arow * LEG_ALD + lane] = live ? x1 : 0.0;
+                Ab[(8 + arow) * LEG_ALD + lane] = live ? x2 : 0.0;
+            }
+            const double pn = fma(c[j].x * x, p_cur, -c[j].y * p_prev);
+            p_prev = p_cur;
+            p_cur = pn;
+        }
+        if (e < 0 && ((__double2hiint(p_cur) >> 20) & 0x7ff) > 1023 + 128) {
+            p_cur *= 0x1p-256;
+            p_prev *= 0x1p-256;
+            e += 256;
+        }
+        return __ballot_sync(0xffffffffu, live);
+    };
+
+    double* Aw = As + warp * 2 * AROWS * LEG_ALD;
     load_chunk(0, 0);
     __syncthreads();   // coefficient arrays visible
+    unsigned bal = recur8(Aw, 0);
 
     // spin 2: B2 fragment = +-B1 at a permuted column inside each group of four
     const int gperm = (g & 4) + 3 - (g & 3);
     const double gsign = ((g & 3) == 0 || (g & 3) == 3) ? -1.0 : 1.0;
 
-    int k = 0;   // next k to emit
+    int gi = 0;   // group being contracted
     for (int ck = 0; ck < nchunk; ck++) {
-        const int buf = ck & 1;
         cp_async_wait<0>();
         __syncthreads();
-        if (ck + 1 < nchunk) load_chunk(ck + 1, buf ^ 1);
-        const double* Bb = Bs + (size_t)buf * LEG_KC * LEG_BLD;
+        if (ck + 1 < nchunk) load_chunk(ck + 1, (ck + 1) & 1);
+        const double* Bb = Bs + (size_t)(ck & 1) * LEG_KC * LEG_BLD;
+        const int gend = min(ngroups, (ck + 1) * LEG_GPC);
 #pragma unroll 1
-        for (int grp = 0; grp < LEG_KC / 8; grp++) {
-            // ---- 8 recurrence steps, emit into the warp-private tile (parity-split rows)
+        for (; gi < gend; gi++) {
+            __syncwarp();   // buffer gi&1 (written one iteration ago by every lane) is visible
+            const double* Ac = Aw + (gi & 1) * AROWS * LEG_ALD;
+            double* An = Aw + ((gi + 1) & 1) * AROWS * LEG_ALD;
+            const int grp = gi - ck * LEG_GPC;
+            unsigned bal_next;
+            if (bal) {
+                int pm[4];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool live = (e == 0);
-                const int arow = (j & 1) * 4 + (j >> 1);
-                if (SPIN == 0) {
-                    Aw[arow * LEG_ALD + lane] = live ? p_cur : 0.0;
-                } else {
-                    const double l = (double)(m + k), mm = (double)m;
-                    const double tn = cn[k], tg = cg[k];
-                    const double al = tn * (l - mm * mm), be = 0.5 * tn * l * (l - 1.0), de = tn * mm * (l - 1.0);
-                    const double x1 = -(al * is2 + be) * p_cur + tg * cs2 * p_prev;
-                    const double x2 = -de * cs2 * p_cur + mm * tg * is2 * p_prev;
-                    Aw[arow * LEG_ALD + lane] = live ? x1 : 0.0;
-                    Aw[(8 + arow) * LEG_ALD + lane] = live ? x2 : 0.0;
-                }
-                double cc1 = c1[k + 1], cc2 = c2[k + 1];
-                double pn = fma(cc1 * x, p_cur, -cc2 * p_prev);
-                p_prev = p_cur;
-                p_cur = pn;
-                if (e < 0 && fabs(p_cur) > 0x1p128) {
-                    p_cur *= 0x1p-256;
-                    p_prev *= 0x1p-256;
-                    e += 256;
-                }
-                k++;
-            }
-            const bool active = __any_sync(0xffffffffu, e == 0);
-            __syncwarp();
-            if (active) {
+                for (int mb = 0; mb < 4; mb++) pm[mb] = (int)((bal >> (8 * mb)) & 0xffu);
+                double af[2][4], bf[2][4];
 #pragma unroll
                 for (int par = 0; par < 2; par++) {
-                    double af[4], bf[4];
 #pragma unroll
-                    for (int mb = 0; mb < 4; mb++) af[mb] = Aw[(par * 4 + t) * LEG_ALD + 8 * mb + g];
+                    for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(par * 4 + t) * LEG_ALD + 8 * mb + g];
 #pragma unroll
-                    for (int nb = 0; nb < 4; nb++) bf[nb] = Bb[(grp * 8 + 2 * t + par) * LEG_BLD + 8 * nb + g];
+                    for (int nb = 0; nb < 4; nb++) bf[par][nb] = Bb[(grp * 8 + 2 * t + par) * LEG_BLD + 8 * nb + g];
+                }
+                bal_next = recur8(An, (gi + 1) * 8);
+#pragma unroll
+                for (int par = 0; par < 2; par++)
 #pragma unroll
                     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
                         for (int nb = 0; nb < 4; nb++)
-                            dmma884(acc[par][mb][nb][0], acc[par][mb][nb][1], af[mb], bf[nb]);
-                    if (SPIN) {
-                        // X2 rows of l-parity `par` have theta-parity 1-par
+                            dmma884_p(acc[par][mb][nb][0], acc[par][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
+                if (SPIN) {
+                    // X2 rows of l-parity `par` have theta-parity 1-par
 #pragma unroll
-                        for (int mb = 0; mb < 4; mb++) af[mb] = Aw[(8 + par * 4 + t) * LEG_ALD + 8 * mb + g];
+                    for (int par = 0; par < 2; par++) {
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(8 + par * 4 + t) * LEG_ALD + 8 * mb + g];
 #pragma unroll
                         for (int nb = 0; nb < 4; nb++)
-                            bf[nb] = gsign * Bb[(grp * 8 + 2 * t + par) * LEG_BLD + 8 * nb + gperm];
+                            bf[par][nb] = gsign * Bb[(grp * 8 + 2 * t + par) * LEG_BLD + 8 * nb + gperm];
+                    }
+#pragma unroll
+                    for (int par = 0; par < 2; par++)
 #pragma unroll
                         for (int mb = 0; mb < 4; mb++)
 #pragma unroll
                             for (int nb = 0; nb < 4; nb++)
-                                dmma884(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[mb], bf[nb]);
-                    }
+                                dmma884_p(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
                 }
+            } else {
+                bal_next = recur8(An, (gi + 1) * 8);
             }
-            __syncwarp();
+            bal = bal_next;
         }
     }
 
@@ -376,7 +414,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
     const int nring_tot = 4 * P.nside - 1;
 #pragma unroll
     for (int mb = 0; mb < 4; mb++) {
-        const int rr = rb * LEG_RT + warp * 32 + 8 * mb + g;   // north ring index
+        const int rr = rb * LEG_RT + ((mb * 8 + warp) << 3) + g;   // north ring index
         if (rr >= P.nrn) continue;
         const int r_n = rr;                       // ring array index of the north ring
         const int r_s = nring_tot - 1 - rr;       // mirror ring
@@ -697,8 +735,8 @@ static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* a
     P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
     P.nrb = ceil_div(pl->nrn, LEG_RT);
     P.ncb = ceil_div(nb, SPIN ? LEG_NCH / 2 : LEG_NCH);
-    P.Lpad = ((pl->lmax + 1 + LEG_KC) / LEG_KC + 1) * LEG_KC + 8;
-    size_t smem = sizeof(double) * ((SPIN ? 4 : 2) * (size_t)P.Lpad + 2 * LEG_KC * LEG_BLD + LEG_WARPS * (SPIN ? 16 : 8) * LEG_ALD);
+    P.Lpad = ((pl->lmax + 1 + 7) / 8 + 2) * 8 + 8;   // recur8 runs one group past the end
+    size_t smem = sizeof(double) * ((SPIN ? 4 : 2) * (size_t)P.Lpad + 2 * LEG_KC * LEG_BLD + LEG_WARPS * 2 * (SPIN ? 16 : 8) * LEG_ALD);
     CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
     CB_CUDA(cudaFuncSetAttribute(sht_legendre_kernel<SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
