@@ -112,7 +112,7 @@ class Corr21cm(maps.Sky3d):
     # ---- device table ----------------------------------------------------------------
     def table(self):
         """Device-resident DCT tables, built once (``corr.py:915-942``), layout
-        ``tab[(y * 500 + x) * 3 + {dd, dv, vv}]``."""
+        planar ``tab[{dd, dv, vv}][y][x]``."""
         if self._tab is None:
             t = _dev.torch()
             lib = _lib.load()

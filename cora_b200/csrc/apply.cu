@@ -78,9 +78,14 @@ struct ApplyParams {
     int nz, lmax, chan0, nu0, nnu;
 };
 
-__global__ void __launch_bounds__(256) apply_kernel(ApplyParams P) {
-    __shared__ __align__(16) double As[AP_TM * AP_ALD];
-    __shared__ __align__(16) double Bs[AP_KC * AP_BLD];
+constexpr int AP_STAGES = 3;
+constexpr int AP_STAGE_DOUBLES = AP_TM * AP_ALD + AP_KC * AP_BLD;
+
+// FAST = true: operands staged with a 3-deep cp.async pipeline (needs an even nz so that every
+// 16-byte piece of a root row is aligned); FAST = false: plain loads, any nz.
+template <bool FAST>
+__global__ void __launch_bounds__(256, 2) apply_kernel(ApplyParams P) {
+    extern __shared__ __align__(16) double ap_smem[];
     const int li = blockIdx.z;
     const LDesc d = P.ldesc[li];
     const int m0 = blockIdx.x * (AP_TN / 2);
@@ -104,25 +109,57 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyParams P) {
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    for (int k0 = 0; k0 < kend; k0 += AP_KC) {
-        __syncthreads();
-        // A tile: 128 x 16
+    const int nit = (kend + AP_KC - 1) / AP_KC;
+    auto stage_load = [&](int it, int slot) {
+        double* As = ap_smem + slot * AP_STAGE_DOUBLES;
+        double* Bs = As + AP_TM * AP_ALD;
+        const int k0 = it * AP_KC;
+        if (FAST) {
+            // A tile 128 x 16: 1024 pieces of 2 doubles
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int e = tid + q * 256;
-            const int rr = e >> 4, kk = e & 15;
-            const int r = r0 + rr, k = k0 + kk;
-            As[rr * AP_ALD + kk] = (r < nz && k < nz) ? M[(long long)r * nz + k] : 0.0;
-        }
-        // B tile: 16 x 64
+            for (int q = 0; q < 4; q++) {
+                const int e = tid + q * 256;
+                const int rr = e >> 3, kk = (e & 7) * 2;
+                const int r = r0 + rr, k = k0 + kk;
+                const bool ok = (r < nz) && (k < nz) && (it < nit);
+                cp_async16(As + rr * AP_ALD + kk, M + (ok ? ((long long)r * nz + k) : 0), ok);
+            }
+            // B tile 16 x 64: 512 pieces of one complex
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int e = tid + q * 256;
-            const int kk = e >> 6, cc = e & 63;
-            const int k = k0 + kk, col = 2 * m0 + cc;
-            Bs[kk * AP_BLD + cc] = (k < nz && col < ncols) ? Gd[(long long)k * gld + col] : 0.0;
+            for (int q = 0; q < 2; q++) {
+                const int e = tid + q * 256;
+                const int kk = e >> 5, cc = (e & 31) * 2;
+                const int k = k0 + kk, col = 2 * m0 + cc;
+                const bool ok = (k < nz) && (col < ncols) && (it < nit);
+                cp_async16(Bs + kk * AP_BLD + cc, Gd + (ok ? ((long long)k * gld + col) : 0), ok);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int e = tid + q * 256;
+                const int rr = e >> 4, kk = e & 15;
+                const int r = r0 + rr, k = k0 + kk;
+                As[rr * AP_ALD + kk] = (r < nz && k < nz && it < nit) ? M[(long long)r * nz + k] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int e = tid + q * 256;
+                const int kk = e >> 6, cc = e & 63;
+                const int k = k0 + kk, col = 2 * m0 + cc;
+                Bs[kk * AP_BLD + cc] = (k < nz && col < ncols && it < nit) ? Gd[(long long)k * gld + col] : 0.0;
+            }
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < AP_STAGES - 1; s++) stage_load(s, s);
+    for (int it = 0; it < nit; it++) {
+        cp_async_wait<AP_STAGES - 2>();
+        __syncthreads();   // stage `it` landed for everyone; the slot refilled below was consumed last iteration
+        stage_load(it + AP_STAGES - 1, (it + AP_STAGES - 1) % AP_STAGES);
+        const double* As = ap_smem + (it % AP_STAGES) * AP_STAGE_DOUBLES;
+        const double* Bs = As + AP_TM * AP_ALD;
 #pragma unroll
         for (int k4 = 0; k4 < AP_KC / 4; k4++) {
             double af[4], bf[4];
@@ -136,6 +173,7 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyParams P) {
                 for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
         }
     }
+    cp_async_wait<0>();
     // epilogue: C[g][2t], C[g][2t+1] = (re, im) of (nu = row g, m = col t)
     const int lmax = P.lmax;
 #pragma unroll
@@ -226,7 +264,17 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
         P.nu_base = nu_base; P.nu_width = nu_width;
         P.nz = nz; P.lmax = lmax; P.chan0 = chan0; P.nu0 = nu0; P.nnu = nnu;
         dim3 grid(ceil_div(lbig + 1, AP_TN / 2), ceil_div(nnu, AP_TM), nb);
-        { KTimer kt(K_APPLY, st); apply_kernel<<<grid, 256, 0, st>>>(P); }
+        {
+            KTimer kt(K_APPLY, st);
+            const size_t smem = sizeof(double) * AP_STAGES * AP_STAGE_DOUBLES;
+            if (nz % 2 == 0) {
+                CB_CUDA(cudaFuncSetAttribute(apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                apply_kernel<true><<<grid, 256, smem, st>>>(P);
+            } else {
+                CB_CUDA(cudaFuncSetAttribute(apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                apply_kernel<false><<<grid, 256, smem, st>>>(P);
+            }
+        }
         count_launch();
         CB_LAUNCH_CHECK();
         if (i1 < nl) CB_CUDA(cudaStreamSynchronize(st));   // workspace reuse

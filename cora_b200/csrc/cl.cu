@@ -50,6 +50,10 @@ constexpr int NKPERP = 500;
 constexpr int NKPAR = 32768;
 constexpr double KPERP_MIN = 1e-4, KPERP_MAX = 40.0, KPAR_MAX = 20.0;
 
+// device table layout: planar, tab[t][y][x] (t = dd, dv, vv; y = r_par index; x = k_perp index):
+// a fixed-y row of one table is 500 contiguous doubles, which is what the fill kernel streams.
+__device__ __forceinline__ long long tab_idx(int t, int y, int x) { return ((long long)t * NKPAR + y) * NKPERP + x; }
+
 // natural cubic spline in (ln k, ln P), linear extrapolation outside (cubicspline.pyx:124-175)
 __device__ double spline_eval(const double* __restrict__ xs, const double* __restrict__ ys,
                               const double* __restrict__ y2, int n, double x) {
@@ -106,7 +110,7 @@ __global__ void ps21_costab_kernel(double* ctab) {
 //   X_k = x_0 + (-1)^k x_{N-1} + 2 sum_{n=1}^{N-2} x_n cos(pi n k/(N-1)),   times KPAR_MAX/(2N)
 // (scipy.fftpack.dct type 1, corr.py:938-942).  One thread per output k, DCT_ROWS rows
 // (x, table) at a time from shared memory; two-level summation keeps the rounding error
-// at the 1e-15 level.  Output is y-major and table-interleaved: tab[(k*NKPERP + x)*3 + t].
+// at the 1e-15 level.  Output is planar: tab[t][k][x].
 constexpr int DCT_ROWS = 12;   // 4 k_perp values x 3 tables
 constexpr int DCT_CHUNK = 256;
 __global__ void __launch_bounds__(256) ps21_dct_kernel(const double* __restrict__ pk, const double* __restrict__ ctab,
@@ -147,13 +151,20 @@ __global__ void __launch_bounds__(256) ps21_dct_kernel(const double* __restrict_
     for (int r = 0; r < DCT_ROWS; r++) {
         const int row = row0 + r;
         const int x = row / 3, t = row % 3;
-        tab[((long long)k * NKPERP + x) * 3 + t] = tot[r] * norm;
+        tab[tab_idx(t, k, x)] = tot[r] * norm;
     }
 }
 
 // ---------------------------------------------------------------------- 21cm fill
-// One CTA per channel pair (i >= j); threads stride over l.  Per sample pair (a, b) the
-// y-interpolation rows and all l-independent factors are staged in shared memory.
+// One CTA per channel pair (i >= j, nu <-> nu' symmetry).  For a sample pair e = (a, b) the
+// table row index y and every l-independent factor are fixed, and only the k_perp coordinate
+// x(l, e) = (log10 l - shift_e) * xscale moves with l.  So per batch of 9 sample pairs the CTA
+// first builds, for the x band the l block can reach, the y-interpolated and table-combined row
+//     R_e[x] = sum_t c_t(e) [ (1 - wy_e) T_t[y0_e][x] + wy_e T_t[y1_e][x] ]
+// in shared memory from coalesced row reads, then every thread evaluates its l's with two
+// shared-memory reads and one interpolation in x.  Algebraically identical to the reference's
+// 4-corner bilinear form (bilinearmap.pyx:49-57); it cuts the bytes moved per evaluation from
+// 96 (12 table reads) to ~35, which is what bounds this kernel (L1 bandwidth).
 struct PairPre {
     double shift;      // log10(xc * KPERP_MIN)
     double wy;         // fractional part of y
@@ -161,13 +172,38 @@ struct PairPre {
     int y0, y1;
 };
 
+constexpr int FILL_LPT = 4;          // l's per thread per l block
+constexpr int FILL_WMAX = 384;       // widest x band held in shared memory
+constexpr int FILL_EB = 9;           // sample pairs per batch
+
+__device__ __forceinline__ double fill_direct(const double* __restrict__ tab, const PairPre& p, double lx, double xscale) {
+    double x = (lx - p.shift) * xscale;
+    x = fmin(fmax(x, 0.0), (double)NKPERP - 1e-5);
+    const unsigned x0 = (unsigned)x;
+    const unsigned x1 = min(x0 + 1u, (unsigned)(NKPERP - 1));
+    const double wx = x - (double)x0;
+    // reference weights (bilinearmap.pyx:49-57): wa=(x1-x)(y1-y) [x0,y0], wb=(x1-x)(y-y0) [x0,y1],
+    // wc=(x-x0)(y1-y) [x1,y0], wd=(x-x0)(y-y0) [x1,y1]
+    const double wa = (1.0 - wx) * (1.0 - p.wy), wb = (1.0 - wx) * p.wy;
+    const double wc = wx * (1.0 - p.wy), wd = wx * p.wy;
+    double v[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+        v[t] = wa * tab[tab_idx(t, p.y0, x0)] + wb * tab[tab_idx(t, p.y1, x0)] + wc * tab[tab_idx(t, p.y0, x1)] +
+               wd * tab[tab_idx(t, p.y1, x1)];
+    return p.cdd * v[0] + p.cdv * v[1] + p.cvv * v[2];
+}
+
 __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict__ tab, const double* __restrict__ chi,
                                                         const double* __restrict__ bb, const double* __restrict__ ff,
                                                         const double* __restrict__ pf, const double* __restrict__ DD,
                                                         const double* __restrict__ w, int l0, int l_step, int nl, int nz,
                                                         int zint, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    PairPre* pre = (PairPre*)smraw;
+    PairPre* pre = (PairPre*)smraw;                                     // [zint*zint]
+    double* R = (double*)(smraw + sizeof(PairPre) * zint * zint);        // [FILL_EB][FILL_WMAX]
+    __shared__ double s_min, s_max;
+    __shared__ double s_red[256];
     // decode lower-triangle pair index
     const long long pidx = blockIdx.x;
     int i = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
@@ -175,8 +211,9 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
     while ((long long)i * (i + 1) / 2 > pidx) i--;
     const int j = (int)(pidx - (long long)i * (i + 1) / 2);
     const int npair = zint * zint;
+    const int tid = threadIdx.x;
     const double PI = 3.14159265358979323846;
-    for (int e = threadIdx.x; e < npair; e += blockDim.x) {
+    for (int e = tid; e < npair; e += blockDim.x) {
         const int a = e / zint, b = e % zint;
         const int s1 = i * zint + a, s2 = j * zint + b;
         const double x1 = chi[s1], x2 = chi[s2];
@@ -197,34 +234,95 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
         pre[e] = p;
     }
     __syncthreads();
+    if (tid == 0) {
+        double mn = pre[0].shift, mx = pre[0].shift;
+        for (int e = 1; e < npair; e++) { mn = fmin(mn, pre[e].shift); mx = fmax(mx, pre[e].shift); }
+        s_min = mn; s_max = mx;
+    }
+    __syncthreads();
+    const double smin = s_min, smax = s_max;
     const double xscale = (double)(NKPERP - 1) / log10(KPERP_MAX / KPERP_MIN);
+    const double xtopclip = (double)NKPERP - 1e-5;
     const long long nz2 = (long long)nz * nz;
-    for (int li = threadIdx.x; li < nl; li += blockDim.x) {
-        const int l = l0 + li * l_step;
-        const double lx = log10(l == 0 ? 1e-10 : (double)l);
-        double acc = 0.0;
-        for (int e = 0; e < npair; e++) {
-            const PairPre p = pre[e];
-            double x = (lx - p.shift) * xscale;
-            x = fmin(fmax(x, 0.0), (double)NKPERP - 1e-5);
-            const unsigned x0 = (unsigned)x;
-            const unsigned x1 = min(x0 + 1u, (unsigned)(NKPERP - 1));
-            const double wx = x - (double)x0;
-            const double* r0a = tab + ((long long)p.y0 * NKPERP + x0) * 3;
-            const double* r0b = tab + ((long long)p.y0 * NKPERP + x1) * 3;
-            const double* r1a = tab + ((long long)p.y1 * NKPERP + x0) * 3;
-            const double* r1b = tab + ((long long)p.y1 * NKPERP + x1) * 3;
-            // reference weights (bilinearmap.pyx:49-57): wa=(x1-x)(y1-y) [x0,y0], wb=(x1-x)(y-y0) [x0,y1],
-            // wc=(x-x0)(y1-y) [x1,y0], wd=(x-x0)(y-y0) [x1,y1]
-            const double wa = (1.0 - wx) * (1.0 - p.wy), wb = (1.0 - wx) * p.wy;
-            const double wc = wx * (1.0 - p.wy), wd = wx * p.wy;
-            const double dd = wa * r0a[0] + wb * r1a[0] + wc * r0b[0] + wd * r1b[0];
-            const double dv = wa * r0a[1] + wb * r1a[1] + wc * r0b[1] + wd * r1b[1];
-            const double vv = wa * r0a[2] + wb * r1a[2] + wc * r0b[2] + wd * r1b[2];
-            acc += p.cdd * dd + p.cdv * dv + p.cvv * vv;
+    const long long oij = (long long)i * nz + j, oji = (long long)j * nz + i;
+
+    for (int lb = 0; lb < nl; lb += 256 * FILL_LPT) {
+        const int lend = min(nl, lb + 256 * FILL_LPT);
+        // x band reachable by l >= 1 of this block (one entry of margin either side)
+        const int lfirst = max(1, l0 + lb * l_step), llast = max(1, l0 + (lend - 1) * l_step);
+        const double xa = fmin(fmax((log10((double)lfirst) - smax) * xscale, 0.0), xtopclip);
+        const double xb = fmin(fmax((log10((double)llast) - smin) * xscale, 0.0), xtopclip);
+        const int xbase = max(0, (int)xa - 1);
+        const int xtop = min(NKPERP - 1, (int)xb + 2);
+        const int W = xtop - xbase + 1;
+        const bool banded = (W <= FILL_WMAX);
+
+        double lx[FILL_LPT], acc[FILL_LPT];
+        int lv[FILL_LPT];
+#pragma unroll
+        for (int q = 0; q < FILL_LPT; q++) {
+            const int li = lb + tid + q * 256;
+            lv[q] = (li < lend) ? l0 + li * l_step : -1;
+            lx[q] = log10(lv[q] <= 0 ? 1e-10 : (double)lv[q]);
+            acc[q] = 0.0;
         }
-        out[(long long)li * nz2 + (long long)i * nz + j] = acc;
-        if (i != j) out[(long long)li * nz2 + (long long)j * nz + i] = acc;
+        if (banded) {
+            for (int e0 = 0; e0 < npair; e0 += FILL_EB) {
+                const int ne = min(FILL_EB, npair - e0);
+                __syncthreads();   // previous batch fully consumed
+                for (int idx = tid; idx < ne * W; idx += 256) {
+                    const int el = idx / W, xi = idx - el * W;
+                    const PairPre p = pre[e0 + el];
+                    const int x = xbase + xi;
+                    const double u0 = 1.0 - p.wy, u1 = p.wy;
+                    const double dd = u0 * tab[tab_idx(0, p.y0, x)] + u1 * tab[tab_idx(0, p.y1, x)];
+                    const double dv = u0 * tab[tab_idx(1, p.y0, x)] + u1 * tab[tab_idx(1, p.y1, x)];
+                    const double vv = u0 * tab[tab_idx(2, p.y0, x)] + u1 * tab[tab_idx(2, p.y1, x)];
+                    R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < FILL_LPT; q++) {
+                    if (lv[q] < 1) continue;
+                    double a = acc[q];
+                    for (int el = 0; el < ne; el++) {
+                        double x = (lx[q] - pre[e0 + el].shift) * xscale;
+                        x = fmin(fmax(x, 0.0), xtopclip);
+                        const int x0 = (int)x;
+                        const double wx = x - (double)x0;
+                        const double* Rr = R + el * FILL_WMAX + (x0 - xbase);
+                        const int up = (x0 < NKPERP - 1) ? 1 : 0;
+                        a += (1.0 - wx) * Rr[0] + wx * Rr[up];
+                    }
+                    acc[q] = a;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < FILL_LPT; q++) {
+                if (lv[q] < 1) continue;
+                for (int e = 0; e < npair; e++) acc[q] += fill_direct(tab, pre[e], lx[q], xscale);
+            }
+        }
+        // l = 0 (replaced by 1e-10, corr.py:957): x clips to 0, outside the band -> direct, spread over threads
+        if (l0 == 0 && lb == 0) {
+            double v = 0.0;
+            for (int e = tid; e < npair; e += 256) v += fill_direct(tab, pre[e], log10(1e-10), xscale);
+            s_red[tid] = v;
+            __syncthreads();
+            if (tid == 0) {
+                double tsum = 0.0;
+                for (int k = 0; k < min(npair, 256); k++) tsum += s_red[k];
+                acc[0] = tsum;     // thread 0, q = 0 holds li = 0 <-> l = 0
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < FILL_LPT; q++) {
+            const int li = lb + tid + q * 256;
+            if (li >= lend) continue;
+            out[(long long)li * nz2 + oij] = acc[q];
+            if (i != j) out[(long long)li * nz2 + oji] = acc[q];
+        }
     }
 }
 
@@ -281,13 +379,12 @@ __global__ void cl21_points_kernel(const double* __restrict__ tab, const double*
     const unsigned xn = min(x0 + 1u, (unsigned)(NKPERP - 1)), yn = min(y0 + 1u, (unsigned)(NKPAR - 1));
     const double wx = x - (double)x0, wy = y - (double)y0;
     const double wa = (1.0 - wx) * (1.0 - wy), wb = (1.0 - wx) * wy, wc = wx * (1.0 - wy), wd = wx * wy;
-    const double* r00 = tab + ((long long)y0 * NKPERP + x0) * 3;
-    const double* r01 = tab + ((long long)yn * NKPERP + x0) * 3;
-    const double* r10 = tab + ((long long)y0 * NKPERP + xn) * 3;
-    const double* r11 = tab + ((long long)yn * NKPERP + xn) * 3;
-    const double dd = wa * r00[0] + wb * r01[0] + wc * r10[0] + wd * r11[0];
-    const double dv = wa * r00[1] + wb * r01[1] + wc * r10[1] + wd * r11[1];
-    const double vv = wa * r00[2] + wb * r01[2] + wc * r10[2] + wd * r11[2];
+    double v[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+        v[t] = wa * tab[tab_idx(t, y0, x0)] + wb * tab[tab_idx(t, yn, x0)] + wc * tab[tab_idx(t, y0, xn)] +
+               wd * tab[tab_idx(t, yn, xn)];
+    const double dd = v[0], dv = v[1], vv = v[2];
     out[e] = (D1 * D2 * pf1 * pf2 / (xc * xc * PI)) * ((b1 * b2) * dd + (f1 * b2 + f2 * b1) * dv + (f1 * f2) * vv);
 }
 
@@ -296,8 +393,7 @@ __global__ void ps21_gather_kernel(const double* __restrict__ tab, const int* __
                                    int n, double* __restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    const double* r = tab + ((long long)ys[e] * NKPERP + xs[e]) * 3;
-    out[3 * e] = r[0]; out[3 * e + 1] = r[1]; out[3 * e + 2] = r[2];
+    for (int t = 0; t < 3; t++) out[3 * e + t] = tab[tab_idx(t, ys[e], xs[e])];
 }
 
 }  // namespace cb
@@ -363,7 +459,7 @@ extern "C" int cora_b200_cl_fill_21cm(const double* tab, const double* chi, cons
     CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_21cm: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
     const long long npairs = (long long)nz * (nz + 1) / 2;
     CB_REQUIRE(npairs < 2147483647LL, 3, "cl_fill_21cm: too many channel pairs");
-    size_t smem = sizeof(PairPre) * (size_t)zint * zint;
+    size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
     CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KTimer kt(K_CL_FILL, (cudaStream_t)stream);
     cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl);

@@ -99,17 +99,16 @@ def _dist():
     return dist
 
 
-def exchange(send, plan, rank, group=None):
+def exchange(send, plan, rank, group=None, out=None):
     """The one collective of the path: l-major slabs -> channel-major slabs
     (``alm_array.redistribute(axis=0)``, ``skysim.py:128``).  ``send``: complex128 tensor
     (CUDA under NCCL, CPU under gloo).  Returns the receive buffer."""
     import torch
 
     dist = _dist()
-    recv = torch.empty(sum(plan.recv_splits(rank)), dtype=send.dtype, device=send.device)
     if plan.size == 1:
-        recv.copy_(send)
-        return recv
+        return send   # one rank: the send slab already is the receive slab
+    recv = torch.empty(sum(plan.recv_splits(rank)), dtype=send.dtype, device=send.device) if out is None else out
     s_r, r_r = torch.view_as_real(send).reshape(-1), torch.view_as_real(recv).reshape(-1)
     dist.all_to_all_single(r_r, s_r, output_split_sizes=[2 * n for n in plan.recv_splits(rank)],
                            input_split_sizes=[2 * n for n in plan.send_splits(rank)], group=group)
@@ -149,12 +148,19 @@ class ShardedSky(object):
         self.nu_base, self.nu_width = _dev.to_device(base, t.int64), _dev.to_device(width, t.int32)
         self.l_off = _dev.to_device(self.plan.l_offsets(rank), t.int64)
         self.row0 = self.plan.send_row0(rank)
+        self._buf = {}
+
+    def _persistent(self, name, make):
+        """Buffers reused from step to step (no allocator traffic inside a step)."""
+        if name not in self._buf:
+            self._buf[name] = make()
+        return self._buf[name]
 
     def fill(self, out=None):
         """This rank's C_l(nu, nu') rows, ``float64[nl, nz, nz]`` (``skysim.clarray`` for the local l's)."""
         t = _dev.torch()
         if out is None:
-            out = _dev.empty((self.nl, self.nz, self.nz), t.float64)
+            out = self._persistent("cla", lambda: _dev.empty((self.nl, self.nz, self.nz), t.float64))
         if self.plan.partition == "interleaved":
             self.model._b200_fill(self.fill_inputs, int(self.l_list[0]) if self.nl else 0, self.size, self.nl, self.nz,
                                   self.zint, out)
@@ -167,21 +173,27 @@ class ShardedSky(object):
         t = _dev.torch()
         lib = _lib.load()
         if roots is None:
-            root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16)
+            outb = self._persistent("root", lambda: (_dev.empty((self.nl, self.nz, self.nz), t.float64),
+                                                     _dev.empty((self.nl,), t.int32), _dev.empty((self.nl,), t.int32)))
+            rws = self._persistent("root_ws", lambda: nputil.root_workspace(self.nl, self.nz, max_eigh=max(4, self.nl // 8)))
+            root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16, out=outb, ws=rws)
         else:
             root, used = _dev.to_device(roots, t.float64), None
-        send = _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128)
+        send = self._persistent("send", lambda: _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128))
         lmax_loc = int(self.l_list.max())
         if gauss is None:
-            full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
-            one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
-            nbytes = min(full, max(one, _dev.free_bytes() - (2 << 30)))
+            def mk():
+                full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
+                one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
+                return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
+
+            ws = self._persistent("draw_ws", mk)
             gptr, gld = None, 0
         else:
             gauss = _dev.to_device(gauss, t.complex128)
-            nbytes = 64 * self.nl + 4096
+            ws = _dev.workspace(64 * self.nl + 4096)
             gptr, gld = _lib.ptr(gauss), int(gauss.shape[-1])
-        ws = _dev.workspace(nbytes)
+        nbytes = ws.numel()
         _lib.call("cora_b200_draw_apply_slabs", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
                   self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(self.row0), _lib.ptr(self.nu_base),
                   _lib.ptr(self.nu_width), _lib.ptr(send), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
@@ -191,17 +203,21 @@ class ShardedSky(object):
         """received slabs -> PANEL -> maps of this rank's channels."""
         t = _dev.torch()
         nalm = (self.lmax + 1) * (self.lmax + 2) // 2
-        panel = _dev.empty((nalm, self.cb), t.complex128)
+        panel = self._persistent("panel", lambda: _dev.empty((nalm, self.cb), t.complex128))
         _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(recv), _lib.ptr(self.l_off), self.lmax, self.cb, _lib.ptr(panel),
                   self.cb, 0, _lib.stream_ptr())
-        return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out)
+        plan = _dev.sht_plan(self.nside, self.lmax)
+        ws = self._persistent("sht_ws", lambda: _dev.sht_workspace(plan, _lib.ALM_PANEL, self.cb, reserve=(4 << 30) + 8 * self.cb * self.npix)[0])
+        return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out, ws=ws)
 
     def step(self, seed=0, out=None):
         cla = self.fill()
         send = self.alm_local(cla, seed=seed)
         del cla
-        recv = exchange(send, self.plan, self.rank, self.group)
-        del send
+        rbuf = None
+        if self.size > 1:
+            rbuf = self._persistent("recv", lambda: _dev.empty((sum(self.plan.recv_splits(self.rank)),), _dev.torch().complex128))
+        recv = exchange(send, self.plan, self.rank, self.group, out=rbuf)
         return self.synthesize(recv, out=out)
 
 

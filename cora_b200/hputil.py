@@ -58,7 +58,7 @@ def _make_half_alm(alm_full):
 
 
 # ------------------------------------------------------------------ device-level SHT
-def alm2map_device(alm_dev, nside, lmax, layout, alm_stride, nchan, out=None, stream=None):
+def alm2map_device(alm_dev, nside, lmax, layout, alm_stride, nchan, out=None, stream=None, ws=None):
     """Scalar synthesis on device buffers.  ``alm_dev``: CUDA complex128 tensor in PACKED
     ([chan][nalm]) or PANEL ([nalm][stride]) layout; returns CUDA float64 [nchan, npix]."""
     t = _dev.torch()
@@ -66,7 +66,10 @@ def alm2map_device(alm_dev, nside, lmax, layout, alm_stride, nchan, out=None, st
     npix = 12 * nside * nside
     if out is None:
         out = _dev.empty((nchan, npix), t.float64)
-    ws, nbytes = _dev.sht_workspace(plan, layout, nchan)
+    if ws is None:
+        ws, nbytes = _dev.sht_workspace(plan, layout, nchan)
+    else:
+        nbytes = ws.numel()
     _lib.call("cora_b200_alm2map", plan, _lib.ptr(alm_dev), int(layout), int(alm_stride), int(nchan),
               _lib.ptr(out), _lib.ptr(ws), int(nbytes), _lib.stream_ptr(stream))
     return out

@@ -7,7 +7,7 @@ import numpy as np
 from . import _dev, _lib
 
 
-def root_batched_device(cl_dev, jitter_rel=0.0, clip_rel=1e-16, stream=None):
+def root_batched_device(cl_dev, jitter_rel=0.0, clip_rel=1e-16, stream=None, out=None, ws=None):
     """Batched root on device: ``cl_dev`` CUDA float64 [nl, nz, nz] -> (root, used_eigh, num_pos).
 
     Semantics of ``skysim.py:116-119`` + ``nputil.py:51-101`` (``truncate=False``): jitter on the
@@ -15,17 +15,25 @@ def root_batched_device(cl_dev, jitter_rel=0.0, clip_rel=1e-16, stream=None):
     """
     t = _dev.torch()
     nl, nz = int(cl_dev.shape[0]), int(cl_dev.shape[1])
-    root = _dev.empty((nl, nz, nz), t.float64)
-    used = _dev.empty((nl,), t.int32)
-    npos = _dev.empty((nl,), t.int32)
-    lib = _lib.load()
-    full = lib.cora_b200_root_workspace_bytes(nl, nz)
-    one = lib.cora_b200_root_workspace_bytes(nl, nz) - 16 * nz * nz * (nl - 1)
-    nbytes = min(full, max(one, _dev.free_bytes() - (2 << 30)))
-    ws = _dev.workspace(nbytes)
+    if out is None:
+        out = (_dev.empty((nl, nz, nz), t.float64), _dev.empty((nl,), t.int32), _dev.empty((nl,), t.int32))
+    root, used, npos = out
+    if ws is None:
+        ws = root_workspace(nl, nz)
+    nbytes = ws.numel()
     _lib.call("cora_b200_root_batched", _lib.ptr(cl_dev), nl, nz, float(jitter_rel), float(clip_rel), _lib.ptr(root),
               _lib.ptr(used), _lib.ptr(npos), _lib.ptr(ws), int(nbytes), _lib.stream_ptr(stream))
     return root, used, npos
+
+
+def root_workspace(nl, nz, max_eigh=None):
+    """Workspace for ``root_batched_device``: room for ``max_eigh`` simultaneous eigen fallbacks
+    (default: all nl matrices, bounded by free memory)."""
+    lib = _lib.load()
+    full = lib.cora_b200_root_workspace_bytes(nl, nz)
+    one = full - 16 * nz * nz * (nl - 1)
+    want = full if max_eigh is None else one + 16 * nz * nz * (max(1, min(nl, max_eigh)) - 1)
+    return _dev.workspace(min(want, max(one, _dev.free_bytes() - (2 << 30))))
 
 
 def matrix_root_manynull(mat, threshold=1e-16, truncate=True):

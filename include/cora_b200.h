@@ -93,7 +93,7 @@ int cora_b200_cl_fill_sck(double A, double beta, double l_ref, double alpha, dou
                           double* out_cl, void* stream);
 
 /* 21cm: one-off P(k_perp, k_par) table -> three DCT-I tables (dd, dv, vv), stored
- * y-major and interleaved: tab[(y * nkperp + x) * 3 + {dd,dv,vv}].
+ * planar: tab[({dd,dv,vv} * nkpar + y) * nkperp + x]  (y = r_par index, x = k_perp index).
  * replaces: the cache build of RedshiftCorrelation.angular_powerspectrum_fft
  * (cora/signal/corr.py:915-942) incl. the log-log cubic spline of ps_z1.5.dat
  * (cora/util/cubicspline.pyx:124-175,274-288) and the exp(-k^2/2k*^2) cut
