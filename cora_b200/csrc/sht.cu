@@ -29,12 +29,15 @@ struct RingDesc {
     int nph;              // pixels in ring
     int shifted;          // phi0 = pi/nph (1) or 0 (0)
     int cap;              // index into the per-size Bluestein tables (cap ring number i), or -1
+    int logM;             // FFT size 2^logM: nph itself (power of two) or the Bluestein size >= 2 nph - 1
+    int bluestein;
 };
 
+// rings launched together: all rings whose FFT fits Mmax points of shared memory per channel pair
 struct PhaseClass {
-    int M, logM, bluestein, P;      // FFT size, pairs per CTA
+    int Mmax, P, threads;           // smem FFT capacity, channel pairs per CTA, CTA size
     int nrings;
-    int* d_rings;                   // ring indices of this class
+    int* d_rings;                   // ring indices of this class, longest ring first
 };
 
 struct ShtPlan {
@@ -173,7 +176,7 @@ struct LegParams {
     const double *cth, *sth;  // [nrn]
     const double* nm_mant;
     const int* nm_exp;
-    int nside, lmax, nrn, nrb, ncb, Lpad;
+    int nside, lmax, nrn, nrb, ncb, Lpad, ncg;   // ncg = ceil(nb / 4) channel groups in F
 };
 
 __device__ __forceinline__ void norm_frexp(double& m, long long& e) {
@@ -425,22 +428,26 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
             if (SPIN == 0) {
                 const int ch = cb * NCH + 4 * nb + t;
                 if (ch >= P.nb) continue;
-                P.F[((long long)r_n * L + m) * P.nb + ch] = make_double2(er + orr, ei + oi);
-                if (r_s != r_n) P.F[((long long)r_s * L + m) * P.nb + ch] = make_double2(er - orr, ei - oi);
+                const int cg = ch >> 2, cc = ch & 3;
+                P.F[(((long long)r_n * P.ncg + cg) * L + m) * 4 + cc] = make_double2(er + orr, ei + oi);
+                if (r_s != r_n) P.F[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cc] = make_double2(er - orr, ei - oi);
             } else {
                 const int ch = cb * NCH + 2 * nb + (t >> 1);
                 if (ch >= P.nb) continue;
                 double2* Fo = (t & 1) ? P.F2 : P.F;   // even t: Q, odd t: U
-                Fo[((long long)r_n * L + m) * P.nb + ch] = make_double2(-(er + orr), -(ei + oi));
-                if (r_s != r_n) Fo[((long long)r_s * L + m) * P.nb + ch] = make_double2(-(er - orr), -(ei - oi));
+                const int cg = ch >> 2, cc = ch & 3;
+                Fo[(((long long)r_n * P.ncg + cg) * L + m) * 4 + cc] = make_double2(-(er + orr), -(ei + oi));
+                if (r_s != r_n) Fo[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cc] = make_double2(-(er - orr), -(ei - oi));
             }
         }
     }
 }
 
 // --------------------------------------------------------------------------- phase stage
+// F layout: [ring][channel group of 4][m][4] -- the 64 bytes the Legendre epilogue writes per
+// (ring, m) are the 64 bytes one phase CTA reads, and a CTA's whole input is one contiguous block.
 struct PhaseParams {
-    const double2* F;        // [nring][L][nb]
+    const double2* F;        // [nring][ncg][L][4]
     double* map;             // [nchan][npix] (pointer already offset to the batch's first channel)
     long long npix;
     const RingDesc* rings;
@@ -449,57 +456,316 @@ struct PhaseParams {
     const double2* chirp;
     const double2* bhat;
     const long long *chirp_off, *bhat_off;
-    int lmax, nb, M, logM, P, bluestein, log_tw;
+    int lmax, nb, ncg, P, Mmax, log_tw;
 };
 
 __device__ __forceinline__ int bitrev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - bits)); }
 
-__global__ void __launch_bounds__(256) sht_phase_kernel(PhaseParams Q) {
-    extern __shared__ __align__(16) double2 xs[];   // [P][M]
+// shared-memory FFT buffers are padded by one element every 8: every fused pass below then reads
+// and writes conflict-free per quarter-warp, whatever its stride
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+template <int SIGN> __device__ __forceinline__ double2 ld_tw(const double2* __restrict__ tw, int j) {
+    double2 w = tw[j];
+    if (SIGN < 0) w.y = -w.y;
+    return w;
+}
+// multiply by (SIGN i)
+template <int SIGN> __device__ __forceinline__ double2 mul_i(double2 a) {
+    return SIGN > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+// multiply by exp(SIGN 2 pi i q / 8), q = 0..3
+template <int SIGN, int Q> __device__ __forceinline__ double2 mul_c8(double2 a) {
+    const double r = 0.70710678118654752440;
+    if (Q == 0) return a;
+    if (Q == 2) return mul_i<SIGN>(a);
+    if (Q == 1) return SIGN > 0 ? make_double2(r * (a.x - a.y), r * (a.x + a.y)) : make_double2(r * (a.x + a.y), r * (a.y - a.x));
+    return SIGN > 0 ? make_double2(-r * (a.x + a.y), r * (a.x - a.y)) : make_double2(r * (a.y - a.x), -r * (a.x + a.y));
+}
+
+// Radix-2 decimation-in-frequency stages s, s-1, .. fused in registers (natural in -> bit-reversed
+// out, in place; identical data flow to one radix-2 stage after the other).
+template <int SIGN>
+__device__ __forceinline__ void dif8(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
+    const int S = 1 << (s - 2);
+    const int low = b & (S - 1);
+    const int base = ((b >> (s - 2)) << (s + 1)) | low;
+    double2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = x[pidx(base + j * S)];
+    const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
+    const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - s));
+    const double2 w4 = ld_tw<SIGN>(tw, low << (log_tw - s + 1));
+    {   // stage s: pairs (j, j+4), twiddle w1 c8^j
+        double2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+        v[0] = cadd(v[0], v[4]); v[1] = cadd(v[1], v[5]); v[2] = cadd(v[2], v[6]); v[3] = cadd(v[3], v[7]);
+        v[4] = cmul(d0, w1);
+        v[5] = cmul(mul_c8<SIGN, 1>(d1), w1);
+        v[6] = cmul(mul_c8<SIGN, 2>(d2), w1);
+        v[7] = cmul(mul_c8<SIGN, 3>(d3), w1);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {   // stage s-1: pairs (j, j+2), twiddle w2 (SIGN i)^j
+        double2 d0 = csub(v[h], v[h + 2]), d1 = csub(v[h + 1], v[h + 3]);
+        v[h] = cadd(v[h], v[h + 2]); v[h + 1] = cadd(v[h + 1], v[h + 3]);
+        v[h + 2] = cmul(d0, w2);
+        v[h + 3] = cmul(mul_i<SIGN>(d1), w2);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {   // stage s-2: pairs (j, j+1), twiddle w4
+        double2 d = csub(v[h], v[h + 1]);
+        v[h] = cadd(v[h], v[h + 1]);
+        v[h + 1] = cmul(d, w4);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[pidx(base + j * S)] = v[j];
+}
+template <int SIGN>
+__device__ __forceinline__ void dif4(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
+    const int S = 1 << (s - 1);
+    const int low = b & (S - 1);
+    const int base = ((b >> (s - 1)) << (s + 1)) | low;
+    double2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = x[pidx(base + j * S)];
+    const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
+    const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - s));
+    double2 d0 = csub(v[0], v[2]), d1 = csub(v[1], v[3]);
+    v[0] = cadd(v[0], v[2]); v[1] = cadd(v[1], v[3]);
+    v[2] = cmul(d0, w1);
+    v[3] = cmul(mul_i<SIGN>(d1), w1);
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+        double2 d = csub(v[h], v[h + 1]);
+        v[h] = cadd(v[h], v[h + 1]);
+        v[h + 1] = cmul(d, w2);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[pidx(base + j * S)] = v[j];
+}
+template <int SIGN>
+__device__ __forceinline__ void dif2(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
+    const int S = 1 << s;
+    const int low = b & (S - 1);
+    const int base = ((b >> s) << (s + 1)) | low;
+    const double2 u = x[pidx(base)], v = x[pidx(base + S)];
+    x[pidx(base)] = cadd(u, v);
+    x[pidx(base + S)] = cmul(csub(u, v), ld_tw<SIGN>(tw, low << (log_tw - 1 - s)));
+}
+
+// Decimation-in-time stages s, s+1, .. fused (bit-reversed in -> natural out, in place).
+template <int SIGN>
+__device__ __forceinline__ void dit8(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
+    const int S = 1 << s;
+    const int low = b & (S - 1);
+    const int base = ((b >> s) << (s + 3)) | low;
+    double2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = x[pidx(base + j * S)];
+    const double2 w4 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
+    const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - 2 - s));
+    const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 3 - s));
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {   // stage s
+        const double2 t = cmul(v[h + 1], w4);
+        v[h + 1] = csub(v[h], t);
+        v[h] = cadd(v[h], t);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {   // stage s+1
+        const double2 t0 = cmul(v[h + 2], w2);
+        const double2 t1 = mul_i<SIGN>(cmul(v[h + 3], w2));
+        v[h + 2] = csub(v[h], t0); v[h] = cadd(v[h], t0);
+        v[h + 3] = csub(v[h + 1], t1); v[h + 1] = cadd(v[h + 1], t1);
+    }
+    {   // stage s+2
+        const double2 t0 = cmul(v[4], w1);
+        const double2 t1 = mul_c8<SIGN, 1>(cmul(v[5], w1));
+        const double2 t2 = mul_c8<SIGN, 2>(cmul(v[6], w1));
+        const double2 t3 = mul_c8<SIGN, 3>(cmul(v[7], w1));
+        v[4] = csub(v[0], t0); v[0] = cadd(v[0], t0);
+        v[5] = csub(v[1], t1); v[1] = cadd(v[1], t1);
+        v[6] = csub(v[2], t2); v[2] = cadd(v[2], t2);
+        v[7] = csub(v[3], t3); v[3] = cadd(v[3], t3);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[pidx(base + j * S)] = v[j];
+}
+template <int SIGN>
+__device__ __forceinline__ void dit4(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
+    const int S = 1 << s;
+    const int low = b & (S - 1);
+    const int base = ((b >> s) << (s + 2)) | low;
+    double2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = x[pidx(base + j * S)];
+    const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
+    const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 2 - s));
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+        const double2 t = cmul(v[h + 1], w2);
+        v[h + 1] = csub(v[h], t);
+        v[h] = cadd(v[h], t);
+    }
+    const double2 t0 = cmul(v[2], w1);
+    const double2 t1 = mul_i<SIGN>(cmul(v[3], w1));
+    v[2] = csub(v[0], t0); v[0] = cadd(v[0], t0);
+    v[3] = csub(v[1], t1); v[1] = cadd(v[1], t1);
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[pidx(base + j * S)] = v[j];
+}
+template <int SIGN>
+__device__ __forceinline__ void dit2(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
+    const int S = 1 << s;
+    const int low = b & (S - 1);
+    const int base = ((b >> s) << (s + 1)) | low;
+    const double2 u = x[pidx(base)];
+    const double2 t = cmul(x[pidx(base + S)], ld_tw<SIGN>(tw, low << (log_tw - 1 - s)));
+    x[pidx(base)] = cadd(u, t);
+    x[pidx(base + S)] = csub(u, t);
+}
+
+// P sequences of M points at xs + p * seq_stride (padded layout); whole CTA participates.
+template <int SIGN>
+__device__ void fft_dif_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw) {
+    int s = logM - 1;
+    for (; s >= 2; s -= 3) {
+        const int nbf = M >> 3;
+        for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+            const int p = w / nbf;
+            dif8<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, s, tw, log_tw);
+        }
+        __syncthreads();
+    }
+    if (s == 1) {
+        const int nbf = M >> 2;
+        for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+            const int p = w / nbf;
+            dif4<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 1, tw, log_tw);
+        }
+        __syncthreads();
+    } else if (s == 0) {
+        const int nbf = M >> 1;
+        for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+            const int p = w / nbf;
+            dif2<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 0, tw, log_tw);
+        }
+        __syncthreads();
+    }
+}
+template <int SIGN>
+__device__ void fft_dit_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw) {
+    int s = 0;
+    const int rem = logM % 3;
+    if (rem == 1) {
+        const int nbf = M >> 1;
+        for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+            const int p = w / nbf;
+            dit2<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 0, tw, log_tw);
+        }
+        __syncthreads();
+        s = 1;
+    } else if (rem == 2) {
+        const int nbf = M >> 2;
+        for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+            const int p = w / nbf;
+            dit4<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 0, tw, log_tw);
+        }
+        __syncthreads();
+        s = 2;
+    }
+    for (; s + 2 < logM; s += 3) {
+        const int nbf = M >> 3;
+        for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+            const int p = w / nbf;
+            dit8<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, s, tw, log_tw);
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int PH_MAXSLICE_ITEMS = 512;   // fold work items (bin, pair, slice) staged for the slice reduction
+
+__global__ void __launch_bounds__(512) sht_phase_kernel(PhaseParams Q) {
+    extern __shared__ __align__(16) double2 xs[];   // [P][pidx(Mmax)] + slice partials
     const int r = Q.ring_list[blockIdx.x];
     const RingDesc rd = Q.rings[r];
-    const int n = rd.nph, M = Q.M, Pp = Q.P;
-    const int c0 = blockIdx.y * 2 * Pp;
+    const int n = rd.nph, logM = rd.logM, M = 1 << logM, Pp = Q.P;
+    const bool blu = rd.bluestein != 0;
+    const int seq = pidx(Q.Mmax) + 1;               // padded sequence stride
+    double2* part = xs + (size_t)Pp * seq;          // [PH_MAXSLICE_ITEMS][4]
+    const int gpc = 2 / Pp;                         // CTAs per channel group
+    const int cg = blockIdx.y / gpc;
+    const int pair0 = (blockIdx.y % gpc) * Pp;      // first pair (of the group's two) handled here
     const int L = Q.lmax + 1;
-    const double2* Fr = Q.F + (long long)r * L * Q.nb;
+    const double2* Fr = Q.F + (((long long)r * Q.ncg + cg) * L) * 4;
     const int half = n >> 1;
-    const double2* chirp = Q.bluestein ? Q.chirp + Q.chirp_off[rd.cap] : nullptr;
+    const double2* chirp = blu ? Q.chirp + Q.chirp_off[rd.cap] : nullptr;
 
-    if (Q.bluestein) {
+    if (blu) {
         for (int w = threadIdx.x; w < Pp * (M - n); w += blockDim.x) {
-            int p = w / (M - n), k = n + (w - p * (M - n));
-            xs[(size_t)p * M + k] = make_double2(0.0, 0.0);
+            const int p = w / (M - n), k = n + (w - p * (M - n));
+            xs[(size_t)p * seq + pidx(k)] = make_double2(0.0, 0.0);
         }
     }
-    // ---- fold m -> m mod nph, Hermitian part, two channels per complex series
-    for (int w = threadIdx.x; w < (half + 1) * Pp; w += blockDim.x) {
-        const int pair = w % Pp, k = w / Pp;
-        const int ch = c0 + 2 * pair;
-        const bool has1 = ch < Q.nb, has2 = ch + 1 < Q.nb;
+    // ---- fold m -> m mod nph.  Work item = (bin k <= n/2, pair, slice): a slice sums every
+    // nsl-th aliased m of its bin; short rings get several slices per bin so the CTA stays busy.
+    const int nbin = (half + 1) * Pp;
+    int nsl = 1;
+    while (nsl * 2 * nbin <= min((int)blockDim.x, PH_MAXSLICE_ITEMS) && nsl * 2 * n <= L) nsl *= 2;
+    for (int w0 = 0; w0 < nbin * nsl; w0 += blockDim.x) {
+        const int w = w0 + threadIdx.x;
+        const bool act = w < nbin * nsl;
+        const int sl = act ? w / nbin : 0;
+        const int wb = act ? w - sl * nbin : 0;
+        const int pair = wb % Pp, k = wb / Pp;
+        const int c = 2 * (pair0 + pair);                      // channel inside the group of 4
+        const int ch = cg * 4 + c;
+        const bool has1 = act && ch < Q.nb, has2 = act && ch + 1 < Q.nb;
         double2 a1 = make_double2(0, 0), a2 = a1, b1 = a1, b2 = a1;
+        const int kk = n - k;
+        const bool twin = (k != 0 && kk != k);
         if (has1) {
-            double sg = 1.0;
-            for (int m = k; m <= Q.lmax; m += n) {
-                const double wgt = (m == 0) ? 1.0 : 2.0;
-                double2 f1 = Fr[(long long)m * Q.nb + ch];
-                double2 f2 = has2 ? Fr[(long long)m * Q.nb + ch + 1] : make_double2(0, 0);
+            // (-1)^q of the aliased copy q (m = k + q n) on shifted rings
+            for (int q = sl; k + q * n <= Q.lmax; q += nsl) {
+                const int m = k + q * n;
+                double2 f1 = Fr[m * 4 + c];
+                double2 f2 = has2 ? Fr[m * 4 + c + 1] : make_double2(0, 0);
                 if (m == 0) { f1.y = 0.0; f2.y = 0.0; }
-                const double s = sg * wgt;
-                a1.x += s * f1.x; a1.y += s * f1.y;
-                a2.x += s * f2.x; a2.y += s * f2.y;
-                if (rd.shifted) sg = -sg;
+                double sg = (m == 0) ? 1.0 : 2.0;
+                if (rd.shifted && (q & 1)) sg = -sg;
+                a1.x += sg * f1.x; a1.y += sg * f1.y;
+                a2.x += sg * f2.x; a2.y += sg * f2.y;
             }
-            const int kk = n - k;
-            if (k != 0 && kk != k) {
-                sg = 1.0;
-                for (int m = kk; m <= Q.lmax; m += n) {
-                    double2 f1 = Fr[(long long)m * Q.nb + ch];
-                    double2 f2 = has2 ? Fr[(long long)m * Q.nb + ch + 1] : make_double2(0, 0);
-                    const double s = sg * 2.0;
-                    b1.x += s * f1.x; b1.y += s * f1.y;
-                    b2.x += s * f2.x; b2.y += s * f2.y;
-                    if (rd.shifted) sg = -sg;
+            if (twin) {
+                for (int q = sl; kk + q * n <= Q.lmax; q += nsl) {
+                    const int m = kk + q * n;
+                    const double2 f1 = Fr[m * 4 + c];
+                    const double2 f2 = has2 ? Fr[m * 4 + c + 1] : make_double2(0, 0);
+                    const double sg = (rd.shifted && (q & 1)) ? -2.0 : 2.0;
+                    b1.x += sg * f1.x; b1.y += sg * f1.y;
+                    b2.x += sg * f2.x; b2.y += sg * f2.y;
                 }
+            }
+        }
+        if (nsl > 1) {
+            // fixed-order reduction over the slices (deterministic)
+            if (act) {
+                double2* pp = part + (size_t)w * 4;
+                pp[0] = a1; pp[1] = a2; pp[2] = b1; pp[3] = b2;
+            }
+            __syncthreads();
+            if (act && sl == 0) {
+                for (int s2 = 1; s2 < nsl; s2++) {
+                    const double2* pp = part + (size_t)(s2 * nbin + wb) * 4;
+                    a1 = cadd(a1, pp[0]); a2 = cadd(a2, pp[1]); b1 = cadd(b1, pp[2]); b2 = cadd(b2, pp[3]);
+                }
+            }
+        }
+        if (act && sl == 0) {
+            if (twin) {
                 if (rd.shifted) {
                     // e^{i pi k/n} on bin k;  e^{i pi (n-k)/n} = -conj(e^{i pi k/n}) on bin n-k
                     double sn, cs;
@@ -515,44 +781,45 @@ __global__ void __launch_bounds__(256) sht_phase_kernel(PhaseParams Q) {
                 }
                 b1 = a1; b2 = a2;
             }
+            // H = (G_k + conj(G_{n-k}))/2
+            const double2 h1 = make_double2(0.5 * (a1.x + b1.x), 0.5 * (a1.y - b1.y));
+            const double2 h2 = make_double2(0.5 * (a2.x + b2.x), 0.5 * (a2.y - b2.y));
+            double2 zk = make_double2(h1.x - h2.y, h1.y + h2.x);
+            double2 zn = make_double2(h1.x + h2.y, -h1.y + h2.x);
+            double2* xp = xs + (size_t)pair * seq;
+            if (blu) {
+                xp[pidx(k)] = cmul(zk, chirp[k]);
+                if (twin) xp[pidx(kk)] = cmul(zn, chirp[kk]);
+            } else {
+                xp[pidx(bitrev(k, logM))] = zk;
+                if (twin) xp[pidx(bitrev(kk, logM))] = zn;
+            }
         }
-        // H = (G_k + conj(G_{n-k}))/2
-        const double2 h1 = make_double2(0.5 * (a1.x + b1.x), 0.5 * (a1.y - b1.y));
-        const double2 h2 = make_double2(0.5 * (a2.x + b2.x), 0.5 * (a2.y - b2.y));
-        double2 zk = make_double2(h1.x - h2.y, h1.y + h2.x);
-        double2 zn = make_double2(h1.x + h2.y, -h1.y + h2.x);
-        double2* xp = xs + (size_t)pair * M;
-        const int kk = n - k;
-        if (Q.bluestein) {
-            xp[k] = cmul(zk, chirp[k]);
-            if (k != 0 && kk != k) xp[kk] = cmul(zn, chirp[kk]);
-        } else {
-            xp[bitrev(k, Q.logM)] = zk;
-            if (k != 0 && kk != k) xp[bitrev(kk, Q.logM)] = zn;
-        }
+        if (nsl > 1) __syncthreads();   // partials consumed before the next round overwrites them
     }
     __syncthreads();
 
-    if (Q.bluestein) {
-        fft_batch<false>(xs, M, Q.logM, Pp, -1, Q.tw, Q.log_tw);
+    if (blu) {
+        fft_dif_padded<-1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
         const double2* bh = Q.bhat + Q.bhat_off[rd.cap];
         for (int w = threadIdx.x; w < Pp * M; w += blockDim.x) {
-            int k = w % M;
-            xs[w] = cmul(xs[w], bh[k]);
+            const int p = w >> logM, k = w & (M - 1);
+            double2* e = xs + (size_t)p * seq + pidx(k);
+            *e = cmul(*e, bh[k]);
         }
         __syncthreads();
-        fft_batch<true>(xs, M, Q.logM, Pp, +1, Q.tw, Q.log_tw);
+        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
     } else {
-        fft_batch<true>(xs, M, Q.logM, Pp, +1, Q.tw, Q.log_tw);
+        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
     }
 
     // ---- store: real part -> first channel of the pair, imaginary part -> second
     for (int w = threadIdx.x; w < n * Pp; w += blockDim.x) {
         const int pair = w / n, j = w - pair * n;
-        const int ch = c0 + 2 * pair;
+        const int ch = cg * 4 + 2 * (pair0 + pair);
         if (ch >= Q.nb) continue;
-        double2 v = xs[(size_t)pair * M + j];
-        if (Q.bluestein) v = cmul(v, chirp[j]);
+        double2 v = xs[(size_t)pair * seq + pidx(j)];
+        if (blu) v = cmul(v, chirp[j]);
         Q.map[(long long)ch * Q.npix + rd.start + j] = v.x;
         if (ch + 1 < Q.nb) Q.map[(long long)(ch + 1) * Q.npix + rd.start + j] = v.y;
     }
@@ -677,27 +944,33 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
         count_launch();
         CB_LAUNCH_CHECK();
     }
-    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
-    // group rings into (bluestein, M) classes
-    std::vector<std::vector<int>> byclass(2 * 16);
-    for (int r = 0; r < nring; r++) {
-        int n = pl->h_rings[r].nph;
-        int bl = is_pow2(n) ? 0 : 1;
-        int M = n; if (bl) { M = 1; while (M < 2 * n - 1) M <<= 1; }
-        byclass[bl * 16 + ilog2(M)].push_back(r);
+    // per-ring FFT size; rings launched together by shared-memory footprint, longest first
+    for (auto& rd : pl->h_rings) {
+        const int n = rd.nph;
+        rd.bluestein = is_pow2(n) ? 0 : 1;
+        int M = n; if (rd.bluestein) { M = 1; while (M < 2 * n - 1) M <<= 1; }
+        rd.logM = ilog2(M);
     }
-    for (int bl = 0; bl < 2; bl++)
-        for (int lg = 0; lg < 16; lg++) {
-            auto& v = byclass[bl * 16 + lg];
+    CB_CUDA(cudaMemcpy(pl->d_rings, pl->h_rings.data(), sizeof(RingDesc) * nring, cudaMemcpyHostToDevice));
+    {
+        std::vector<std::vector<int>> bycls(16);
+        for (int r = 0; r < nring; r++) bycls[std::max(9, pl->h_rings[r].logM)].push_back(r);
+        for (int lg = 15; lg >= 9; lg--) {
+            auto& v = bycls[lg];
             if (v.empty()) continue;
+            std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return pl->h_rings[x].nph > pl->h_rings[y].nph; });
             PhaseClass pc;
-            pc.M = 1 << lg; pc.logM = lg; pc.bluestein = bl; pc.nrings = (int)v.size();
-            pc.P = std::max(1, std::min(8, 4096 / pc.M));
+            pc.Mmax = 1 << lg;
+            pc.P = (pc.Mmax <= 4096) ? 2 : 1;          // 2 pairs x 4096 points (padded) = 147 KB
+            pc.threads = (pc.Mmax >= 4096) ? 512 : 256;
+            pc.nrings = (int)v.size();
             CB_CUDA(cudaMalloc(&pc.d_rings, sizeof(int) * v.size()));
             CB_CUDA(cudaMemcpy(pc.d_rings, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
             pl->classes.push_back(pc);
         }
+    }
     CB_CUDA(cudaDeviceSynchronize());
     *plan_out = pl;
     return 0;
@@ -721,9 +994,11 @@ static long long ws_per_chan(const ShtPlan* pl, int layout) {
     return f + a;
 }
 
+static long long round4(long long n) { return (n + 3) & ~3LL; }
+
 extern "C" long long cora_b200_alm2map_workspace_bytes(void* plan, int layout, int nchan_batch) {
     if (!plan) return -1;
-    return ws_per_chan((ShtPlan*)plan, layout) * (long long)nchan_batch + 256;
+    return ws_per_chan((ShtPlan*)plan, layout) * round4(nchan_batch) + 256;
 }
 
 template <int SPIN>
@@ -735,6 +1010,7 @@ static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* a
     P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
     P.nrb = ceil_div(pl->nrn, LEG_RT);
     P.ncb = ceil_div(nb, SPIN ? LEG_NCH / 2 : LEG_NCH);
+    P.ncg = ceil_div(nb, 4);
     P.Lpad = ((pl->lmax + 1 + 7) / 8 + 2) * 8 + 8;   // recur8 runs one group past the end
     size_t smem = sizeof(double) * ((SPIN ? 4 : 2) * (size_t)P.Lpad + 2 * LEG_KC * LEG_BLD + LEG_WARPS * 2 * (SPIN ? 16 : 8) * LEG_ALD);
     CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
@@ -747,6 +1023,11 @@ static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* a
     return 0;
 }
 
+static size_t phase_smem(const PhaseClass& pc) {
+    const size_t seq = (size_t)pc.Mmax + pc.Mmax / 8 + 1;
+    return pc.P * seq * 16 + (pc.Mmax <= 512 ? (size_t)PH_MAXSLICE_ITEMS * 4 * 16 : 0);
+}
+
 static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, cudaStream_t st) {
     KTimer kt(K_PHASE, st);
     for (const auto& pc : pl->classes) {
@@ -754,12 +1035,9 @@ static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, c
         Q.F = F; Q.map = map; Q.npix = pl->npix; Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
         Q.tw = pl->d_tw; Q.chirp = pl->d_chirp; Q.bhat = pl->d_bhat;
         Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
-        Q.lmax = pl->lmax; Q.nb = nb; Q.M = pc.M; Q.logM = pc.logM; Q.bluestein = pc.bluestein; Q.log_tw = pl->log_tw;
-        int npairs = (nb + 1) / 2;
-        Q.P = std::min(pc.P, npairs);
-        dim3 grid(pc.nrings, ceil_div(npairs, Q.P));
-        size_t smem = (size_t)Q.P * pc.M * 16;
-        sht_phase_kernel<<<grid, 256, smem, st>>>(Q);
+        Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
+        dim3 grid(pc.nrings, Q.ncg * (2 / pc.P));
+        sht_phase_kernel<<<grid, pc.threads, phase_smem(pc), st>>>(Q);
         count_launch();
         CB_LAUNCH_CHECK();
     }
@@ -774,17 +1052,17 @@ extern "C" int cora_b200_alm2map(void* plan, const void* alm, int layout, long l
     ShtPlan* pl = (ShtPlan*)plan;
     cudaStream_t st = (cudaStream_t)stream;
     long long per = ws_per_chan(pl, layout);
-    long long cap = (ws_bytes - 256) / per;
-    CB_REQUIRE(cap >= 1, 4, "alm2map: workspace too small (%lld B; need %lld B per channel)", ws_bytes, per);
+    long long cap = ((ws_bytes - 256) / per) & ~3LL;   // F rows are padded to groups of 4 channels
+    CB_REQUIRE(cap >= 4, 4, "alm2map: workspace too small (%lld B; need %lld B per 4 channels)", ws_bytes, 4 * per);
     int nbmax = (int)std::min<long long>(cap, nchan);
-    if (nbmax >= 16) nbmax -= nbmax % 16; else if (nbmax >= 2) nbmax -= nbmax % 2;
+    if (nbmax < nchan && nbmax >= 16) nbmax -= nbmax % 16;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     for (int c0 = 0; c0 < nchan; c0 += nbmax) {
         int nb = std::min(nbmax, nchan - c0);
         double2* F = (double2*)ws;
         const double2* almT; long long stride; int chan0;
         if (layout == CORA_B200_ALM_PACKED) {
-            double2* T = (double2*)(ws + (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16 * nbmax);
+            double2* T = (double2*)(ws + (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16 * round4(nbmax));
             dim3 grid(ceil_div(pl->nalm, 32), ceil_div(nb, 32));
             { KTimer kt(K_LAYOUT, st);
               alm_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const double2*)alm + (long long)c0 * alm_stride, alm_stride, nb,
@@ -812,18 +1090,18 @@ extern "C" int cora_b200_alm2map_spin2(void* plan, const void* almE, const void*
     cudaStream_t st = (cudaStream_t)stream;
     const long long fbytes = (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16;
     const long long per = 2 * fbytes + ((layout == CORA_B200_ALM_PACKED) ? 2 * pl->nalm * 16 : 0);
-    long long cap = (ws_bytes - 256) / per;
-    CB_REQUIRE(cap >= 1, 4, "alm2map_spin2: workspace too small (%lld B; need %lld B per channel)", ws_bytes, per);
+    long long cap = ((ws_bytes - 256) / per) & ~3LL;
+    CB_REQUIRE(cap >= 4, 4, "alm2map_spin2: workspace too small (%lld B; need %lld B per 4 channels)", ws_bytes, 4 * per);
     int nbmax = (int)std::min<long long>(cap, nchan);
-    if (nbmax >= 8) nbmax -= nbmax % 8; else if (nbmax >= 2) nbmax -= nbmax % 2;
+    if (nbmax < nchan && nbmax >= 8) nbmax -= nbmax % 8;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     for (int c0 = 0; c0 < nchan; c0 += nbmax) {
         int nb = std::min(nbmax, nchan - c0);
         double2* FQ = (double2*)ws;
-        double2* FU = (double2*)(ws + fbytes * nbmax);
+        double2* FU = (double2*)(ws + fbytes * round4(nbmax));
         const double2 *pE, *pB; long long stride; int chan0;
         if (layout == CORA_B200_ALM_PACKED) {
-            double2* TE = (double2*)(ws + 2 * fbytes * nbmax);
+            double2* TE = (double2*)(ws + 2 * fbytes * round4(nbmax));
             double2* TB = TE + pl->nalm * nbmax;
             dim3 grid(ceil_div(pl->nalm, 32), ceil_div(nb, 32));
             { KTimer kt(K_LAYOUT, st);
