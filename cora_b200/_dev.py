@@ -50,6 +50,18 @@ def to_host(x):
     return h.numpy()
 
 
+_copy_streams = {}
+
+
+def copy_stream():
+    """Side stream for device->host copies overlapped with compute (one per device)."""
+    t = torch()
+    d = t.cuda.current_device()
+    if d not in _copy_streams:
+        _copy_streams[d] = t.cuda.Stream()
+    return _copy_streams[d]
+
+
 def empty(shape, dtype):
     return torch().empty(shape, dtype=dtype, device=device())
 

@@ -104,6 +104,11 @@ def ptr(t):
     return ctypes.c_void_p(t.ctypes.data)
 
 
+def ptr_off(t, nbytes):
+    """Device pointer of a torch tensor advanced by ``nbytes``."""
+    return ctypes.c_void_p(t.data_ptr() + int(nbytes))
+
+
 def stream_ptr(stream=None):
     import torch
 

@@ -688,7 +688,8 @@ __device__ void fft_dit_padded(double2* xs, int seq_stride, int M, int logM, int
 
 constexpr int PH_MAXSLICE_ITEMS = 512;   // fold work items (bin, pair, slice) staged for the slice reduction
 
-__global__ void __launch_bounds__(512) sht_phase_kernel(PhaseParams Q) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_phase_kernel(PhaseParams Q) {
     extern __shared__ __align__(16) double2 xs[];   // [P][pidx(Mmax)] + slice partials
     const int r = Q.ring_list[blockIdx.x];
     const RingDesc rd = Q.rings[r];
@@ -944,7 +945,8 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
         count_launch();
         CB_LAUNCH_CHECK();
     }
-    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
     // per-ring FFT size; rings launched together by shared-memory footprint, longest first
     for (auto& rd : pl->h_rings) {
@@ -1037,7 +1039,8 @@ static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, c
         Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
         Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
         dim3 grid(pc.nrings, Q.ncg * (2 / pc.P));
-        sht_phase_kernel<<<grid, pc.threads, phase_smem(pc), st>>>(Q);
+        if (pc.threads == 256) sht_phase_kernel<256><<<grid, 256, phase_smem(pc), st>>>(Q);
+        else sht_phase_kernel<512><<<grid, 512, phase_smem(pc), st>>>(Q);
         count_launch();
         CB_LAUNCH_CHECK();
     }

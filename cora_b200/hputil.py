@@ -75,6 +75,43 @@ def alm2map_device(alm_dev, nside, lmax, layout, alm_stride, nchan, out=None, st
     return out
 
 
+def alm2map_to_host(alm_panel, nside, lmax, nchan, nbatch=4):
+    """Scalar synthesis of a PANEL alm array straight into a pinned host array: the channels are
+    transformed in ``nbatch`` batches and every finished batch is copied back on a second
+    stream while the next one is computed (the PCIe copy of the float64 maps takes longer than
+    the transform itself)."""
+    t = _dev.torch()
+    npix = 12 * nside * nside
+    plan = _dev.sht_plan(nside, lmax)
+    host = t.empty((nchan, npix), dtype=t.float64, pin_memory=True)
+    cb = max(16, -(-nchan // nbatch))
+    cb += (-cb) % 16
+    main, side = t.cuda.current_stream(), _dev.copy_stream()
+    bufs = [_dev.empty((min(cb, nchan), npix), t.float64) for _ in range(2)]
+    ws, nbytes = _dev.sht_workspace(plan, _lib.ALM_PANEL, min(cb, nchan))
+    freed = [None, None]
+    stride = int(alm_panel.shape[1])
+    for i, c0 in enumerate(range(0, nchan, cb)):
+        n = min(cb, nchan - c0)
+        buf = bufs[i & 1]
+        if freed[i & 1] is not None:
+            main.wait_event(freed[i & 1])          # the copy out of this buffer has finished
+        _lib.call("cora_b200_alm2map", plan, _lib.ptr_off(alm_panel, 16 * c0), _lib.ALM_PANEL, stride, n, _lib.ptr(buf),
+                  _lib.ptr(ws), int(nbytes), _lib.stream_ptr(main))
+        done = t.cuda.Event()
+        done.record(main)
+        side.wait_event(done)
+        with t.cuda.stream(side):
+            host[c0 : c0 + n].copy_(buf[:n], non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record(side)
+        freed[i & 1] = ev
+    side.synchronize()
+    main.wait_stream(side)
+    _dev.traffic["d2h"] += host.numel() * 8
+    return host.numpy()
+
+
 def alm2map_spin2_device(almE_dev, almB_dev, nside, lmax, layout, alm_stride, nchan, outQ=None, outU=None, stream=None):
     t = _dev.torch()
     plan = _dev.sht_plan(nside, lmax)

@@ -176,5 +176,6 @@ def mkfullsky(corr, nside, alms=False, rng=None, *, seed=None, roots=None, gauss
         out = dense.reshape(numz, 1, L, L)
         return out if device_out else _dev.to_host(out)
 
-    sky = hputil.alm2map_device(panel, nside, maxl, _lib.ALM_PANEL, numz, numz)
-    return sky if device_out else _dev.to_host(sky)
+    if not device_out:
+        return hputil.alm2map_to_host(panel, nside, maxl, numz)
+    return hputil.alm2map_device(panel, nside, maxl, _lib.ALM_PANEL, numz, numz)
