@@ -18,6 +18,7 @@
 #include "cora_b200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
@@ -44,6 +45,7 @@ struct ShtPlan {
     int nside, lmax, nrn;           // nrn = 2*nside north rings incl. equator
     long long npix, nalm;
     double *d_cth, *d_sth;          // [nrn]
+    double2* d_rc;                  // [nalm] recurrence coefficients, row idx(l, m) holds those of step l -> l+1
     double* d_nm_mant;              // [lmax+1]   N_m = mant * 2^exp
     int* d_nm_exp;                  // [lmax+1]
     RingDesc* d_rings;              // [4*nside-1]
@@ -91,6 +93,24 @@ __device__ __forceinline__ void fft_batch(double2* x, int M, int logM, int P, in
         }
         __syncthreads();
     }
+}
+
+// lam_{l+1} = c1 x lam_l - c2 lam_{l-1}:  rc[idx(l, m)] = (c1, c2) of the step that produces l + 1
+// (zeros once l + 1 > lmax, so the recurrence runs cleanly off the end of the table).
+__global__ void recur_coef_kernel(double2* rc, int lmax) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (l < m || l > lmax) return;
+    const double ln = (double)(l + 1), mm = (double)m;
+    double a = 0.0, r = 0.0;
+    if (l + 1 <= lmax) {
+        a = sqrt((4.0 * ln * ln - 1.0) / (ln * ln - mm * mm));
+        if (l + 1 >= m + 2) {
+            const double lp = ln - 1.0;
+            r = a / sqrt((4.0 * lp * lp - 1.0) / (lp * lp - mm * mm));
+        }
+    }
+    rc[(long long)m * (2 * lmax + 1 - m) / 2 + l] = make_double2(a, r);
 }
 
 __global__ void twiddle_kernel(double2* tw, int n) {
@@ -176,6 +196,7 @@ struct LegParams {
     const double *cth, *sth;  // [nrn]
     const double* nm_mant;
     const int* nm_exp;
+    const double2* rc;        // [nalm] recurrence coefficients (a_{l+1}, a_{l+1}/a_l) at idx(l, m)  (ws kernel)
     int nside, lmax, nrn, nrb, ncb, Lpad, ncg;   // ncg = ceil(nb / 4) channel groups in F
 };
 
@@ -438,6 +459,305 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
                 const int cg = ch >> 2, cc = ch & 3;
                 Fo[(((long long)r_n * P.ncg + cg) * L + m) * 4 + cc] = make_double2(-(er + orr), -(ei + oi));
                 if (r_s != r_n) Fo[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cc] = make_double2(-(er - orr), -(ei - oi));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------- Legendre stage, warp-specialised (scalar)
+// Same arithmetic as sht_legendre_kernel<0>, restructured for the Blackwell SM: 4 producer warps
+// run the lambda_lm recurrence (one ring per lane) into a 4-deep ring of shared-memory A tiles,
+// 8 consumer warps do nothing but fragment loads and DMMAs (two consumers, 32 columns each,
+// share a producer's 32 rings), and the alm operand arrives through the TMA engine
+// (cp.async.bulk, one 512-byte row per instruction) into a 3-deep ring of B tiles.  All hand-offs
+// are mbarrier full/empty pairs; registers are moved from the producers to the consumers with
+// setmaxnreg.  The dependent FP64 chain of the recurrence never sits in a warp that issues DMMAs.
+#ifndef LWS_EXP
+#define LWS_EXP 0
+#endif
+namespace lws {
+constexpr int NCONS = 8, NPROD = 4, THREADS = 32 * (NCONS + NPROD);   // 3 warps per SM sub-partition
+constexpr int RT = 32 * NPROD;   // rings per work item
+constexpr int NCOL = 64;         // real columns per work item (32 channels)
+constexpr int GPC = 4;           // 8-l groups per B chunk
+constexpr int KC = 8 * GPC;      // l's per B chunk
+constexpr int NSB = 4, NSA = 3;   // B ring / A ring depth, both in chunks of GPC groups
+constexpr int ALD = 36;          // A tile [8][36]
+constexpr int BLD = 66;          // B tile [KC][66]  (66 = 2 mod 8: conflict-free fragment reads, 16-byte rows)
+constexpr int REG_PROD = 56, REG_CONS = 224;   // 2 x 224 + 56 = 3 x 168 per sub-partition
+}  // namespace lws
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    // test_wait, not try_wait: a poll must not suspend the thread until the hardware time limit
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra MBAR_DONE;\n"
+        " bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Persistent: one CTA per SM walks the work items (m, ring block, channel block) it is dealt
+// round-robin -- items are ordered by m, i.e. by decreasing cost, so the deal is balanced, and the
+// CTAs that run concurrently share the same few m (their alm rows hit in L2).  Roles run ahead of
+// each other across item boundaries: while the consumers drain item i and write its F rows, the
+// producers already compute the recurrence table and seeds of item i+1 and the TMA warp fetches
+// its first alm chunks.
+__global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegParams P, int nitems) {
+    using namespace lws;
+    extern __shared__ __align__(16) double smem[];
+    double2* Cs = (double2*)smem;                                   // [NSB][KC] recurrence coefficients of the chunk
+    double* Bs = (double*)(Cs + NSB * KC);                          // [NSB][KC][BLD]
+    double* As = Bs + NSB * KC * BLD;                               // [NPROD][NSA][GPC][8][ALD]
+    unsigned* balA = (unsigned*)(As + NPROD * NSA * GPC * 8 * ALD); // [NPROD][NSA][GPC] live-lane ballots
+    unsigned long long* bars = (unsigned long long*)(balA + NPROD * NSA * GPC);
+    unsigned long long* fullA = bars;                               // [NPROD][NSA]
+    unsigned long long* emptyA = fullA + NPROD * NSA;               // [NPROD][NSA]
+    unsigned long long* fullB = emptyA + NPROD * NSA;               // [NSB]
+    unsigned long long* emptyB = fullB + NSB;                       // [NSB]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lmax = P.lmax;
+
+    if (tid == 0) {
+        for (int i = 0; i < NPROD * NSA; i++) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 2); }
+        for (int i = 0; i < NSB; i++) { mbar_init(fullB + i, 32); mbar_init(emptyB + i, NCONS + NPROD); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= NCONS) {
+        // ================================================================= producer warp: lambda_lm
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_PROD));
+        const int p = warp - NCONS;
+        double* Ap = As + (size_t)p * NSA * GPC * 8 * ALD;
+        unsigned cglob = 0;                       // chunks produced so far
+        // alm chunks: producer p also feeds the B ring with the chunks whose running number is
+        // p mod NPROD (one 512-byte row per lane through the TMA engine), polled from its wait loops
+        // so that it never blocks the recurrence.  (b_it, b_c) = item and chunk of the next one.
+        int b_it = blockIdx.x, b_c = 0;
+        unsigned b_glob = 0;
+        auto b_nchunk = [&](int it) { return (lmax - it / (P.ncb * P.nrb) + 1 + KC - 1) / KC; };
+        auto b_advance = [&](int n) {
+            for (int i = 0; i < n && b_it < nitems; i++) {
+                b_glob++;
+                if (++b_c == b_nchunk(b_it)) { b_c = 0; b_it += gridDim.x; }
+            }
+        };
+        b_advance(p);
+        auto service_B = [&]() {
+            if (b_it >= nitems) return;
+            const int sb = b_glob % NSB;
+            unsigned ready = 0;
+            if (lane == 0) ready = mbar_test(emptyB + sb, ((b_glob / NSB) & 1) ^ 1) ? 1u : 0u;
+            if (!__shfl_sync(0xffffffffu, ready, 0)) return;
+            const int bm = b_it / (P.ncb * P.nrb), bcb = b_it % P.ncb;
+            const int bnk = lmax - bm + 1;
+            const long long brow0 = (long long)bm * (2 * lmax + 1 - bm) / 2 + bm;   // idx(l = m, m)
+            const int ch0 = bcb * (NCOL / 2);
+            const int nvalid = min(NCOL / 2, P.nb - ch0);                           // channels actually present
+            double* dst = Bs + (size_t)sb * KC * BLD + lane * BLD;
+            const int k = b_c * KC + lane;
+            const int nrows = min(KC, bnk - b_c * KC);
+            if (k < bnk) {
+                bulk_g2s(dst, P.almT + (brow0 + k) * P.alm_stride + P.chan0 + ch0, (unsigned)nvalid * 16u, fullB + sb);
+            } else {
+                // rows past lmax: zeros (lambda is 0 there, but 0 x stale shared memory may be NaN)
+                for (int j = 0; j < NCOL; j++) dst[j] = 0.0;
+                Cs[sb * KC + lane] = make_double2(0.0, 0.0);
+            }
+            if (lane == 0) {
+                bulk_g2s(Cs + sb * KC, P.rc + brow0 + (long long)b_c * KC, (unsigned)nrows * 16u, fullB + sb);
+                mbar_arrive_expect_tx(fullB + sb, (unsigned)nrows * ((unsigned)nvalid + 1u) * 16u);
+            } else {
+                mbar_arrive(fullB + sb);
+            }
+            b_advance(NPROD);
+        };
+        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+            const int rb = (it / P.ncb) % P.nrb;
+            const int m = it / (P.ncb * P.nrb);
+            const int nk = lmax - m + 1;
+            const int ngroups = (nk + 7) / 8;
+            // ring owned by this lane: octet (lane/8)*NPROD + p of the item's 16 octets
+            const int rn = rb * RT + (((lane >> 3) * NPROD + p) << 3) + (lane & 7);
+            double x = 0.0, p_cur = 0.0, p_prev = 0.0;
+            int e = -(1 << 20);
+            if (rn < P.nrn) {
+                x = P.cth[rn];
+                double bm = P.sth[rn];
+                long long be = 0;
+                norm_frexp(bm, be);
+                double rm = 1.0;
+                long long re = 0;
+                int n = m;
+                while (n) {
+                    if (n & 1) { rm *= bm; re += be; norm_frexp(rm, re); }
+                    bm *= bm; be *= 2; norm_frexp(bm, be);
+                    n >>= 1;
+                }
+                rm *= P.nm_mant[m];
+                re += P.nm_exp[m];
+                norm_frexp(rm, re);
+                if (m & 1) rm = -rm;
+                long long q = (re >= 0) ? 0 : -((-re) / 256);
+                e = (int)(q * 256);
+                p_cur = ldexp(rm, (int)(re - (long long)e));
+            }
+            const int nchunk = (ngroups + GPC - 1) / GPC;
+            for (int c = 0; c < nchunk; c++, cglob++) {
+                const int sa = cglob % NSA, sbc = cglob % NSB;
+                const int ng = min(GPC, ngroups - c * GPC);
+                service_B();
+                // hand-offs are per chunk (an mbarrier probe costs ~100-150 cycles): the chunk's
+                // coefficients have landed, and the consumers are done with this A stage
+                for (;;) {
+                    unsigned ready = 0;
+                    if (lane == 0)
+                        ready = (mbar_test(fullB + sbc, (cglob / NSB) & 1) && mbar_test(emptyA + p * NSA + sa, ((cglob / NSA) & 1) ^ 1)) ? 1u : 0u;
+                    if (__shfl_sync(0xffffffffu, ready, 0)) break;
+                    service_B();
+                }
+                for (int grp = 0; grp < ng; grp++) {
+                    double* Ab = Ap + (sa * GPC + grp) * 8 * ALD;
+                    const bool live = (e == 0);
+                    double2 cf[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) cf[j] = Cs[sbc * KC + grp * 8 + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int arow = (j & 1) * 4 + (j >> 1);
+                        Ab[arow * ALD + lane] = live ? p_cur : 0.0;
+#if LWS_EXP != 1
+                        const double pn = fma(cf[j].x * x, p_cur, -cf[j].y * p_prev);
+                        p_prev = p_cur;
+                        p_cur = pn;
+#else
+                        p_cur = cf[j].x;   // experiment: no FP64 arithmetic in the producer
+#endif
+                    }
+                    if (e < 0 && ((__double2hiint(p_cur) >> 20) & 0x7ff) > 1023 + 128) {
+                        p_cur *= 0x1p-256;
+                        p_prev *= 0x1p-256;
+                        e += 256;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, live);
+                    if (lane == 0) balA[(p * NSA + sa) * GPC + grp] = bal;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(fullA + p * NSA + sa);
+                    mbar_arrive(emptyB + sbc);
+                }
+            }
+        }
+        while (b_it < nitems) service_B();   // (nothing left in practice: a chunk is consumed before its groups end)
+    } else {
+        // ================================================================= consumer warp: DMMA
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_CONS));
+        const int p = warp >> 1, h = warp & 1;
+        const int g = lane >> 2, t = lane & 3;
+        const double* Ap = As + (size_t)p * NSA * GPC * 8 * ALD;
+        const int L = lmax + 1;
+        const int nring_tot = 4 * P.nside - 1;
+        unsigned cglob = 0;
+        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+            const int cb = it % P.ncb;
+            const int rb = (it / P.ncb) % P.nrb;
+            const int m = it / (P.ncb * P.nrb);
+            const int nk = lmax - m + 1;
+            const int ngroups = (nk + 7) / 8;
+            double acc[2][4][4][2];
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][b][c][0] = acc[a][b][c][1] = 0.0;
+            const int nchunk = (ngroups + GPC - 1) / GPC;
+#pragma unroll 1
+            for (int c = 0; c < nchunk; c++, cglob++) {
+                const int sb = cglob % NSB, sa = cglob % NSA;
+                const int ng = min(GPC, ngroups - c * GPC);
+                mbar_wait(fullB + sb, (cglob / NSB) & 1);
+                mbar_wait(fullA + p * NSA + sa, (cglob / NSA) & 1);
+#pragma unroll 1
+                for (int grp = 0; grp < ng; grp++) {
+                    unsigned bal = balA[(p * NSA + sa) * GPC + grp];
+#if LWS_EXP == 2
+                    bal = 0;   // experiment: consumers skip the DMMAs
+#endif
+                    if (!bal) continue;
+                    const double* Ac = Ap + (sa * GPC + grp) * 8 * ALD;
+                    const double* Bb = Bs + (size_t)sb * KC * BLD + 32 * h;
+                    int pm[4];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++) pm[mb] = (int)((bal >> (8 * mb)) & 0xffu);
+                    double af[2][4], bf[2][4];
+#pragma unroll
+                    for (int par = 0; par < 2; par++) {
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(par * 4 + t) * ALD + 8 * mb + g];
+#pragma unroll
+                        for (int nb = 0; nb < 4; nb++) bf[par][nb] = Bb[(grp * 8 + 2 * t + par) * BLD + 8 * nb + g];
+                    }
+#pragma unroll
+                    for (int par = 0; par < 2; par++)
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++)
+                                dmma884_p(acc[par][mb][nb][0], acc[par][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(emptyA + p * NSA + sa);
+                    mbar_arrive(emptyB + sb);
+                }
+            }
+            // ---- epilogue: north = even + odd, south = even - odd;  F[ring][cg][m][4]
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                const int rr = rb * RT + ((mb * NPROD + p) << 3) + g;   // north ring index
+                if (rr >= P.nrn) continue;
+                const int r_s = nring_tot - 1 - rr;                      // mirror ring
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) {
+                    const int ch = cb * (NCOL / 2) + 16 * h + 4 * nb + t;
+                    if (ch >= P.nb) continue;
+                    const double er = acc[0][mb][nb][0], ei = acc[0][mb][nb][1];
+                    const double orr = acc[1][mb][nb][0], oi = acc[1][mb][nb][1];
+                    const int cg = ch >> 2, cq = ch & 3;
+                    P.F[(((long long)rr * P.ncg + cg) * L + m) * 4 + cq] = make_double2(er + orr, ei + oi);
+                    if (r_s != rr) P.F[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cq] = make_double2(er - orr, ei - oi);
+                }
             }
         }
     }
@@ -892,6 +1212,10 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
         }
     }
 
+    CB_CUDA(cudaMalloc(&pl->d_rc, sizeof(double2) * pl->nalm));
+    recur_coef_kernel<<<dim3(ceil_div(lmax + 1, 128), lmax + 1), 128>>>(pl->d_rc, lmax);
+    count_launch();
+    CB_LAUNCH_CHECK();
     CB_CUDA(cudaMalloc(&pl->d_cth, sizeof(double) * pl->nrn));
     CB_CUDA(cudaMalloc(&pl->d_sth, sizeof(double) * pl->nrn));
     CB_CUDA(cudaMalloc(&pl->d_nm_mant, sizeof(double) * (lmax + 1)));
@@ -981,6 +1305,7 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
 extern "C" int cora_b200_sht_plan_destroy(void* plan) {
     if (!plan) return 0;
     ShtPlan* pl = (ShtPlan*)plan;
+    cudaFree(pl->d_rc);
     cudaFree(pl->d_cth); cudaFree(pl->d_sth); cudaFree(pl->d_nm_mant); cudaFree(pl->d_nm_exp);
     cudaFree(pl->d_rings); cudaFree(pl->d_tw); cudaFree(pl->d_chirp); cudaFree(pl->d_bhat);
     cudaFree(pl->d_chirp_off); cudaFree(pl->d_bhat_off);
@@ -1003,17 +1328,40 @@ extern "C" long long cora_b200_alm2map_workspace_bytes(void* plan, int layout, i
     return ws_per_chan((ShtPlan*)plan, layout) * round4(nchan_batch) + 256;
 }
 
+// 1: warp-specialised scalar Legendre kernel (default); 0: the single-role kernel.  Switchable
+// (CORA_B200_LEGENDRE_WS=0) so the two can be compared on the device.
+static int g_legendre_ws = [] { const char* e = getenv("CORA_B200_LEGENDRE_WS"); return (e && e[0] == '0') ? 0 : 1; }();
+
 template <int SPIN>
 static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* almB, long long alm_stride, int chan0, int nb,
                         double2* F, double2* F2, cudaStream_t st) {
     LegParams P;
     P.almT = almT; P.almB = almB; P.alm_stride = alm_stride; P.chan0 = chan0; P.nb = nb; P.F = F; P.F2 = F2;
-    P.cth = pl->d_cth; P.sth = pl->d_sth; P.nm_mant = pl->d_nm_mant; P.nm_exp = pl->d_nm_exp;
+    P.cth = pl->d_cth; P.sth = pl->d_sth; P.nm_mant = pl->d_nm_mant; P.nm_exp = pl->d_nm_exp; P.rc = pl->d_rc;
     P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
     P.nrb = ceil_div(pl->nrn, LEG_RT);
     P.ncb = ceil_div(nb, SPIN ? LEG_NCH / 2 : LEG_NCH);
     P.ncg = ceil_div(nb, 4);
     P.Lpad = ((pl->lmax + 1 + 7) / 8 + 2) * 8 + 8;   // recur8 runs one group past the end
+    if (SPIN == 0 && g_legendre_ws) {
+        using namespace lws;
+        P.nrb = ceil_div(pl->nrn, RT);
+        P.ncb = ceil_div(nb, NCOL / 2);
+        size_t smem = 16 * (size_t)NSB * KC + 8 * ((size_t)NSB * KC * BLD + (size_t)NPROD * NSA * GPC * 8 * ALD) +
+                      4 * NPROD * NSA * GPC + 8 * (2 * NPROD * NSA + 2 * NSB) + 64;
+        CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
+        CB_CUDA(cudaFuncSetAttribute(sht_legendre_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long nitems = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
+        CB_REQUIRE(nitems < 2147483647LL, 3, "alm2map: too many Legendre work items (%lld)", nitems);
+        int dev, nsm;
+        CB_CUDA(cudaGetDevice(&dev));
+        CB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        const unsigned grid = (unsigned)std::min<long long>(nitems, nsm);   // persistent: one CTA per SM
+        { KTimer kt(K_LEGENDRE, st); sht_legendre_ws_kernel<<<grid, THREADS, smem, st>>>(P, (int)nitems); }
+        count_launch();
+        CB_LAUNCH_CHECK();
+        return 0;
+    }
     size_t smem = sizeof(double) * ((SPIN ? 4 : 2) * (size_t)P.Lpad + 2 * LEG_KC * LEG_BLD + LEG_WARPS * 2 * (SPIN ? 16 : 8) * LEG_ALD);
     CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
     CB_CUDA(cudaFuncSetAttribute(sht_legendre_kernel<SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
