@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "cora_b200.h"
 
+#include <cuda.h>   // CUtensorMap (the encode entry point is fetched through the runtime, no -lcuda)
+
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -465,26 +467,34 @@ __global__ void __launch_bounds__(LEG_THREADS, 1) sht_legendre_kernel(LegParams 
 }
 
 // ------------------------------------------------- Legendre stage, warp-specialised (scalar)
-// Same arithmetic as sht_legendre_kernel<0>, restructured for the Blackwell SM: 4 producer warps
-// run the lambda_lm recurrence (one ring per lane) into a 4-deep ring of shared-memory A tiles,
-// 8 consumer warps do nothing but fragment loads and DMMAs (two consumers, 32 columns each,
-// share a producer's 32 rings), and the alm operand arrives through the TMA engine
-// (cp.async.bulk, one 512-byte row per instruction) into a 3-deep ring of B tiles.  All hand-offs
-// are mbarrier full/empty pairs; registers are moved from the producers to the consumers with
-// setmaxnreg.  The dependent FP64 chain of the recurrence never sits in a warp that issues DMMAs.
-#ifndef LWS_EXP
-#define LWS_EXP 0
-#endif
+// Same arithmetic as sht_legendre_kernel<0>, restructured for the Blackwell SM.  4 producer warps
+// run the lambda_lm recurrence (one ring per lane) into a ring of shared-memory A tiles; 8 consumer
+// warps do nothing but fragment loads and DMMAs (two consumers, 32 columns each, share a
+// producer's 32 rings); the alm operand arrives through the TMA engine as 2-D tiled loads
+// (cp.async.bulk.tensor, 128-byte swizzle; SASS UTMALDG) together with the chunk's recurrence
+// coefficients (precomputed once per plan) into a 4-deep ring of B tiles.  All hand-offs are
+// mbarrier full/empty pairs at chunk (32 l) granularity -- one probe costs 100-150 cycles.
+//
+// Measured behaviour that shapes this (profiles/r01): scalar FP64 and DMMA share one pipe and a
+// warp's DFMA is starved while two other warps keep that pipe full of DMMAs, so a warp that
+// alternates recurrence and DMMA (sht_legendre_kernel) serialises them; here the recurrence lives
+// in its own warps, runs ahead by up to three chunks and only costs pipe time when it executes.
 namespace lws {
-constexpr int NCONS = 8, NPROD = 4, THREADS = 32 * (NCONS + NPROD);   // 3 warps per SM sub-partition
-constexpr int RT = 32 * NPROD;   // rings per work item
+constexpr int NCONS = 8, NPROD = 4, RPL = 1;   // consumer warps; producer warps; rings per producer lane
+constexpr int NVP = NPROD * RPL;                // ring groups of 32 ("virtual producers")
+constexpr int THREADS = 32 * (NCONS + NPROD);   // 12 warps: 2 consumers + 1 producer per SM sub-partition
+constexpr int RT = 32 * NVP;     // rings per work item
 constexpr int NCOL = 64;         // real columns per work item (32 channels)
 constexpr int GPC = 4;           // 8-l groups per B chunk
 constexpr int KC = 8 * GPC;      // l's per B chunk
 constexpr int NSB = 4, NSA = 3;   // B ring / A ring depth, both in chunks of GPC groups
 constexpr int ALD = 36;          // A tile [8][36]
-constexpr int BLD = 66;          // B tile [KC][66]  (66 = 2 mod 8: conflict-free fragment reads, 16-byte rows)
-constexpr int REG_PROD = 56, REG_CONS = 224;   // 2 x 224 + 56 = 3 x 168 per sub-partition
+// B tile of one chunk: NCOL/16 column blocks of [KC rows][16 doubles = 128 B], each written by one
+// 2-D TMA box with the 128-byte swizzle (16-byte unit u of row r lands at unit u ^ (r & 7)), which
+// makes the DMMA fragment reads below conflict-free without padding.
+constexpr int BBLK = KC * 16;    // doubles per column block
+constexpr int BSTAGE = (NCOL / 16) * BBLK;
+// (no setmaxnreg: 12 warps x 168 registers fill the register file and both roles fit in 168)
 }  // namespace lws
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -530,14 +540,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // each other across item boundaries: while the consumers drain item i and write its F rows, the
 // producers already compute the recurrence table and seeds of item i+1 and the TMA warp fetches
 // its first alm chunks.
-__global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegParams P, int nitems) {
+// 2-D tiled TMA load (SASS: UTMALDG): box of the tensor map at (c0 = column in doubles, c1 = row)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegParams P, int nitems,
+                                                                           const __grid_constant__ CUtensorMap tmapB) {
     using namespace lws;
     extern __shared__ __align__(16) double smem[];
-    double2* Cs = (double2*)smem;                                   // [NSB][KC] recurrence coefficients of the chunk
-    double* Bs = (double*)(Cs + NSB * KC);                          // [NSB][KC][BLD]
-    double* As = Bs + NSB * KC * BLD;                               // [NPROD][NSA][GPC][8][ALD]
-    unsigned* balA = (unsigned*)(As + NPROD * NSA * GPC * 8 * ALD); // [NPROD][NSA][GPC] live-lane ballots
-    unsigned long long* bars = (unsigned long long*)(balA + NPROD * NSA * GPC);
+    // the 128-byte swizzle pattern repeats every 1024 bytes of shared-memory address: align the B ring explicitly
+    double* Bs = (double*)((char*)smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u));   // [NSB][NCOL/16][KC][16]
+    double2* Cs = (double2*)(Bs + NSB * BSTAGE);                    // [NSB][KC] recurrence coefficients of the chunk
+    double* As = (double*)(Cs + NSB * KC);                          // [NVP][NSA][GPC][8][ALD]
+    unsigned* balA = (unsigned*)(As + NVP * NSA * GPC * 8 * ALD);   // [NVP][NSA][GPC] live-lane ballots
+    unsigned long long* bars = (unsigned long long*)(balA + NVP * NSA * GPC);
     unsigned long long* fullA = bars;                               // [NPROD][NSA]
     unsigned long long* emptyA = fullA + NPROD * NSA;               // [NPROD][NSA]
     unsigned long long* fullB = emptyA + NPROD * NSA;               // [NSB]
@@ -547,7 +567,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
     const int lmax = P.lmax;
 
     if (tid == 0) {
-        for (int i = 0; i < NPROD * NSA; i++) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 2); }
+        for (int i = 0; i < NPROD * NSA; i++) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 2 * RPL); }
         for (int i = 0; i < NSB; i++) { mbar_init(fullB + i, 32); mbar_init(emptyB + i, NCONS + NPROD); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -555,9 +575,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
 
     if (warp >= NCONS) {
         // ================================================================= producer warp: lambda_lm
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_PROD));
         const int p = warp - NCONS;
-        double* Ap = As + (size_t)p * NSA * GPC * 8 * ALD;
         unsigned cglob = 0;                       // chunks produced so far
         // alm chunks: producer p also feeds the B ring with the chunks whose running number is
         // p mod NPROD (one 512-byte row per lane through the TMA engine), polled from its wait loops
@@ -581,21 +599,17 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
             const int bm = b_it / (P.ncb * P.nrb), bcb = b_it % P.ncb;
             const int bnk = lmax - bm + 1;
             const long long brow0 = (long long)bm * (2 * lmax + 1 - bm) / 2 + bm;   // idx(l = m, m)
-            const int ch0 = bcb * (NCOL / 2);
-            const int nvalid = min(NCOL / 2, P.nb - ch0);                           // channels actually present
-            double* dst = Bs + (size_t)sb * KC * BLD + lane * BLD;
-            const int k = b_c * KC + lane;
             const int nrows = min(KC, bnk - b_c * KC);
-            if (k < bnk) {
-                bulk_g2s(dst, P.almT + (brow0 + k) * P.alm_stride + P.chan0 + ch0, (unsigned)nvalid * 16u, fullB + sb);
-            } else {
-                // rows past lmax: zeros (lambda is 0 there, but 0 x stale shared memory may be NaN)
-                for (int j = 0; j < NCOL; j++) dst[j] = 0.0;
-                Cs[sb * KC + lane] = make_double2(0.0, 0.0);
-            }
+            // coefficient rows past lmax: zeros (the alm rows there are finite -- they belong to the next m or
+            // are zero-filled by the TMA unit beyond the tensor -- and meet lambda = 0)
+            if (lane >= nrows) Cs[sb * KC + lane] = make_double2(0.0, 0.0);
             if (lane == 0) {
+                double* dst = Bs + (size_t)sb * BSTAGE;
+                const int row = (int)(brow0 + (long long)b_c * KC);
+#pragma unroll
+                for (int jb = 0; jb < NCOL / 16; jb++) tma_load_2d(dst + jb * BBLK, &tmapB, bcb * NCOL + 16 * jb, row, fullB + sb);
                 bulk_g2s(Cs + sb * KC, P.rc + brow0 + (long long)b_c * KC, (unsigned)nrows * 16u, fullB + sb);
-                mbar_arrive_expect_tx(fullB + sb, (unsigned)nrows * ((unsigned)nvalid + 1u) * 16u);
+                mbar_arrive_expect_tx(fullB + sb, (unsigned)(BSTAGE * 8) + (unsigned)nrows * 16u);
             } else {
                 mbar_arrive(fullB + sb);
             }
@@ -606,30 +620,37 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
             const int m = it / (P.ncb * P.nrb);
             const int nk = lmax - m + 1;
             const int ngroups = (nk + 7) / 8;
-            // ring owned by this lane: octet (lane/8)*NPROD + p of the item's 16 octets
-            const int rn = rb * RT + (((lane >> 3) * NPROD + p) << 3) + (lane & 7);
-            double x = 0.0, p_cur = 0.0, p_prev = 0.0;
-            int e = -(1 << 20);
-            if (rn < P.nrn) {
-                x = P.cth[rn];
-                double bm = P.sth[rn];
-                long long be = 0;
-                norm_frexp(bm, be);
-                double rm = 1.0;
-                long long re = 0;
-                int n = m;
-                while (n) {
-                    if (n & 1) { rm *= bm; re += be; norm_frexp(rm, re); }
-                    bm *= bm; be *= 2; norm_frexp(bm, be);
-                    n >>= 1;
+            // RPL rings per lane (independent recurrence chains -> the FP64 latency overlaps): ring group
+            // v = p * RPL + u; inside a group the lane owns octet (lane/8)*NVP + v of the item's octets
+            double x[RPL], p_cur[RPL], p_prev[RPL];
+            int e[RPL];
+#pragma unroll
+            for (int u = 0; u < RPL; u++) {
+                const int v = p * RPL + u;
+                const int rn = rb * RT + (((lane >> 3) * NVP + v) << 3) + (lane & 7);
+                x[u] = 0.0; p_cur[u] = 0.0; p_prev[u] = 0.0;
+                e[u] = -(1 << 20);
+                if (rn < P.nrn) {
+                    x[u] = P.cth[rn];
+                    double bm = P.sth[rn];
+                    long long be = 0;
+                    norm_frexp(bm, be);
+                    double rm = 1.0;
+                    long long re = 0;
+                    int n = m;
+                    while (n) {
+                        if (n & 1) { rm *= bm; re += be; norm_frexp(rm, re); }
+                        bm *= bm; be *= 2; norm_frexp(bm, be);
+                        n >>= 1;
+                    }
+                    rm *= P.nm_mant[m];
+                    re += P.nm_exp[m];
+                    norm_frexp(rm, re);
+                    if (m & 1) rm = -rm;
+                    long long q = (re >= 0) ? 0 : -((-re) / 256);
+                    e[u] = (int)(q * 256);
+                    p_cur[u] = ldexp(rm, (int)(re - (long long)e[u]));
                 }
-                rm *= P.nm_mant[m];
-                re += P.nm_exp[m];
-                norm_frexp(rm, re);
-                if (m & 1) rm = -rm;
-                long long q = (re >= 0) ? 0 : -((-re) / 256);
-                e = (int)(q * 256);
-                p_cur = ldexp(rm, (int)(re - (long long)e));
             }
             const int nchunk = (ngroups + GPC - 1) / GPC;
             for (int c = 0; c < nchunk; c++, cglob++) {
@@ -646,30 +667,37 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                     service_B();
                 }
                 for (int grp = 0; grp < ng; grp++) {
-                    double* Ab = Ap + (sa * GPC + grp) * 8 * ALD;
-                    const bool live = (e == 0);
+                    bool live[RPL];
+                    double* Ab[RPL];
+#pragma unroll
+                    for (int u = 0; u < RPL; u++) {
+                        live[u] = (e[u] == 0);
+                        Ab[u] = As + ((size_t)((p * RPL + u) * NSA + sa) * GPC + grp) * 8 * ALD;
+                    }
                     double2 cf[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) cf[j] = Cs[sbc * KC + grp * 8 + j];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int arow = (j & 1) * 4 + (j >> 1);
-                        Ab[arow * ALD + lane] = live ? p_cur : 0.0;
-#if LWS_EXP != 1
-                        const double pn = fma(cf[j].x * x, p_cur, -cf[j].y * p_prev);
-                        p_prev = p_cur;
-                        p_cur = pn;
-#else
-                        p_cur = cf[j].x;   // experiment: no FP64 arithmetic in the producer
-#endif
+#pragma unroll
+                        for (int u = 0; u < RPL; u++) {
+                            Ab[u][arow * ALD + lane] = live[u] ? p_cur[u] : 0.0;
+                            const double pn = fma(cf[j].x * x[u], p_cur[u], -cf[j].y * p_prev[u]);
+                            p_prev[u] = p_cur[u];
+                            p_cur[u] = pn;
+                        }
                     }
-                    if (e < 0 && ((__double2hiint(p_cur) >> 20) & 0x7ff) > 1023 + 128) {
-                        p_cur *= 0x1p-256;
-                        p_prev *= 0x1p-256;
-                        e += 256;
+#pragma unroll
+                    for (int u = 0; u < RPL; u++) {
+                        if (e[u] < 0 && ((__double2hiint(p_cur[u]) >> 20) & 0x7ff) > 1023 + 128) {
+                            p_cur[u] *= 0x1p-256;
+                            p_prev[u] *= 0x1p-256;
+                            e[u] += 256;
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, live[u]);
+                        if (lane == 0) balA[((p * RPL + u) * NSA + sa) * GPC + grp] = bal;
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, live);
-                    if (lane == 0) balA[(p * NSA + sa) * GPC + grp] = bal;
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -681,10 +709,10 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
         while (b_it < nitems) service_B();   // (nothing left in practice: a chunk is consumed before its groups end)
     } else {
         // ================================================================= consumer warp: DMMA
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_CONS));
-        const int p = warp >> 1, h = warp & 1;
+        const int v = warp >> 1, h = warp & 1;     // ring group, column half
+        const int p = v / RPL;                       // the producer warp that feeds this ring group
         const int g = lane >> 2, t = lane & 3;
-        const double* Ap = As + (size_t)p * NSA * GPC * 8 * ALD;
+        const double* Ap = As + (size_t)v * NSA * GPC * 8 * ALD;
         const int L = lmax + 1;
         const int nring_tot = 4 * P.nside - 1;
         unsigned cglob = 0;
@@ -710,13 +738,10 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                 mbar_wait(fullA + p * NSA + sa, (cglob / NSA) & 1);
 #pragma unroll 1
                 for (int grp = 0; grp < ng; grp++) {
-                    unsigned bal = balA[(p * NSA + sa) * GPC + grp];
-#if LWS_EXP == 2
-                    bal = 0;   // experiment: consumers skip the DMMAs
-#endif
+                    const unsigned bal = balA[(v * NSA + sa) * GPC + grp];
                     if (!bal) continue;
                     const double* Ac = Ap + (sa * GPC + grp) * 8 * ALD;
-                    const double* Bb = Bs + (size_t)sb * KC * BLD + 32 * h;
+                    const double* Bb = Bs + (size_t)sb * BSTAGE;
                     int pm[4];
 #pragma unroll
                     for (int mb = 0; mb < 4; mb++) pm[mb] = (int)((bal >> (8 * mb)) & 0xffu);
@@ -726,7 +751,12 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
 #pragma unroll
                         for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(par * 4 + t) * ALD + 8 * mb + g];
 #pragma unroll
-                        for (int nb = 0; nb < 4; nb++) bf[par][nb] = Bb[(grp * 8 + 2 * t + par) * BLD + 8 * nb + g];
+                        for (int nb = 0; nb < 4; nb++) {
+                            // column 32h + 8nb + g of row r: block 2h + nb/2, 16-byte unit 4(nb&1) + g/2, swizzled
+                            const int r = grp * 8 + 2 * t + par;
+                            const int unit = (4 * (nb & 1) + (g >> 1)) ^ (r & 7);
+                            bf[par][nb] = Bb[(2 * h + (nb >> 1)) * BBLK + r * 16 + unit * 2 + (g & 1)];
+                        }
                     }
 #pragma unroll
                     for (int par = 0; par < 2; par++)
@@ -745,7 +775,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
             // ---- epilogue: north = even + odd, south = even - odd;  F[ring][cg][m][4]
 #pragma unroll
             for (int mb = 0; mb < 4; mb++) {
-                const int rr = rb * RT + ((mb * NPROD + p) << 3) + g;   // north ring index
+                const int rr = rb * RT + ((mb * NVP + v) << 3) + g;   // north ring index
                 if (rr >= P.nrn) continue;
                 const int r_s = nring_tot - 1 - rr;                      // mirror ring
 #pragma unroll
@@ -1347,8 +1377,33 @@ static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* a
         using namespace lws;
         P.nrb = ceil_div(pl->nrn, RT);
         P.ncb = ceil_div(nb, NCOL / 2);
-        size_t smem = 16 * (size_t)NSB * KC + 8 * ((size_t)NSB * KC * BLD + (size_t)NPROD * NSA * GPC * 8 * ALD) +
-                      4 * NPROD * NSA * GPC + 8 * (2 * NPROD * NSA + 2 * NSB) + 64;
+        size_t smem = 16 * (size_t)NSB * KC + 8 * ((size_t)NSB * BSTAGE + (size_t)NVP * NSA * GPC * 8 * ALD) +
+                      4 * NVP * NSA * GPC + 8 * (2 * NPROD * NSA + 2 * NSB) + 1024;
+        // tensor map over this batch's alm panel columns: [nalm rows][2 nb doubles], row pitch = panel stride;
+        // columns past the batch are out of bounds -> zero-filled by the TMA unit
+        CUtensorMap tmap;
+        {
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static EncodeFn encode = nullptr;
+            if (!encode) {
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult qres;
+                CB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+                CB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, 5, "alm2map: cuTensorMapEncodeTiled is not available");
+                encode = (EncodeFn)fn;
+            }
+            const cuuint64_t gdim[2] = {(cuuint64_t)nb * 2, (cuuint64_t)pl->nalm};
+            const cuuint64_t gstr[1] = {(cuuint64_t)alm_stride * 16};
+            const cuuint32_t box[2] = {16, (cuuint32_t)KC};
+            const cuuint32_t estr[2] = {1, 1};
+            CB_REQUIRE(alm_stride % 1 == 0 && ((uintptr_t)(almT + chan0) % 16) == 0, 5, "alm2map: alm panel must be 16-byte aligned");
+            CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)(almT + chan0), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CB_REQUIRE(cr == CUDA_SUCCESS, 5, "alm2map: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        }
         CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
         CB_CUDA(cudaFuncSetAttribute(sht_legendre_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long nitems = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
@@ -1357,7 +1412,7 @@ static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* a
         CB_CUDA(cudaGetDevice(&dev));
         CB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         const unsigned grid = (unsigned)std::min<long long>(nitems, nsm);   // persistent: one CTA per SM
-        { KTimer kt(K_LEGENDRE, st); sht_legendre_ws_kernel<<<grid, THREADS, smem, st>>>(P, (int)nitems); }
+        { KTimer kt(K_LEGENDRE, st); sht_legendre_ws_kernel<<<grid, THREADS, smem, st>>>(P, (int)nitems, tmap); }
         count_launch();
         CB_LAUNCH_CHECK();
         return 0;
