@@ -41,98 +41,152 @@ __global__ void root_prepare_kernel(const double* __restrict__ cl, int nz, doubl
     }
 }
 
-// In-place lower Cholesky of root[l] (row-major, lower triangle holds the matrix).
+// In-place lower Cholesky of root[l] (row-major, lower triangle holds the matrix), one CTA per
+// matrix, left-looking over 32-wide block columns:
+//   (1) panel update  A[kb:, kb:kb+32] -= L[kb:, :kb] L[kb:kb+32, :kb]^T  on the FP64 tensor cores
+//       (DMMA.8x8x4; both operands are row slices of L, staged [row][k] through a cp.async double
+//       buffer; 8 warps x 32 rows per pass),
+//   (2) the 32 x 32 diagonal block factored by one warp in shared memory,
+//   (3) the rows below solved against it by substitution, one row per thread.
 // fail[l] = 1 if a pivot is <= 0 or NaN (LAPACK dpotrf info > 0).
-__global__ void __launch_bounds__(CH_THREADS) cholesky_kernel(double* __restrict__ root, int nz, int* __restrict__ fail) {
-    __shared__ double Lc[CH_NB][CH_NB + 1];     // rows kb..kb+NB of the previous-columns chunk / diagonal block
-    __shared__ double Lr[64][CH_NB + 1];        // a 64-row slab of the same column chunk
+constexpr int CH_KC = 16;                  // k per staged chunk
+constexpr int CH_LD = 20;                  // [row][k] tiles, row pitch 20 doubles: conflict-free fragments, 16-byte rows
+constexpr int CH_ROWS = 256;               // rows per pass (8 warps x 32)
+constexpr int CH_STAGE = (CH_ROWS + CH_NB) * CH_LD;   // doubles per stage: row tile + the block column's own rows
+
+template <bool FAST>
+__global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restrict__ root, int nz, int* __restrict__ fail) {
+    extern __shared__ __align__(16) double ch_smem[];
+    double* stage = ch_smem;                              // [2][CH_STAGE]
+    double (*Ld)[CH_NB + 1] = (double (*)[CH_NB + 1])(ch_smem + 2 * CH_STAGE);   // diagonal block
     __shared__ int s_fail;
     double* A = root + (long long)blockIdx.x * nz * nz;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     if (tid == 0) s_fail = 0;
     __syncthreads();
+
     for (int kb = 0; kb < nz; kb += CH_NB) {
         const int nbk = min(CH_NB, nz - kb);
-        // (1) panel update: A[r, kb+c] -= sum_{p<kb} A[r,p] A[kb+c,p]   for r >= kb
+        // ---- (1) panel update with DMMA
         if (kb > 0) {
-            for (int r0 = kb; r0 < nz; r0 += 64) {
-                const int c = tid & 31, rq = tid >> 5;   // 8 row groups
-                double acc[8];
+            const int nchunk = (kb + CH_KC - 1) / CH_KC;
+            for (int r0 = kb; r0 < nz; r0 += CH_ROWS) {
+                double acc[4][4][2];
 #pragma unroll
-                for (int q = 0; q < 8; q++) acc[q] = 0.0;
-                for (int p0 = 0; p0 < kb; p0 += CH_NB) {
-                    __syncthreads();
-                    for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
-                        const int rr = e >> 5, pp = e & 31;
-                        Lc[rr][pp] = (kb + rr < nz) ? A[(long long)(kb + rr) * nz + p0 + pp] : 0.0;
-                    }
-                    for (int e = tid; e < 64 * CH_NB; e += CH_THREADS) {
-                        const int rr = e >> 5, pp = e & 31;
-                        Lr[rr][pp] = (r0 + rr < nz) ? A[(long long)(r0 + rr) * nz + p0 + pp] : 0.0;
-                    }
-                    __syncthreads();
-#pragma unroll 8
-                    for (int pp = 0; pp < CH_NB; pp++) {
-                        const double lc = Lc[c][pp];
+                for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int q = 0; q < 8; q++) acc[q] = fma(Lr[rq + 8 * q][pp], lc, acc[q]);
+                    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+                auto load = [&](int ck, int slot) {
+                    double* S = stage + slot * CH_STAGE;
+                    const int p0 = ck * CH_KC;
+                    // rows 0..255: the row tile; rows 256..287: the block column's own rows kb..kb+31
+                    for (int e = tid; e < (CH_ROWS + CH_NB) * (CH_KC / 2); e += CH_THREADS) {
+                        const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
+                        const int r = (rr < CH_ROWS) ? r0 + rr : kb + (rr - CH_ROWS);
+                        const int k = p0 + kk;
+                        double* dst = S + rr * CH_LD + kk;
+                        if (FAST) {
+                            const bool ok = (r < nz) && (k < kb);   // kb is a multiple of 32: k, k+1 < kb together
+                            cp_async16(dst, A + (ok ? ((long long)r * nz + k) : 0), ok);
+                        } else {
+                            dst[0] = (r < nz && k < kb) ? A[(long long)r * nz + k] : 0.0;
+                            dst[1] = (r < nz && k + 1 < kb) ? A[(long long)r * nz + k + 1] : 0.0;
+                        }
+                    }
+                    cp_async_commit();
+                };
+                load(0, 0);
+                for (int ck = 0; ck < nchunk; ck++) {
+                    cp_async_wait<0>();
+                    __syncthreads();
+                    if (ck + 1 < nchunk) load(ck + 1, (ck + 1) & 1);
+                    const double* S = stage + (ck & 1) * CH_STAGE;
+                    const double* Sa = S + warp * 32 * CH_LD;
+                    const double* Sb = S + CH_ROWS * CH_LD;
+                    if (r0 + warp * 32 < nz) {
+#pragma unroll
+                        for (int k4 = 0; k4 < CH_KC / 4; k4++) {
+                            double af[4], bf[4];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++) af[mb] = Sa[(8 * mb + g) * CH_LD + k4 * 4 + t];
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++) bf[nb] = Sb[(8 * nb + g) * CH_LD + k4 * 4 + t];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                                for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+                        }
                     }
                 }
+                __syncthreads();   // all fragment reads done before the next pass refills stage 0
+                // C[g][2t], C[g][2t+1]: row 8 mb + g, columns 8 nb + 2t, + 1
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int r = r0 + rq + 8 * q;
-                    if (r < nz && c < nbk && kb + c <= r) A[(long long)r * nz + kb + c] -= acc[q];
+                for (int mb = 0; mb < 4; mb++) {
+                    const int r = r0 + warp * 32 + 8 * mb + g;
+                    if (r >= nz) continue;
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) {
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int c = 8 * nb + 2 * t + q;
+                            if (c < nbk && kb + c <= r) A[(long long)r * nz + kb + c] -= acc[mb][nb][q];
+                        }
+                    }
                 }
             }
         }
         __syncthreads();
-        // (2) factor the diagonal block in shared memory (unblocked, column by column)
+        // ---- (2) diagonal block: one warp, lane = row
         for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
             const int rr = e >> 5, cc = e & 31;
-            Lc[rr][cc] = (rr < nbk && cc <= rr) ? A[(long long)(kb + rr) * nz + kb + cc] : 0.0;
+            Ld[rr][cc] = (rr < nbk && cc <= rr) ? A[(long long)(kb + rr) * nz + kb + cc] : 0.0;
         }
         __syncthreads();
-        for (int jj = 0; jj < nbk; jj++) {
-            if (tid == 0) {
-                const double d = Lc[jj][jj];
-                if (!(d > 0.0)) s_fail = 1;
-                Lc[jj][jj] = sqrt(d);
+        if (warp == 0) {
+            for (int jj = 0; jj < nbk; jj++) {
+                const double d = Ld[jj][jj];
+                if (!(d > 0.0)) {   // same value in every lane: uniform exit
+                    if (lane == 0) s_fail = 1;
+                    break;
+                }
+                const double dj = sqrt(d);
+                __syncwarp();
+                if (lane == jj) Ld[jj][jj] = dj;
+                double lij = 0.0;
+                if (lane > jj && lane < nbk) { lij = Ld[lane][jj] / dj; Ld[lane][jj] = lij; }
+                __syncwarp();
+                // row `lane` of the trailing block: A[lane][c] -= L[lane][jj] L[c][jj], jj < c <= lane
+                if (lane > jj && lane < nbk)
+                    for (int c = jj + 1; c <= lane; c++) Ld[lane][c] -= lij * Ld[c][jj];
+                __syncwarp();
             }
-            __syncthreads();
-            if (s_fail) break;
-            const double dj = Lc[jj][jj];
-            if (tid > jj && tid < nbk) Lc[tid][jj] /= dj;
-            __syncthreads();
-            // trailing update inside the block
-            for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
-                const int rr = e >> 5, cc = e & 31;
-                if (cc > jj && cc <= rr && rr < nbk) Lc[rr][cc] -= Lc[rr][jj] * Lc[cc][jj];
-            }
-            __syncthreads();
         }
+        __syncthreads();
         if (s_fail) break;
         for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
             const int rr = e >> 5, cc = e & 31;
-            if (rr < nbk && cc <= rr) A[(long long)(kb + rr) * nz + kb + cc] = Lc[rr][cc];
+            if (rr < nbk && cc <= rr) A[(long long)(kb + rr) * nz + kb + cc] = Ld[rr][cc];
         }
-        // (3) triangular solve for the rows below: X L_kk^T = B, one row per thread
+        // ---- (3) triangular solve for the rows below: X L_kk^T = B, one row per thread
         for (int r = kb + nbk + tid; r < nz; r += CH_THREADS) {
+            double* Ar = A + (long long)r * nz + kb;
             double xrow[CH_NB];
 #pragma unroll
-            for (int cc = 0; cc < CH_NB; cc++) xrow[cc] = (cc < nbk) ? A[(long long)r * nz + kb + cc] : 0.0;
+            for (int cc = 0; cc < CH_NB; cc++) xrow[cc] = (cc < nbk) ? Ar[cc] : 0.0;
 #pragma unroll
             for (int cc = 0; cc < CH_NB; cc++) {
                 if (cc < nbk) {
                     double v = xrow[cc];
 #pragma unroll
                     for (int pp = 0; pp < CH_NB; pp++)
-                        if (pp < cc) v -= xrow[pp] * Lc[cc][pp];
-                    xrow[cc] = v / Lc[cc][cc];
+                        if (pp < cc) v -= xrow[pp] * Ld[cc][pp];
+                    xrow[cc] = v / Ld[cc][cc];
                 }
             }
 #pragma unroll
             for (int cc = 0; cc < CH_NB; cc++)
-                if (cc < nbk) A[(long long)r * nz + kb + cc] = xrow[cc];
+                if (cc < nbk) Ar[cc] = xrow[cc];
         }
         __syncthreads();
     }
@@ -319,7 +373,17 @@ extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double j
     { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax); }
     count_launch();
     CB_LAUNCH_CHECK();
-    { KTimer kt(K_CHOLESKY, st); cholesky_kernel<<<nl, CH_THREADS, 0, st>>>(root, nz, fail); }
+    {
+        KTimer kt(K_CHOLESKY, st);
+        const size_t smem = sizeof(double) * (2 * CH_STAGE + CH_NB * (CH_NB + 1));
+        if (nz % 2 == 0) {
+            CB_CUDA(cudaFuncSetAttribute(cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cholesky_kernel<true><<<nl, CH_THREADS, smem, st>>>(root, nz, fail);
+        } else {
+            CB_CUDA(cudaFuncSetAttribute(cholesky_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cholesky_kernel<false><<<nl, CH_THREADS, smem, st>>>(root, nz, fail);
+        }
+    }
     count_launch();
     CB_LAUNCH_CHECK();
     root_flags_kernel<<<1, 32, 0, st>>>(fail, nl, nz, used_eigh, num_pos, fail_list, nfail_d);

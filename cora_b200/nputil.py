@@ -73,16 +73,16 @@ def complex_std_normal(shape, rng=None, seed=None):
     n = int(np.prod(shape))
     if seed is None:
         seed = int(np.random.randint(0, 2**31 - 1))
-    # one "l" with a 1 x 1 identity root: alm[idx(l=n-1, m)] = g[m]
+    # one "l" = n - 1 with a 1 x 1 identity root, written as a single slab: out[m] = g[m], m = 0 .. n-1
     lmax = n - 1
-    nalm = (lmax + 1) * (lmax + 2) // 2
-    panel = _dev.zeros((nalm, 1), t.complex128)
+    out = _dev.empty((n,), t.complex128)
     root = _dev.to_device(np.ones((1, 1, 1)), t.float64)
     llist = np.array([lmax], dtype=np.int32)
+    row0 = np.zeros(1, dtype=np.int64)
+    nu_base = _dev.zeros((1,), t.int64)
+    nu_width = _dev.to_device(np.ones(1, dtype=np.int32), t.int32)
     nbytes = _lib.load().cora_b200_draw_apply_workspace_bytes(1, lmax, 1)
     ws = _dev.workspace(nbytes)
-    _lib.call("cora_b200_draw_apply", _lib.ptr(root), _lib.ptr(llist), None, 1, 1, lmax, ctypes.c_ulonglong(seed), None, 0,
-              _lib.ptr(panel), 1, 0, 0, 1, _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
-    m = np.arange(n)
-    idx = m * (2 * lmax + 1 - m) // 2 + lmax
-    return panel[:, 0].cpu().numpy()[idx].reshape(shape)
+    _lib.call("cora_b200_draw_apply_slabs", _lib.ptr(root), _lib.ptr(llist), None, 1, 1, lmax, ctypes.c_ulonglong(seed), None, 0,
+              _lib.ptr(row0), _lib.ptr(nu_base), _lib.ptr(nu_width), _lib.ptr(out), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+    return out.cpu().numpy().reshape(shape)
