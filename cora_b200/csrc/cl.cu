@@ -204,12 +204,16 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
     double* R = (double*)(smraw + sizeof(PairPre) * zint * zint);        // [FILL_EB][FILL_WMAX]
     __shared__ double s_min, s_max;
     __shared__ double s_red[256];
-    // decode lower-triangle pair index
+    // decode the channel pair.  Pairs are enumerated diagonal by diagonal (d = i - j, then j): CTAs that
+    // run together then share almost the same band of table rows (y ~ |chi_i - chi_j|), which keeps
+    // the band in L2 instead of re-reading it from HBM.  first(d) = d nz - d (d - 1) / 2.
     const long long pidx = blockIdx.x;
-    int i = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
-    while ((long long)(i + 1) * (i + 2) / 2 <= pidx) i++;
-    while ((long long)i * (i + 1) / 2 > pidx) i--;
-    const int j = (int)(pidx - (long long)i * (i + 1) / 2);
+    int d = (int)(((2.0 * nz + 1.0) - sqrt((2.0 * nz + 1.0) * (2.0 * nz + 1.0) - 8.0 * (double)pidx)) * 0.5);
+    d = max(0, min(nz - 1, d));
+    while (d + 1 < nz && (long long)(d + 1) * nz - (long long)(d + 1) * d / 2 <= pidx) d++;
+    while (d > 0 && (long long)d * nz - (long long)d * (d - 1) / 2 > pidx) d--;
+    const int j = (int)(pidx - ((long long)d * nz - (long long)d * (d - 1) / 2));
+    const int i = j + d;
     const int npair = zint * zint;
     const int tid = threadIdx.x;
     const double PI = 3.14159265358979323846;
@@ -270,15 +274,19 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
             for (int e0 = 0; e0 < npair; e0 += FILL_EB) {
                 const int ne = min(FILL_EB, npair - e0);
                 __syncthreads();   // previous batch fully consumed
-                for (int idx = tid; idx < ne * W; idx += 256) {
-                    const int el = idx / W, xi = idx - el * W;
-                    const PairPre p = pre[e0 + el];
+                // one x per thread, all sample pairs of the batch: the 6 * ne row reads are independent,
+                // so they are all in flight together (this phase is L2 / HBM latency bound)
+                for (int xi = tid; xi < W; xi += 256) {
                     const int x = xbase + xi;
-                    const double u0 = 1.0 - p.wy, u1 = p.wy;
-                    const double dd = u0 * tab[tab_idx(0, p.y0, x)] + u1 * tab[tab_idx(0, p.y1, x)];
-                    const double dv = u0 * tab[tab_idx(1, p.y0, x)] + u1 * tab[tab_idx(1, p.y1, x)];
-                    const double vv = u0 * tab[tab_idx(2, p.y0, x)] + u1 * tab[tab_idx(2, p.y1, x)];
-                    R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
+#pragma unroll 3
+                    for (int el = 0; el < ne; el++) {
+                        const PairPre p = pre[e0 + el];
+                        const double u0 = 1.0 - p.wy, u1 = p.wy;
+                        const double dd = u0 * __ldg(tab + tab_idx(0, p.y0, x)) + u1 * __ldg(tab + tab_idx(0, p.y1, x));
+                        const double dv = u0 * __ldg(tab + tab_idx(1, p.y0, x)) + u1 * __ldg(tab + tab_idx(1, p.y1, x));
+                        const double vv = u0 * __ldg(tab + tab_idx(2, p.y0, x)) + u1 * __ldg(tab + tab_idx(2, p.y1, x));
+                        R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
+                    }
                 }
                 __syncthreads();
 #pragma unroll

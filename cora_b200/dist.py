@@ -179,7 +179,8 @@ class ShardedSky(object):
             root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16, out=outb, ws=rws)
         else:
             root, used = _dev.to_device(roots, t.float64), None
-        send = self._persistent("send", lambda: _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128))
+        if self.size > 1:
+            send = self._persistent("send", lambda: _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128))
         lmax_loc = int(self.l_list.max())
         if gauss is None:
             def mk():
@@ -194,6 +195,14 @@ class ShardedSky(object):
             ws = _dev.workspace(64 * self.nl + 4096)
             gptr, gld = _lib.ptr(gauss), int(gauss.shape[-1])
         nbytes = ws.numel()
+        if self.size == 1:
+            # one GPU: no exchange, so the apply kernel writes the PANEL layout the SHT reads directly
+            nalm = (self.lmax + 1) * (self.lmax + 2) // 2
+            panel = self._persistent("panel", lambda: _dev.empty((nalm, self.nz), t.complex128))
+            _lib.call("cora_b200_draw_apply", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
+                      self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(panel), self.nz, 0, 0, self.nz,
+                      _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+            return panel
         _lib.call("cora_b200_draw_apply_slabs", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
                   self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(self.row0), _lib.ptr(self.nu_base),
                   _lib.ptr(self.nu_width), _lib.ptr(send), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
@@ -203,9 +212,12 @@ class ShardedSky(object):
         """received slabs -> PANEL -> maps of this rank's channels."""
         t = _dev.torch()
         nalm = (self.lmax + 1) * (self.lmax + 2) // 2
-        panel = self._persistent("panel", lambda: _dev.empty((nalm, self.cb), t.complex128))
-        _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(recv), _lib.ptr(self.l_off), self.lmax, self.cb, _lib.ptr(panel),
-                  self.cb, 0, _lib.stream_ptr())
+        if self.size == 1:
+            panel = recv    # already in PANEL layout (alm_local)
+        else:
+            panel = self._persistent("panel", lambda: _dev.empty((nalm, self.cb), t.complex128))
+            _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(recv), _lib.ptr(self.l_off), self.lmax, self.cb, _lib.ptr(panel),
+                      self.cb, 0, _lib.stream_ptr())
         plan = _dev.sht_plan(self.nside, self.lmax)
         ws = self._persistent("sht_ws", lambda: _dev.sht_workspace(plan, _lib.ALM_PANEL, self.cb, reserve=(4 << 30) + 8 * self.cb * self.npix)[0])
         return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out, ws=ws)
