@@ -104,7 +104,7 @@ def cpu_reference_setup(wp):
     return time.time() - t0
 
 
-def cpu_reference_step(wp, pool, ncores, scale=1):
+def cpu_reference_step(wp, pool, ncores, scale=4):
     """Time a bounded sample of the path on the host and extrapolate to the whole workload.
 
     Returns (extrapolated seconds for the whole workload, per-stage dict, sample description)."""
@@ -221,57 +221,92 @@ def run_reference(args):
 
 # =============================================================================== clocks
 class ClockSampler(object):
-    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle-reason sampler running during the timed region (NVML from a thread,
+    one sample every few ms -- the C2 timed region is only ~0.2 s, too short for `nvidia-smi -lms`;
+    falls back to the B200_PROFILING.md nvidia-smi line if NVML is unavailable)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, power_w, reasons bitmask)
+        self.stop_flag = False
+        self.thr = None
+        self.nvml = None
+        self.smax = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                return self.gpu
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thr = threading.Thread(target=self._loop, daemon=True)
             self.thr.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken inside [t0, t1] (perf_counter seconds; default: all)."""
+        self.stop_flag = True
+        if self.thr is not None:
+            self.thr.join(timeout=2)
+        if self.nvml is None:
+            return self._smi_once()
+        sel = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1)]
+        if not sel:
+            sel = self.samples[-3:]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": ["no samples"]}
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                0x80: "hw_power_brake_slowdown"}
+        reasons = set()
+        for x in sel:
+            for b, nm in bits.items():
+                if x[3] & b:
                     reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median([x[1] for x in sel])), "sm_max_mhz": self.smax,
+                "power_w_max": float(max(x[2] for x in sel)), "samples": len(sel), "reasons": sorted(reasons),
+                "source": "NVML, sampled every ~4 ms inside the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [nm for nm, v in zip(names, f[5:9]) if v.lower().startswith("active")]
+            return {"sm_mhz": float(f[1]), "sm_max_mhz": float(f[2]), "power_w_max": float(f[3]), "samples": 1,
+                    "reasons": reasons, "source": "nvidia-smi after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
 # =============================================================================== GPU arm
@@ -334,12 +369,14 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tc0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         sh.step(seed=i, out=out)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    tc1 = time.perf_counter()
+    clocks = sampler.stop(tc0, tc1) if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = lib.cora_b200_launch_count() - n0
     nk = lib.cora_b200_timing_kinds()
@@ -360,7 +397,12 @@ def run_ours(args):
 
     # ---- end to end through the public API, host buffers in / host maps out ("e2e")
     nl_local, cb_local = sh.nl, sh.cb
-    del sh, out                      # the resident-path buffers go back to the allocator first
+    exchange_mode = sh.exchange
+    if world > 1 and sh.exchange == "p2p":
+        sh.peers.check()             # a timed-out peer barrier would have produced garbage: fail loudly
+    if world == 1:
+        del sh                       # the resident-path buffers go back to the allocator first
+    del out
     torch.cuda.empty_cache()
     e2e_steps = max(1, min(args.steps, 5))
     _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
@@ -369,19 +411,21 @@ def run_ours(args):
         if world == 1:
             np.random.seed(seed)
             return model.getsky()  # Sky3d.getsky(): clarray + mkfullsky -> numpy float64[nfreq, npix]
-        sh2 = cdist.ShardedSky(model, nside, wp["freq"], lmax=lmax, zromb=wp["zromb"], rank=rank, size=world)
-        return _dev.to_host(sh2.step(seed=seed))
+        return _dev.to_host(sh.step(seed=seed))   # this rank's channels -> pinned host array
 
     e2e_error = None
+    e2e_each = []
     try:
         e2e_once(99)  # warm the pinned-buffer cache
         _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
+            ts = time.perf_counter()
             res = e2e_once(i)
             assert res.shape == (cb_local if world > 1 else nchan, npix)
             del res
+            e2e_each.append(round(1e3 * (time.perf_counter() - ts), 2))
         barrier()
         e2e_s = time.perf_counter() - t0
     except (torch.OutOfMemoryError, RuntimeError) as exc:   # only the oversized extra workloads get here
@@ -407,7 +451,17 @@ def run_ours(args):
     flops_per_launch = sht_flops(nside, lmax, cb_local) * args.steps / max(1, leg_n)
     achieved = flops_per_launch / (leg_ms / max(1, leg_n) * 1e-3) / 1e12 if leg_ms > 0 else 0.0
     step_ms = ms / args.steps
+    traffic = None   # DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+        if tj and tj.get("n_gpus") == world:
+            traffic = tj["bytes_per_launch"]
+    except Exception:
+        traffic = None
     stage_share = {k: round(v[0] / args.steps, 4) for k, v in kernels.items() if v[1]}
+    if world > 1 and exchange_mode == "p2p":
+        sh.peers.check()
+        sh.peers.close()
 
     if rank != 0:
         if world > 1:
@@ -430,17 +484,21 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT[args.workload], "nside": nside, "channels": nchan, "lmax": lmax,
                    "zromb": wp["zromb"], "parallelism": "l-sharded root/apply + channel-sharded SHT x%d" % world,
+                   "exchange": ("none (1 GPU)" if world == 1 else
+                                ("fused: fill/apply kernels store into peer HBM over NVLink + flag barrier" if exchange_mode == "p2p"
+                                 else "NCCL all_to_all_single")),
                    "l2": "per-step working set (C_l %.0f MB, alm %.0f MB, maps %.0f MB per GPU) exceeds the 126 MB L2; no flush needed"
                          % (8e-6 * nl_local * nchan * nchan, 16e-6 * (lmax + 1) * (lmax + 2) / 2 * cb_local, 8e-6 * cb_local * npix),
                    "one_off_table_build_s": round(table_s, 3),
                    "stage_ms_per_step": stage_share},
         "e2e": {"value": None, "unit": UNIT, "error": e2e_error} if e2e_error else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-                "steps": e2e_steps, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
+                "steps": e2e_steps, "ms_each": e2e_each, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "sht_legendre_kernel<0> (FP64 DMMA)", "achieved": achieved,
                      "peak": float(peak[0]), "unit": "TFLOP/s", "frac": achieved / float(peak[0]) if peak[0] else None,
-                     "traffic": None,
+                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, profiles/ncu_traffic.json)",
+                     "algorithmic_bytes_per_launch": 16.0 * cb_local * ((lmax + 1) * (lmax + 2) / 2 + (4 * nside - 1) * (lmax + 1)),
                      "peak_source": "FP64 DMMA peak measured in this run by cora_b200_fp64_peak (MEASURED_PEAKS.json "
                                     "has no FP64 entry; 37.1 TFLOP/s recorded in profiles/microbench/)",
                      "flops_per_launch": flops_per_launch, "launch_ms": leg_ms / max(1, leg_n)},

@@ -188,6 +188,14 @@ class Corr21cm(maps.Sky3d):
                   _lib.ptr(out), _lib.stream_ptr(stream))
 
 
+    def _b200_fill_pairs(self, inputs, nl, nz, zint, pair0, npairs, out_ptrs, l_owner, l_row, stream=None):
+        """Pair-sharded fill with the rows scattered to the GPUs owning each l (multi-GPU path)."""
+        tab, vec, wd = inputs
+        _lib.call("cora_b200_cl_fill_21cm_pairs", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
+                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(nl), int(nz), int(zint), int(pair0), int(npairs),
+                  _lib.ptr(out_ptrs), _lib.ptr(l_owner), _lib.ptr(l_row), _lib.stream_ptr(stream))
+
+
 class EoR21cm(Corr21cm):
     """Parameters more suitable for the reionisation epoch (``corr21cm.py:333-385``)."""
 

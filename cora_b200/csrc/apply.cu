@@ -75,6 +75,9 @@ struct ApplyParams {
     // null -> PANEL output
     const long long* nu_base;
     const int* nu_width;
+    // peer output (multi-GPU, fused exchange): element (l, m, nu) at nu_ptr[nu][idx(l, m) * nu_width[nu]],
+    // nu_ptr[nu] = the PANEL buffer of the GPU that owns channel nu, advanced to that channel's column
+    double2* const* nu_ptr;
     int nz, lmax, chan0, nu0, nnu;
 };
 
@@ -180,6 +183,15 @@ __global__ void __launch_bounds__(256, 2) apply_kernel(ApplyParams P) {
     for (int nb = 0; nb < 4; nb++) {
         const int m = m0 + wn * 16 + 4 * nb + t;
         if (m > d.l) continue;
+        if (P.nu_ptr) {
+            const long long idx = (long long)m * (2 * lmax + 1 - m) / 2 + d.l;
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                const int nu = r0 + wm * 32 + 8 * mb + g;
+                if (nu < nz) P.nu_ptr[nu][idx * P.nu_width[nu]] = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            }
+            continue;
+        }
         if (P.nu_base) {
             const long long orow = d.orow + m;
 #pragma unroll
@@ -207,12 +219,39 @@ extern "C" long long cora_b200_draw_apply_workspace_bytes(int nz, int lmax_in_ba
     return 16LL * nz * (long long)(lmax_in_batch + 1) * nl_batch + 64LL * nl_batch + 1024;
 }
 
+// Descriptor tables are tiny and identical from step to step: keep them in library-owned device
+// memory keyed by content, so a steady-state step uploads nothing and never blocks the host.
+struct DescEntry { int dev; std::vector<LDesc> hd; LDesc* dd; };
+static std::vector<DescEntry> g_desc_cache;
+
+static int cached_descs(const std::vector<LDesc>& hd, LDesc** out) {
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    for (auto& e : g_desc_cache)
+        if (e.dev == dev && e.hd.size() == hd.size() && memcmp(e.hd.data(), hd.data(), sizeof(LDesc) * hd.size()) == 0) {
+            *out = e.dd;
+            return 0;
+        }
+    if (g_desc_cache.size() >= 64) {   // evict the oldest (never one in flight: a sync precedes the free)
+        CB_CUDA(cudaDeviceSynchronize());
+        cudaFree(g_desc_cache.front().dd);
+        g_desc_cache.erase(g_desc_cache.begin());
+    }
+    DescEntry e;
+    e.dev = dev; e.hd = hd; e.dd = nullptr;
+    CB_CUDA(cudaMalloc(&e.dd, sizeof(LDesc) * hd.size()));
+    CB_CUDA(cudaMemcpy(e.dd, hd.data(), sizeof(LDesc) * hd.size(), cudaMemcpyHostToDevice));
+    g_desc_cache.push_back(e);
+    *out = e.dd;
+    return 0;
+}
+
 static int draw_apply_impl(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz, int lmax,
                            unsigned long long seed, const void* gauss, long long gauss_ld, void* alm_panel,
                            long long panel_stride, int chan0, int nu0, int nnu, const long long* row0_h,
                            const long long* nu_base, const int* nu_width, void* workspace, long long ws_bytes,
-                           void* stream) {
-    CB_REQUIRE(root && l_list_h && alm_panel && workspace, 1, "draw_apply: null argument");
+                           void* stream, const void* nu_ptr = nullptr) {
+    CB_REQUIRE(root && l_list_h && (alm_panel || nu_ptr) && workspace, 1, "draw_apply: null argument");
     CB_REQUIRE(nl >= 1 && nz >= 1 && lmax >= 0 && nnu >= 1 && nu0 >= 0 && nu0 + nnu <= nz, 1, "draw_apply: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -243,10 +282,9 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
             if (hd.size() >= 65535) break;
         }
         const int nb = (int)hd.size();
-        LDesc* dd = (LDesc*)ws;
-        double2* Gbuf = (double2*)(ws + ((long long)nb * sizeof(LDesc) + 255) / 256 * 256);
-        CB_CUDA(cudaMemcpyAsync(dd, hd.data(), sizeof(LDesc) * nb, cudaMemcpyHostToDevice, st));
-        CB_CUDA(cudaStreamSynchronize(st));   // hd is about to go out of scope
+        LDesc* dd = nullptr;
+        if (int rc = cached_descs(hd, &dd)) return rc;
+        double2* Gbuf = (double2*)ws;
         int lbig = 0;
         for (auto& d : hd) lbig = std::max(lbig, d.l);
         const double2* Gsrc = (const double2*)gauss;
@@ -261,7 +299,7 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
         P.ldesc = dd;
         P.dense = dense_flag ? dense_flag + i0 : nullptr;
         P.G = Gsrc; P.panel = (double2*)alm_panel; P.panel_stride = panel_stride;
-        P.nu_base = nu_base; P.nu_width = nu_width;
+        P.nu_base = nu_base; P.nu_width = nu_width; P.nu_ptr = (double2* const*)nu_ptr;
         P.nz = nz; P.lmax = lmax; P.chan0 = chan0; P.nu0 = nu0; P.nnu = nnu;
         dim3 grid(ceil_div(lbig + 1, AP_TN / 2), ceil_div(nnu, AP_TM), nb);
         {
@@ -298,4 +336,13 @@ extern "C" int cora_b200_draw_apply_slabs(const double* root, const int* l_list_
     CB_REQUIRE(row0_h && nu_base && nu_width, 1, "draw_apply_slabs: null slab description");
     return draw_apply_impl(root, l_list_h, dense_flag, nl, nz, lmax, seed, gauss, gauss_ld, send, 0, 0, 0, nz, row0_h,
                            nu_base, nu_width, workspace, ws_bytes, stream);
+}
+
+extern "C" int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
+                                          int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
+                                          const void* nu_ptr, const int* nu_width, void* workspace, long long ws_bytes,
+                                          void* stream) {
+    CB_REQUIRE(nu_ptr && nu_width, 1, "draw_apply_peers: null peer description");
+    return draw_apply_impl(root, l_list_h, dense_flag, nl, nz, lmax, seed, gauss, gauss_ld, nullptr, 0, 0, 0, nz, nullptr,
+                           nullptr, nu_width, workspace, ws_bytes, stream, nu_ptr);
 }

@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
                                                         const double* __restrict__ bb, const double* __restrict__ ff,
                                                         const double* __restrict__ pf, const double* __restrict__ DD,
                                                         const double* __restrict__ w, int l0, int l_step, int nl, int nz,
-                                                        int zint, double* __restrict__ out) {
+                                                        int zint, double* __restrict__ out, long long pair0,
+                                                        double* const* __restrict__ out_ptrs,
+                                                        const int* __restrict__ l_owner, const int* __restrict__ l_row) {
     extern __shared__ __align__(16) unsigned char smraw[];
     PairPre* pre = (PairPre*)smraw;                                     // [zint*zint]
     double* R = (double*)(smraw + sizeof(PairPre) * zint * zint);        // [FILL_EB][FILL_WMAX]
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
     // decode the channel pair.  Pairs are enumerated diagonal by diagonal (d = i - j, then j): CTAs that
     // run together then share almost the same band of table rows (y ~ |chi_i - chi_j|), which keeps
     // the band in L2 instead of re-reading it from HBM.  first(d) = d nz - d (d - 1) / 2.
-    const long long pidx = blockIdx.x;
+    const long long pidx = pair0 + blockIdx.x;
     int d = (int)(((2.0 * nz + 1.0) - sqrt((2.0 * nz + 1.0) * (2.0 * nz + 1.0) - 8.0 * (double)pidx)) * 0.5);
     d = max(0, min(nz - 1, d));
     while (d + 1 < nz && (long long)(d + 1) * nz - (long long)(d + 1) * d / 2 <= pidx) d++;
@@ -328,8 +330,13 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
         for (int q = 0; q < FILL_LPT; q++) {
             const int li = lb + tid + q * 256;
             if (li >= lend) continue;
-            out[(long long)li * nz2 + oij] = acc[q];
-            if (i != j) out[(long long)li * nz2 + oji] = acc[q];
+            double* o = out + (long long)li * nz2;
+            if (out_ptrs) {   // pair-sharded fill: row l lives on the GPU that owns l (peer store over NVLink)
+                const int l = l0 + li * l_step;
+                o = out_ptrs[l_owner[l]] + (long long)l_row[l] * nz2;
+            }
+            o[oij] = acc[q];
+            if (i != j) o[oji] = acc[q];
         }
     }
 }
@@ -470,7 +477,28 @@ extern "C" int cora_b200_cl_fill_21cm(const double* tab, const double* chi, cons
     size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
     CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KTimer kt(K_CL_FILL, (cudaStream_t)stream);
-    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl);
+    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl,
+                                                                            0, nullptr, nullptr, nullptr);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cora_b200_cl_fill_21cm_pairs(const double* tab, const double* chi, const double* b, const double* f,
+                                            const double* pf, const double* D, const double* w, int nl, int nz, int zint,
+                                            long long pair0, long long npairs, const void* out_ptrs, const int* l_owner,
+                                            const int* l_row, void* stream) {
+    CB_REQUIRE(tab && chi && b && f && pf && D && w && out_ptrs && l_owner && l_row, 1, "cl_fill_21cm_pairs: null argument");
+    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT, 1, "cl_fill_21cm_pairs: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
+    const long long all = (long long)nz * (nz + 1) / 2;
+    CB_REQUIRE(pair0 >= 0 && npairs >= 0 && pair0 + npairs <= all && npairs < 2147483647LL, 1,
+               "cl_fill_21cm_pairs: pair range [%lld, %lld) outside [0, %lld)", pair0, pair0 + npairs, all);
+    if (npairs == 0) return 0;
+    size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
+    CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KTimer kt(K_CL_FILL, (cudaStream_t)stream);
+    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, 0, 1, nl, nz, zint, nullptr,
+                                                                            pair0, (double* const*)out_ptrs, l_owner, l_row);
     count_launch();
     CB_LAUNCH_CHECK();
     return 0;

@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restr
 // G = diag(lambda) V, rows of V the eigenvectors.  Round-robin ordering, one warp per pair.
 __global__ void jacobi_init_kernel(const double* __restrict__ cl, const int* __restrict__ fail_list, int nz,
                                    double jitter_rel, const double* __restrict__ dmax, double* __restrict__ G,
-                                   double* __restrict__ V) {
+                                   double* __restrict__ V, const int* __restrict__ nfail_ptr) {
+    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;   // device-side count: no host round trip
     const int l = fail_list[blockIdx.x];
     const long long src = (long long)l * nz * nz, dst = (long long)blockIdx.x * nz * nz;
     const double cmax = dmax[l] * jitter_rel;
@@ -219,8 +220,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall, double* __restrict__ Vall, int nz,
-                                                      int max_sweeps, int* __restrict__ sweeps_out) {
+                                                      int max_sweeps, int* __restrict__ sweeps_out,
+                                                      const int* __restrict__ nfail_ptr) {
     __shared__ int s_rot;
+    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
     double* G = Gall + (long long)blockIdx.x * nz * nz;
     double* V = Vall + (long long)blockIdx.x * nz * nz;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -276,9 +279,11 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall,
 __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __restrict__ Gall, const double* __restrict__ Vall,
                                                             const int* __restrict__ fail_list, int nz, double clip_rel,
                                                             double* __restrict__ root, int* __restrict__ num_pos,
-                                                            double* __restrict__ evals_ws, int* __restrict__ rank_ws) {
+                                                            double* __restrict__ evals_ws, int* __restrict__ rank_ws,
+                                                            const int* __restrict__ nfail_ptr) {
     __shared__ double s_max;
     __shared__ int s_npos;
+    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
     const int l = fail_list[blockIdx.x];
     const double* G = Gall + (long long)blockIdx.x * nz * nz;
     const double* V = Vall + (long long)blockIdx.x * nz * nz;
@@ -389,26 +394,35 @@ extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double j
     root_flags_kernel<<<1, 32, 0, st>>>(fail, nl, nz, used_eigh, num_pos, fail_list, nfail_d);
     count_launch();
     CB_LAUNCH_CHECK();
+    const int threads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
+    auto wave = [&](int f0, int nb, const int* guard) -> int {
+        double* G = GV;
+        double* V = GV + (long long)nb * nz * nz;
+        KTimer kt(K_EIGH, st);
+        jacobi_init_kernel<<<nb, 256, 0, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, G, V, guard);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0, guard);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, fail_list + f0, nz, clip_rel, root, num_pos, evals, rank, guard);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        return 0;
+    };
+    if (slots >= nl) {
+        // room for every matrix: launch the eigen fallback for all nl slots, CTAs beyond the
+        // device-side failure count exit at once -- the host never waits for the count
+        return wave(0, nl, nfail_d);
+    }
     int nfail = 0;
     CB_CUDA(cudaMemcpyAsync(&nfail, nfail_d, sizeof(int), cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaStreamSynchronize(st));
     if (nfail == 0) return 0;
     CB_REQUIRE(slots >= 1, 4, "root_batched: no workspace for the eigen fallback");
-    const int threads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
     for (int f0 = 0; f0 < nfail; f0 += (int)slots) {
         const int nb = (int)std::min<long long>(slots, nfail - f0);
-        double* G = GV;
-        double* V = GV + (long long)nb * nz * nz;
-        KTimer kt(K_EIGH, st);
-        jacobi_init_kernel<<<nb, 256, 0, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, G, V);
-        count_launch();
-        CB_LAUNCH_CHECK();
-        jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0);
-        count_launch();
-        CB_LAUNCH_CHECK();
-        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, fail_list + f0, nz, clip_rel, root, num_pos, evals, rank);
-        count_launch();
-        CB_LAUNCH_CHECK();
+        if (int rc = wave(f0, nb, nullptr)) return rc;
     }
     return 0;
 }

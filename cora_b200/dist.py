@@ -122,7 +122,12 @@ class ShardedSky(object):
     this rank's channels ``float64[cb, npix]`` as a CUDA tensor."""
 
     def __init__(self, model, nside, frequencies, lmax=None, zromb=3, group=None, partition="interleaved",
-                 rank=None, size=None):
+                 rank=None, size=None, exchange="auto", peers=None):
+        """``exchange``: ``"p2p"`` -- the fill and apply kernels store straight into the consuming
+        GPU's buffers over NVLink (``cora_b200.peer``; needs one process per GPU under NCCL, or
+        ``peers`` = a ``LocalPeers`` view for virtual ranks); ``"collective"`` -- apply packs send
+        slabs and ``torch.distributed.all_to_all_single`` moves them (also the gloo/CPU-testable
+        path); ``"auto"`` -- p2p whenever there is more than one rank and peers can be set up."""
         from . import skysim
 
         t = _dev.torch()
@@ -149,6 +154,13 @@ class ShardedSky(object):
         self.l_off = _dev.to_device(self.plan.l_offsets(rank), t.int64)
         self.row0 = self.plan.send_row0(rank)
         self._buf = {}
+        self.peers = peers
+        if exchange == "auto":
+            exchange = "p2p" if (size > 1 and (peers is not None or (dist.is_available() and dist.is_initialized()
+                                                                      and dist.get_backend(group) == "nccl"))) else "collective"
+        self.exchange = exchange if size > 1 else "collective"
+        self._p2p = None
+        self._k = 0
 
     def _persistent(self, name, make):
         """Buffers reused from step to step (no allocator traffic inside a step)."""
@@ -175,7 +187,7 @@ class ShardedSky(object):
         if roots is None:
             outb = self._persistent("root", lambda: (_dev.empty((self.nl, self.nz, self.nz), t.float64),
                                                      _dev.empty((self.nl,), t.int32), _dev.empty((self.nl,), t.int32)))
-            rws = self._persistent("root_ws", lambda: nputil.root_workspace(self.nl, self.nz, max_eigh=max(4, self.nl // 8)))
+            rws = self._persistent("root_ws", lambda: nputil.root_workspace(self.nl, self.nz, max_eigh=self._max_eigh()))
             root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16, out=outb, ws=rws)
         else:
             root, used = _dev.to_device(roots, t.float64), None
@@ -222,7 +234,139 @@ class ShardedSky(object):
         ws = self._persistent("sht_ws", lambda: _dev.sht_workspace(plan, _lib.ALM_PANEL, self.cb, reserve=(4 << 30) + 8 * self.cb * self.npix)[0])
         return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out, ws=ws)
 
+    # ---- fused-exchange path (exchange == "p2p") -----------------------------------------
+    def _p2p_setup(self):
+        """Peer buffers (double-buffered C_l rows and PANEL) and the pointer tables the kernels use."""
+        if self._p2p is not None:
+            return self._p2p
+        from . import peer as _peer
+
+        t = _dev.torch()
+        if self.peers is None:
+            self.peers = _peer.PeerGroup(self.rank, self.size, self.group)
+        pg = self.peers
+        L = self.lmax + 1
+        nalm = L * (L + 1) // 2
+        st = {"pairs": hasattr(self.model, "_b200_fill_pairs")}
+        st["cla"], st["cla_ptrs"], st["panel"], st["panel_ptrs"] = [], [], [], []
+        for _ in range(2):
+            if st["pairs"]:
+                own, ptrs = pg.alloc(8 * max(1, self.nl) * self.nz * self.nz)
+                st["cla"].append(own)
+                st["cla_ptrs"].append(ptrs)
+            own, ptrs = pg.alloc(16 * nalm * max(1, self.cb))
+            st["panel"].append(own)
+            st["panel_ptrs"].append(ptrs)
+        st["l_owner"] = _dev.to_device(self.plan.owner.astype(np.int32), t.int32)
+        lrow = np.empty(L, dtype=np.int32)
+        for ll in self.plan.l_lists:
+            lrow[ll] = np.arange(len(ll), dtype=np.int32)
+        st["l_row"] = _dev.to_device(lrow, t.int32)
+        width = np.empty(self.nz, dtype=np.int32)
+        for s_ in range(self.size):
+            width[int(self.plan.chan_lo[s_]):int(self.plan.chan_hi[s_])] = int(self.plan.cb[s_])
+        st["nu_width"] = _dev.to_device(width, t.int32)
+        npair = self.nz * (self.nz + 1) // 2
+        st["pair0"] = npair * self.rank // self.size
+        st["npairs"] = npair * (self.rank + 1) // self.size - st["pair0"]
+        st["tables"] = [None, None]
+        self._p2p = st
+        return st
+
+    def _p2p_tables(self, k):
+        """Device pointer tables of buffer set k (resolved on first use: with virtual ranks the
+        other ranks' buffers exist only after every rank ran ``_p2p_setup``)."""
+        from . import peer as _peer
+
+        t = _dev.torch()
+        st = self._p2p_setup()
+        if st["tables"][k] is None:
+            tab = {}
+            if st["pairs"]:
+                tab["cla_ptrs"] = _dev.to_device(np.array(_peer.resolve(st["cla_ptrs"][k]), dtype=np.uint64).view(np.int64), t.int64)
+            pp = _peer.resolve(st["panel_ptrs"][k])
+            nu_ptr = np.empty(self.nz, dtype=np.uint64)
+            for s_ in range(self.size):
+                lo, hi = int(self.plan.chan_lo[s_]), int(self.plan.chan_hi[s_])
+                nu_ptr[lo:hi] = np.uint64(pp[s_]) + np.uint64(16) * np.arange(hi - lo, dtype=np.uint64)
+            tab["nu_ptr"] = _dev.to_device(nu_ptr.view(np.int64), t.int64)
+            st["tables"][k] = tab
+        return st["tables"][k]
+
+    def p2p_fill(self, k):
+        """Phase 1: C_l rows of the l's this rank owns land in ``cla[k]``.  Models whose fill cost
+        is per channel pair (21cm) are sharded over pairs and scatter rows to the owners of l."""
+        t = _dev.torch()
+        st = self._p2p_setup()
+        if st["pairs"]:
+            tab = self._p2p_tables(k)
+            self.model._b200_fill_pairs(self.fill_inputs, self.lmax + 1, self.nz, self.zint, st["pair0"], st["npairs"],
+                                        tab["cla_ptrs"], st["l_owner"], st["l_row"])
+            return True     # remote stores in flight: barrier before the root reads cla[k]
+        self.fill()
+        return False
+
+    def p2p_alm(self, k, seed=0, gauss=None, roots=None, cla=None):
+        """Phase 2: root of the local l's, draws, apply with the a_lm stored straight into the
+        PANEL buffers ``panel[k]`` of the GPUs owning each channel."""
+        t = _dev.torch()
+        lib = _lib.load()
+        st = self._p2p_setup()
+        tab = self._p2p_tables(k)
+        if cla is None:
+            cla = st["cla"][k].tensor((self.nl, self.nz, self.nz), t.float64) if st["pairs"] else self._buf["cla"]
+        if roots is None:
+            outb = self._persistent("root", lambda: (_dev.empty((self.nl, self.nz, self.nz), t.float64),
+                                                     _dev.empty((self.nl,), t.int32), _dev.empty((self.nl,), t.int32)))
+            rws = self._persistent("root_ws", lambda: nputil.root_workspace(self.nl, self.nz, max_eigh=self._max_eigh()))
+            root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16, out=outb, ws=rws)
+        else:
+            root, used = _dev.to_device(roots, t.float64), None
+        lmax_loc = int(self.l_list.max())
+        if gauss is None:
+            def mk():
+                full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
+                one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
+                return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
+
+            ws = self._persistent("draw_ws", mk)
+            gptr, gld = None, 0
+        else:
+            gauss = _dev.to_device(gauss, t.complex128)
+            ws = _dev.workspace(64 * self.nl + 4096)
+            gptr, gld = _lib.ptr(gauss), int(gauss.shape[-1])
+        _lib.call("cora_b200_draw_apply_peers", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
+                  self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(tab["nu_ptr"]), _lib.ptr(st["nu_width"]),
+                  _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr())
+
+    def p2p_sht(self, k, out=None):
+        """Phase 3: inverse SHT of this rank's channels from ``panel[k]``."""
+        t = _dev.torch()
+        st = self._p2p_setup()
+        L = self.lmax + 1
+        panel = st["panel"][k].tensor((L * (L + 1) // 2, self.cb), t.complex128)
+        plan = _dev.sht_plan(self.nside, self.lmax)
+        ws = self._persistent("sht_ws", lambda: _dev.sht_workspace(plan, _lib.ALM_PANEL, self.cb, reserve=(4 << 30) + 8 * self.cb * self.npix)[0])
+        return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out, ws=ws)
+
+    def _max_eigh(self):
+        """Eigen-fallback slots of the root workspace: all local l's when that is cheap (then the
+        root stage never waits on the host), else an eighth of them."""
+        full = 16 * self.nz * self.nz * self.nl
+        return self.nl if full <= _dev.free_bytes() // 8 else max(4, self.nl // 8)
+
+    def _step_p2p(self, seed=0, out=None):
+        k = self._k & 1
+        self._k += 1
+        if self.p2p_fill(k):
+            self.peers.barrier()
+        self.p2p_alm(k, seed=seed)
+        self.peers.barrier()
+        return self.p2p_sht(k, out=out)
+
     def step(self, seed=0, out=None):
+        if self.exchange == "p2p":
+            return self._step_p2p(seed=seed, out=out)
         cla = self.fill()
         send = self.alm_local(cla, seed=seed)
         del cla
@@ -258,7 +402,14 @@ def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, parti
     if corr_local.shape[0] != sh.nl:
         raise Exception("Correlation matrix is incorrect shape.")
     cla = _dev.to_device(corr_local, t.float64)
-    send = sh.alm_local(cla, seed=seed, gauss=gauss, roots=roots)
-    recv = exchange(send, sh.plan, rank, group)
-    sky = sh.synthesize(recv)
+    if sh.exchange == "p2p":
+        sh.p2p_alm(0, seed=seed, gauss=gauss, roots=roots, cla=cla)
+        sh.peers.barrier()
+        sky = sh.p2p_sht(0).clone()
+        sh.peers.check()
+        sh.peers.close()
+    else:
+        send = sh.alm_local(cla, seed=seed, gauss=gauss, roots=roots)
+        recv = exchange(send, sh.plan, rank, group)
+        sky = sh.synthesize(recv)
     return sky if device_out else _dev.to_host(sky)

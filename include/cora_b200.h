@@ -183,6 +183,46 @@ int cora_b200_draw_apply_slabs(const double* root, const int* l_list_h, const in
 int cora_b200_alm_slabs_to_panel(const void* recv, const long long* l_off, int lmax, int nchan, void* alm_panel,
                                  long long panel_stride, int chan0, void* stream);
 
+/* ---- fused exchange over peer memory (NVLink / NVSwitch, one process per GPU) ------------
+ * The reference moves data between ranks with caput's MPIArray.redistribute
+ * (cora/core/skysim.py:128) after the compute.  Here the producing kernels store straight into
+ * the consumer GPU's buffer, so the exchange happens in the kernel epilogue:
+ *   - cora_b200_cl_fill_21cm_pairs: the 21cm C_l fill sharded over channel PAIRS (its cost per
+ *     pair does not shrink with the l range, so l-sharding it would not scale); row l of the
+ *     result is written to the GPU that owns l for the root/apply stage.
+ *   - cora_b200_draw_apply_peers: apply writes a_lm(nu) into the PANEL buffer of the GPU that
+ *     owns channel nu for the SHT stage.
+ * Buffers come from cora_b200_peer_alloc (cudaMalloc + CUDA IPC handle, zero-filled); every
+ * other process maps them with cora_b200_peer_open.  cora_b200_peer_barrier is a flag barrier
+ * over the same memory (stream-ordered; `epoch` strictly increasing; a peer that does not
+ * arrive within timeout_s sets *status != 0 instead of hanging the GPU).                     */
+int cora_b200_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out);
+int cora_b200_peer_free(void* ptr);
+int cora_b200_peer_open(const unsigned char* handle64, void** ptr_out);
+int cora_b200_peer_close(void* ptr);
+/* flags_ptrs: device array [size] of pointers, entry r = rank r's flag array (u64[size]) as mapped here */
+int cora_b200_peer_barrier(const void* flags_ptrs, int rank, int size, unsigned long long epoch,
+                           double timeout_s, int* status, void* stream);
+
+/* 21cm fill for channel pairs [pair0, pair0 + npairs) of the diagonal-major enumeration
+ * (pair index p <-> (i, j), i >= j, ordered by d = i - j then j), all l = 0..nl-1.
+ * out_ptrs: device array of per-GPU C_l buffers; element (l, i, j) and its mirror (l, j, i) go
+ * to out_ptrs[l_owner[l]][(l_row[l] * nz + i) * nz + j].  l_owner / l_row: device int[nl].     */
+int cora_b200_cl_fill_21cm_pairs(const double* tab, const double* chi, const double* b, const double* f,
+                                 const double* pf, const double* D, const double* w, int nl, int nz, int zint,
+                                 long long pair0, long long npairs, const void* out_ptrs, const int* l_owner,
+                                 const int* l_row, void* stream);
+
+/* draw + apply for the local l's with the exchange fused into the epilogue: element (l, m, nu)
+ * is stored at nu_ptr[nu][idx(l, m) * nu_width[nu]] (complex elements), where nu_ptr[nu] (device
+ * array [nz] of pointers) is the PANEL buffer of the GPU owning channel nu advanced to that
+ * channel's column and nu_width[nu] that GPU's channel count.  Other arguments as
+ * cora_b200_draw_apply.                                                                     */
+int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
+                               int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
+                               const void* nu_ptr, const int* nu_width, void* workspace, long long ws_bytes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
