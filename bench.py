@@ -323,6 +323,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_bound = _dev.bind_host_to_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0 and build.needs_build():
@@ -492,7 +493,7 @@ def run_ours(args):
                    "one_off_table_build_s": round(table_s, 3),
                    "stage_ms_per_step": stage_share},
         "e2e": {"value": None, "unit": UNIT, "error": e2e_error} if e2e_error else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-                "steps": e2e_steps, "ms_each": e2e_each, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
+                "steps": e2e_steps, "ms_each": e2e_each, "host_bound_to_gpu_numa_node": numa_bound, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "sht_legendre_kernel<0> (FP64 DMMA)", "achieved": achieved,
