@@ -323,6 +323,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_bound = _dev.bind_host_to_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -473,7 +474,8 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup",
-                                "0", "--workload", args.workload], capture_output=True, text=True, timeout=900)
+                                "0", "--workload", args.workload], capture_output=True, text=True, timeout=900,
+                               preexec_fn=(lambda: os.sched_setaffinity(0, all_cpus)) if all_cpus else None)  # all host cores
             ref = json.loads(p.stdout.strip().splitlines()[-1])
             cpu_baseline = ref["cpu_baseline"]
         except Exception as exc:  # the GPU numbers stand on their own

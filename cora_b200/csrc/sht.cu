@@ -1176,6 +1176,282 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_phase_ker
     }
 }
 
+
+// =============================================================================== analysis
+// Forward transform (map -> alm), the adjoint of the two synthesis stages above times the HEALPix
+// quadrature weight 4 pi / npix:
+//   1. sht_ring_analysis_kernel: per ring, two channels packed into one complex sequence, the
+//      same shared-memory FFT / Bluestein core as the synthesis run on the conjugated input
+//      (forward DFT = conj of the backward DFT of the conjugate), un-aliased onto every m <= lmax
+//      with the ring's phase e^{-i m phi0} and weight.
+//   2. sht_legendre_adj_kernel: a_lm(chan) = sum_rings lambda_lm(theta_ring) F_m(ring, chan) on
+//      the FP64 tensor cores; lambda from the same scaled recurrence, transposed roles (rows = l,
+//      contraction over rings), north/south folded by l - m parity before the contraction.
+// replaces healpy.map2alm as called by cora/util/hputil.py:228-230 (sphtrans_real).
+struct AnaParams {
+    const double* map;       // [nchan][npix] (pointer already offset to the batch's first channel)
+    long long npix;
+    double2* F;              // [nring][ncg][L][4]
+    const RingDesc* rings;
+    const int* ring_list;
+    const double2* tw;
+    const double2* chirp;
+    const double2* bhat;
+    const long long *chirp_off, *bhat_off;
+    const double* wring;     // [2 nside] absolute ring weights (north rings incl. equator) or null
+    double wscale;           // 4 pi / npix
+    int nside, lmax, nb, ncg, P, Mmax, log_tw;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_ring_analysis_kernel(AnaParams Q) {
+    extern __shared__ __align__(16) double2 xs[];   // [P][pidx(Mmax)]
+    const int r = Q.ring_list[blockIdx.x];
+    const RingDesc rd = Q.rings[r];
+    const int n = rd.nph, logM = rd.logM, M = 1 << logM, Pp = Q.P;
+    const bool blu = rd.bluestein != 0;
+    const int seq = pidx(Q.Mmax) + 1;
+    const int gpc = 2 / Pp;
+    const int cg = blockIdx.y / gpc;
+    const int pair0 = (blockIdx.y % gpc) * Pp;
+    const int L = Q.lmax + 1;
+    const double2* chirp = blu ? Q.chirp + Q.chirp_off[rd.cap] : nullptr;
+
+    // ---- load conj(z), z = f1 + i f2 (two channels per complex sequence)
+    for (int w = threadIdx.x; w < Pp * M; w += blockDim.x) {
+        const int p = w >> logM, j = w & (M - 1);
+        const int ch = cg * 4 + 2 * (pair0 + p);
+        double2 v = make_double2(0.0, 0.0);
+        if (j < n && ch < Q.nb) {
+            v.x = Q.map[(long long)ch * Q.npix + rd.start + j];
+            if (ch + 1 < Q.nb) v.y = -Q.map[(long long)(ch + 1) * Q.npix + rd.start + j];
+        }
+        double2* xp = xs + (size_t)p * seq;
+        if (blu) xp[pidx(j)] = (j < n) ? cmul(v, chirp[j]) : v;
+        else xp[pidx(bitrev(j, logM))] = v;
+    }
+    __syncthreads();
+    if (blu) {
+        fft_dif_padded<-1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
+        const double2* bh = Q.bhat + Q.bhat_off[rd.cap];
+        for (int w = threadIdx.x; w < Pp * M; w += blockDim.x) {
+            const int p = w >> logM, k = w & (M - 1);
+            double2* e = xs + (size_t)p * seq + pidx(k);
+            *e = cmul(*e, bh[k]);
+        }
+        __syncthreads();
+        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
+    } else {
+        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
+    }
+    // xs[k] (times chirp[k] for Bluestein) = Y_k = conj(Z_k), Z = DFT_n(z).
+    const int nring = 4 * Q.nside - 1;
+    const int north = min(r, nring - 1 - r);
+    const double wr = Q.wscale * (Q.wring ? Q.wring[north] : 1.0);
+    double2* Fr = Q.F + (((long long)r * Q.ncg + cg) * L) * 4;
+    for (int w = threadIdx.x; w < L * Pp; w += blockDim.x) {
+        const int m = w / Pp, p = w - m * Pp;
+        const int c = 2 * (pair0 + p);
+        const int ch = cg * 4 + c;
+        if (ch >= Q.nb) continue;
+        const int q = m / n, k = m - q * n, kk = (k == 0) ? 0 : n - k;
+        const double2* xp = xs + (size_t)p * seq;
+        double2 yk = xp[pidx(k)], yn = xp[pidx(kk)];
+        if (blu) { yk = cmul(yk, chirp[k]); yn = cmul(yn, chirp[kk]); }
+        // F1_k = (Z_k + conj(Z_{n-k}))/2 = (conj(Y_k) + Y_{n-k})/2,  F2_k = (conj(Y_k) - Y_{n-k})/(2i)
+        double2 g1 = make_double2(0.5 * (yk.x + yn.x), 0.5 * (yn.y - yk.y));
+        const double2 d = make_double2(0.5 * (yk.x - yn.x), 0.5 * (-yk.y - yn.y));
+        double2 g2 = make_double2(d.y, -d.x);
+        double2 ph = make_double2(wr, 0.0);
+        if (rd.shifted) {   // e^{-i m phi0}, phi0 = pi/n:  e^{-i pi k/n} (-1)^q
+            double sn, cs;
+            sincospi((double)k / (double)n, &sn, &cs);
+            const double sg = (q & 1) ? -wr : wr;
+            ph = make_double2(sg * cs, -sg * sn);
+        }
+        Fr[m * 4 + c] = cmul(g1, ph);
+        if (ch + 1 < Q.nb) Fr[m * 4 + c + 1] = cmul(g2, ph);
+    }
+}
+
+constexpr int ADJ_THREADS = 256;
+constexpr int ADJ_RPL = 2;                   // ring sets (of 32) per warp
+constexpr int ADJ_RT = 32 * 8 * ADJ_RPL;     // north rings per CTA
+constexpr int ADJ_NCH = 8;                   // complex channels per CTA (16 real columns)
+constexpr int ADJ_BLD = 20;                  // Bs[ring][20]: (t * 20 + g) conflict-free per half-warp
+constexpr int ADJ_ALD = 36;                  // As[row][36]:  (g * 36 + t)
+
+struct LegAdjParams {
+    const double2* F;         // [nring][ncg][L][4]
+    double2* alm;             // PANEL [nalm][alm_stride]
+    long long alm_stride;
+    int chan0, nb;
+    const double *cth, *sth;
+    const double* nm_mant;
+    const int* nm_exp;
+    const double2* rc;
+    int nside, lmax, nrn, nrb, ncb, ncg, accumulate;
+};
+
+__global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdjParams P) {
+    extern __shared__ __align__(16) double smem[];
+    double* Bs = smem;                                  // [2 parities][RT][BLD]
+    double* As = Bs + 2 * ADJ_RT * ADJ_BLD;             // [8 warps][2 parities][8 l][ALD]
+    double* Cs = As + 8 * 2 * 8 * ADJ_ALD;              // [8 warps][256]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bid = blockIdx.x;
+    const int cb = bid % P.ncb; bid /= P.ncb;
+    const int rb = bid % P.nrb;
+    const int m = bid / P.nrb;
+    const int lmax = P.lmax, L = lmax + 1;
+    const int nk = lmax - m + 1;
+    const int nring_tot = 4 * P.nside - 1;
+
+    // ---- B tile: (north + south, north - south) of F_m for this CTA's rings and channels
+    for (int el = tid; el < ADJ_RT * ADJ_NCH; el += ADJ_THREADS) {
+        const int rr = el / ADJ_NCH, c = el % ADJ_NCH;
+        const int rn = rb * ADJ_RT + rr;
+        const int ch = cb * ADJ_NCH + c;
+        double2 ev = make_double2(0.0, 0.0), od = ev;
+        if (rn < P.nrn && ch < P.nb) {
+            const int cg = ch >> 2, cc = ch & 3;
+            const double2 fn = P.F[(((long long)rn * P.ncg + cg) * L + m) * 4 + cc];
+            const int rs = nring_tot - 1 - rn;
+            if (rs != rn) {
+                const double2 fs = P.F[(((long long)rs * P.ncg + cg) * L + m) * 4 + cc];
+                ev = make_double2(fn.x + fs.x, fn.y + fs.y);
+                od = make_double2(fn.x - fs.x, fn.y - fs.y);
+            } else {
+                ev = fn;   // equator: lambda vanishes for odd l - m
+            }
+        }
+        Bs[(size_t)rr * ADJ_BLD + 2 * c] = ev.x;
+        Bs[(size_t)rr * ADJ_BLD + 2 * c + 1] = ev.y;
+        Bs[(size_t)(ADJ_RT + rr) * ADJ_BLD + 2 * c] = od.x;
+        Bs[(size_t)(ADJ_RT + rr) * ADJ_BLD + 2 * c + 1] = od.y;
+    }
+
+    // ---- recurrence seeds: lane owns ring (set s, lane) of the warp's ADJ_RPL sets
+    double x[ADJ_RPL], p_cur[ADJ_RPL], p_prev[ADJ_RPL];
+    int e[ADJ_RPL];
+#pragma unroll
+    for (int s = 0; s < ADJ_RPL; s++) {
+        const int rn = rb * ADJ_RT + (s * 8 + warp) * 32 + lane;
+        x[s] = 0.0; p_cur[s] = 0.0; p_prev[s] = 0.0; e[s] = -(1 << 20);
+        if (rn < P.nrn) {
+            x[s] = P.cth[rn];
+            double bm = P.sth[rn];
+            long long be = 0;
+            norm_frexp(bm, be);
+            double rm = 1.0;
+            long long re = 0;
+            int n = m;
+            while (n) {
+                if (n & 1) { rm *= bm; re += be; norm_frexp(rm, re); }
+                bm *= bm; be *= 2; norm_frexp(bm, be);
+                n >>= 1;
+            }
+            rm *= P.nm_mant[m];
+            re += P.nm_exp[m];
+            norm_frexp(rm, re);
+            if (m & 1) rm = -rm;
+            long long q = (re >= 0) ? 0 : -((-re) / 256);
+            e[s] = (int)(q * 256);
+            p_cur[s] = ldexp(rm, (int)(re - (long long)e[s]));
+        }
+    }
+    __syncthreads();   // B tile complete
+
+    const long long row0 = (long long)m * (2 * lmax + 1 - m) / 2 + m;   // idx(l = m, m)
+    double* Aw = As + warp * (2 * 8 * ADJ_ALD);
+    const int ngroups = (nk + 15) / 16;
+    for (int gi = 0; gi < ngroups; gi++) {
+        const int kbase = gi * 16;
+        double acc[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll
+        for (int s = 0; s < ADJ_RPL; s++) {
+            const bool live = (e[s] == 0);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int k = kbase + j;
+                Aw[((j & 1) * 8 + (j >> 1)) * ADJ_ALD + lane] = (live && k < nk) ? p_cur[s] : 0.0;
+                const double2 c = (k < nk) ? P.rc[row0 + k] : make_double2(0.0, 0.0);
+                const double pn = fma(c.x * x[s], p_cur[s], -c.y * p_prev[s]);
+                p_prev[s] = p_cur[s];
+                p_cur[s] = pn;
+                if ((j & 7) == 7 && e[s] < 0 && ((__double2hiint(p_cur[s]) >> 20) & 0x7ff) > 1023 + 128) {
+                    p_cur[s] *= 0x1p-256;
+                    p_prev[s] *= 0x1p-256;
+                    e[s] += 256;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            __syncwarp();
+            if (bal) {
+                const int ring0 = (s * 8 + warp) * 32;
+#pragma unroll
+                for (int par = 0; par < 2; par++) {
+#pragma unroll
+                    for (int jb = 0; jb < 8; jb++) {
+                        if (!((bal >> (4 * jb)) & 0xfu)) continue;   // four dead rings: nothing to add
+                        const double af = Aw[(par * 8 + g) * ADJ_ALD + 4 * jb + t];
+                        const double* brow = Bs + (size_t)(par * ADJ_RT + ring0 + 4 * jb + t) * ADJ_BLD;
+                        dmma884(acc[par][0][0], acc[par][0][1], af, brow[g]);
+                        dmma884(acc[par][1][0], acc[par][1][1], af, brow[8 + g]);
+                    }
+                }
+            }
+            __syncwarp();   // fragments read before the next set overwrites the tile
+        }
+        // ---- cross-warp reduction of the 16 l x 16 column tile, fixed order
+#pragma unroll
+        for (int par = 0; par < 2; par++)
+#pragma unroll
+            for (int nb = 0; nb < 2; nb++) {
+                Cs[warp * 256 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t] = acc[par][nb][0];
+                Cs[warp * 256 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t + 1] = acc[par][nb][1];
+            }
+        __syncthreads();
+        {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) v += Cs[w * 256 + tid];
+            const int c8 = tid & 7, gg = (tid >> 3) & 7, nb = (tid >> 6) & 1, par = tid >> 7;
+            const int k = kbase + 2 * gg + par;
+            const int col = nb * 8 + c8;
+            const int ch = cb * ADJ_NCH + (col >> 1);
+            if (k < nk && ch < P.nb) {
+                double* dst = (double*)(P.alm + (row0 + k) * P.alm_stride + P.chan0 + ch) + (col & 1);
+                if (P.nrb > 1) atomicAdd(dst, v);          // ring blocks of one (m, channel block) meet here
+                else if (P.accumulate) *dst += v;
+                else *dst = v;
+            }
+        }
+        __syncthreads();   // Cs consumed
+    }
+}
+
+// out = a - b  (residual map of the Jacobi refinement)
+__global__ void map_sub_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = i; e < n; e += stride) out[e] = a[e] - b[e];
+}
+
+// zero the rows of a PANEL batch (before ring blocks accumulate into it)
+__global__ void panel_zero_kernel(double2* __restrict__ alm, long long nalm, long long stride, int chan0, int nb) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nalm * nb) return;
+    const long long row = e / nb;
+    const int c = (int)(e - row * nb);
+    alm[row * stride + chan0 + c] = make_double2(0.0, 0.0);
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -1528,5 +1804,77 @@ extern "C" int cora_b200_alm2map_spin2(void* plan, const void* almE, const void*
         rc = run_phase(pl, FU, nb, mapU + (long long)c0 * pl->npix, st);
         if (rc) return rc;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- map2alm
+extern "C" long long cora_b200_map2alm_workspace_bytes(void* plan, int nchan_batch) {
+    if (!plan) return -1;
+    const ShtPlan* pl = (const ShtPlan*)plan;
+    return (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16 * round4(nchan_batch) + 256;
+}
+
+extern "C" int cora_b200_map2alm(void* plan, const double* map, int nchan, const double* ring_weights, int accumulate,
+                                 void* alm_panel, long long panel_stride, int chan0, void* workspace, long long ws_bytes,
+                                 void* stream) {
+    CB_REQUIRE(plan && map && alm_panel && workspace, 1, "map2alm: null argument");
+    CB_REQUIRE(nchan >= 1 && chan0 >= 0 && panel_stride >= chan0 + nchan, 1, "map2alm: bad sizes (nchan=%d chan0=%d stride=%lld)", nchan,
+               chan0, panel_stride);
+    ShtPlan* pl = (ShtPlan*)plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long per = (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16;
+    long long cap = ((ws_bytes - 256) / per) & ~3LL;
+    CB_REQUIRE(cap >= 4, 4, "map2alm: workspace too small (%lld B; need %lld B per 4 channels)", ws_bytes, 4 * per);
+    int nbmax = (int)std::min<long long>(cap, nchan);
+    if (nbmax < nchan && nbmax >= 8) nbmax -= nbmax % 8;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t adj_smem = sizeof(double) * (2 * (size_t)ADJ_RT * ADJ_BLD + 8 * 2 * 8 * ADJ_ALD + 8 * 256);
+    CB_CUDA(cudaFuncSetAttribute(sht_legendre_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+    CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int c0 = 0; c0 < nchan; c0 += nbmax) {
+        const int nb = std::min(nbmax, nchan - c0);
+        double2* F = (double2*)ws;
+        {
+            KTimer kt(K_PHASE, st);
+            for (const auto& pc : pl->classes) {
+                AnaParams Q;
+                Q.map = map + (long long)c0 * pl->npix; Q.npix = pl->npix; Q.F = F; Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
+                Q.tw = pl->d_tw; Q.chirp = pl->d_chirp; Q.bhat = pl->d_bhat;
+                Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
+                Q.wring = ring_weights; Q.wscale = 4.0 * 3.14159265358979323846 / (double)pl->npix; Q.nside = pl->nside;
+                Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
+                dim3 grid(pc.nrings, Q.ncg * (2 / pc.P));
+                if (pc.threads == 256) sht_ring_analysis_kernel<256><<<grid, 256, phase_smem(pc), st>>>(Q);
+                else sht_ring_analysis_kernel<512><<<grid, 512, phase_smem(pc), st>>>(Q);
+                count_launch();
+                CB_LAUNCH_CHECK();
+            }
+        }
+        LegAdjParams P;
+        P.F = F; P.alm = (double2*)alm_panel; P.alm_stride = panel_stride; P.chan0 = chan0 + c0; P.nb = nb;
+        P.cth = pl->d_cth; P.sth = pl->d_sth; P.nm_mant = pl->d_nm_mant; P.nm_exp = pl->d_nm_exp; P.rc = pl->d_rc;
+        P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
+        P.nrb = ceil_div(pl->nrn, ADJ_RT); P.ncb = ceil_div(nb, ADJ_NCH); P.ncg = ceil_div(nb, 4);
+        P.accumulate = accumulate;
+        if (P.nrb > 1 && !accumulate) {
+            panel_zero_kernel<<<ceil_div(pl->nalm * nb, 256), 256, 0, st>>>((double2*)alm_panel, pl->nalm, panel_stride, chan0 + c0, nb);
+            count_launch();
+            CB_LAUNCH_CHECK();
+        }
+        const long long grid = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
+        CB_REQUIRE(grid < 2147483647LL, 3, "map2alm: Legendre grid too large (%lld)", grid);
+        { KTimer kt(K_LEGENDRE, st); sht_legendre_adj_kernel<<<(unsigned)grid, ADJ_THREADS, adj_smem, st>>>(P); }
+        count_launch();
+        CB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int cora_b200_map_sub(const double* a, const double* b, long long n, double* out, void* stream) {
+    CB_REQUIRE(a && b && out && n >= 1, 1, "map_sub: bad arguments");
+    map_sub_kernel<<<(unsigned)std::min<long long>(ceil_div(n, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    count_launch();
+    CB_LAUNCH_CHECK();
     return 0;
 }

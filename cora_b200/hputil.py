@@ -201,3 +201,116 @@ def sphtrans_inv_sky(alm, nside, device_out=False):
     if device_out:
         return sky
     return _dev.to_host(sky)
+
+
+# ------------------------------------------------------------------ forward transform
+# cora calls healpy.map2alm with use_weights=True, iter=2 (``hputil.py:46-47``).  healpy's ring
+# weights are data files of the healpy distribution (not available here): pass them explicitly
+# as ``ring_weights`` (absolute weights of the 2*nside northern rings) to reproduce that mode.
+_weight = True
+_iter = 2
+
+
+def map2alm_device(maps_dev, nside, lmax=None, iter=None, ring_weights=None, panel=None):
+    """Batched scalar analysis on device: CUDA float64 ``[nchan, npix]`` -> PANEL alm
+    ``complex128[nalm, nchan]``.  One quadrature pass plus ``iter`` Jacobi refinements
+    ``a += A(map - S a)`` (what ``healpy.map2alm(..., iter=iter)`` does)."""
+    t = _dev.torch()
+    nchan = int(maps_dev.shape[0])
+    lmax = 3 * nside - 1 if lmax is None else int(lmax)
+    iter = _iter if iter is None else int(iter)
+    plan = _dev.sht_plan(nside, lmax)
+    lib = _lib.load()
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    if panel is None:
+        panel = _dev.empty((nalm, nchan), t.complex128)
+    rw = None
+    if ring_weights is not None:
+        rw = np.asarray(ring_weights, dtype=np.float64)
+        if rw.shape != (2 * nside,):
+            raise ValueError("ring_weights must have 2*nside entries")
+        rw = _dev.to_device(rw, t.float64)
+    need = max(lib.cora_b200_map2alm_workspace_bytes(plan, nchan), lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, nchan))
+    per16 = max(lib.cora_b200_map2alm_workspace_bytes(plan, 16), lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, 16))
+    nbytes = min(need, max(per16, _dev.free_bytes() - (2 << 30)))
+    ws = _dev.workspace(nbytes)
+
+    def analyse(src, accumulate):
+        _lib.call("cora_b200_map2alm", plan, _lib.ptr(src), nchan, _lib.ptr(rw), int(accumulate), _lib.ptr(panel),
+                  int(panel.shape[1]), 0, _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+
+    analyse(maps_dev, 0)
+    if iter > 0:
+        res = _dev.empty(tuple(maps_dev.shape), t.float64)
+        for _ in range(iter):
+            _lib.call("cora_b200_alm2map", plan, _lib.ptr(panel), _lib.ALM_PANEL, int(panel.shape[1]), nchan, _lib.ptr(res),
+                      _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+            _lib.call("cora_b200_map_sub", _lib.ptr(maps_dev), _lib.ptr(res), int(maps_dev.numel()), _lib.ptr(res),
+                      _lib.stream_ptr())
+            analyse(res, 1)
+    return panel
+
+
+def _nside_of(npix):
+    nside = int(round(np.sqrt(npix / 12.0)))
+    if 12 * nside * nside != npix:
+        raise ValueError("Wrong pixel number (it is not 12*nside**2)")   # healpy.npix2nside's message
+    return nside
+
+
+def sphtrans_real(hpmap, lmax=None, lside=None, ring_weights=None):
+    """Spherical harmonic transform of a real map -> ``alm[l, m]``, m >= 0 (``hputil.py:195-234``)."""
+    t = _dev.torch()
+    hpmap = np.ascontiguousarray(hpmap, dtype=np.float64)
+    nside = _nside_of(hpmap.size)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    if lside is None or lside < lmax:
+        lside = lmax
+    panel = map2alm_device(_dev.to_device(hpmap[np.newaxis], t.float64), nside, lmax, ring_weights=ring_weights)
+    dense = panel_to_dense(panel, lmax, 1)[0].cpu().numpy()
+    alm = np.zeros([lside + 1, lside + 1], dtype=np.complex128)
+    alm[: lmax + 1, : lmax + 1] = dense
+    return alm
+
+
+def sphtrans_complex(hpmap, lmax=None, centered=False, lside=None):
+    """Transform of a complex function (``hputil.py:237-271``): real and imaginary parts separately."""
+    if lmax is None:
+        lmax = 3 * _nside_of(hpmap.size) - 1
+    alm = _make_full_alm(sphtrans_real(hpmap.real, lmax=lmax, lside=lside), centered=centered)
+    alm = alm + 1.0j * _make_full_alm(sphtrans_real(hpmap.imag, lmax=lmax, lside=lside), centered=centered)
+    return alm
+
+
+def sphtrans_sky(skymap, lmax=None, device_out=False, ring_weights=None):
+    """Transform a 3-D sky map channel by channel (``hputil.py:460-497``), all channels batched.
+
+    ``skymap[freq, pixel]`` -> ``alms[freq, l, m]``.  The polarised branch of the reference
+    (``skymap[freq, pol >= 3, pixel]`` through ``healpy.map2alm([T, Q, U])``) needs the spin-2
+    analysis, which is not built yet: it raises ``NotImplementedError`` rather than fall back."""
+    t = _dev.torch()
+    if len(skymap.shape) == 3 and skymap.shape[1] >= 3:
+        raise NotImplementedError("polarised sphtrans_sky (spin-2 analysis) is not implemented in cora_b200 yet")
+    if len(skymap.shape) == 3:
+        raise Exception("skymap wrong shape.")   # [freq, pol < 3, pix]: the reference hands a 2-D block to healpy and fails there
+    nside = _nside_of(skymap.shape[-1])
+    if lmax is None:
+        lmax = 3 * nside - 1
+    maps = _dev.to_device(skymap, t.float64)
+    panel = map2alm_device(maps, nside, lmax, ring_weights=ring_weights)
+    dense = panel_to_dense(panel, lmax, int(maps.shape[0]))
+    return dense if device_out else _dev.to_host(dense)
+
+
+def sph_ps(map1, map2=None, lmax=None):
+    """Angular (cross) power spectrum of real maps (``hputil.py:607-619``):
+    ``C_l = (a1_l0 conj(a2_l0) + 2 Re sum_{m>0} a1_lm conj(a2_lm)) / (2l + 1)``.
+    (The reference tests ``if map is not None`` -- the builtin, always true -- so its auto-spectrum
+    call dies inside ``sphtrans_real(None)``; here ``map2=None`` means the auto-spectrum.)"""
+    lmax = lmax if lmax is not None else (3 * _nside_of(np.asarray(map1).size) - 1)
+    alm1 = sphtrans_real(map1, lmax)
+    alm2 = sphtrans_real(map2, lmax) if map2 is not None else alm1
+    prod = alm1 * alm2.conj()
+    s = prod[:, 0] + 2 * prod[:, 1:].sum(axis=1).real
+    return s / (2.0 * np.arange(lmax + 1) + 1.0)

@@ -183,6 +183,23 @@ int cora_b200_draw_apply_slabs(const double* root, const int* l_list_h, const in
 int cora_b200_alm_slabs_to_panel(const void* recv, const long long* l_off, int lmax, int nchan, void* alm_panel,
                                  long long panel_stride, int chan0, void* stream);
 
+/* ------------------------------------------------------------------ forward SHT --- */
+/* Scalar analysis of `nchan` RING maps: one HEALPix quadrature pass
+ *   a_lm = (4 pi / npix) sum_rings w_ring lambda_lm(theta_ring) sum_j map(ring, j) exp(-i m phi_j)
+ * written to (accumulate = 0) or added to (accumulate = 1) the PANEL array
+ * alm_panel[idx(l, m) * panel_stride + chan0 + c].  healpy.map2alm's `iter` Jacobi refinements
+ * are a += A(map - S a): cora_b200_alm2map + cora_b200_map_sub + this with accumulate = 1.
+ * replaces: healpy.map2alm at cora/util/hputil.py:228-230 (sphtrans_real), :310-321
+ * (sphtrans_real_pol, T and V), used by sphtrans_sky (:460-497) and sph_ps (:607-619).
+ * ring_weights: device float64[2 nside] absolute weights of the northern rings incl. the equator
+ * (healpy's use_weights=True tables are data files of the healpy distribution), or NULL = 1.   */
+long long cora_b200_map2alm_workspace_bytes(void* plan, int nchan_batch);
+int cora_b200_map2alm(void* plan, const double* map, int nchan, const double* ring_weights, int accumulate,
+                      void* alm_panel, long long panel_stride, int chan0, void* workspace, long long ws_bytes,
+                      void* stream);
+/* out[i] = a[i] - b[i], i < n (the residual map of the refinement) */
+int cora_b200_map_sub(const double* a, const double* b, long long n, double* out, void* stream);
+
 /* ---- fused exchange over peer memory (NVLink / NVSwitch, one process per GPU) ------------
  * The reference moves data between ranks with caput's MPIArray.redistribute
  * (cora/core/skysim.py:128) after the compute.  Here the producing kernels store straight into

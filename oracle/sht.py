@@ -244,3 +244,87 @@ def alm2map_direct(alm, nside, lmax=None):
             else:
                 out += 2.0 * (a * sph_harm_y(l, m, theta, phi)).real
     return out
+
+
+# ------------------------------------------------------------------- analysis (map -> alm)
+# Restates ``healpy.map2alm(map, lmax=lmax, use_weights=..., iter=...)`` as used by
+# ``cora/util/hputil.py:195-234`` (``sphtrans_real``), ``:274-323`` (``sphtrans_real_pol``),
+# ``:460-497`` (``sphtrans_sky``) and ``:607-619`` (``sph_ps``): the HEALPix quadrature
+#
+#     a_lm^(0) = (4 pi / npix) sum_rings w_ring lambda_lm(theta_ring) sum_j f(ring, j) exp(-i m phi_j)
+#
+# followed by ``iter`` Jacobi refinements  a += A(f - S a)  (HEALPix ``map2alm_iterative``).
+# cora calls it with ``use_weights=True, iter=2`` (``hputil.py:46-47``); healpy then reads the ring
+# weights from its data files (``weight_ring_n%05d.fits``), which are not available here, so the
+# weights are an explicit argument (absolute, one per northern ring incl. the equator; default 1).
+# Parity unpinned for the same reason as the synthesis (no healpy); pinned analytically by the
+# adjoint identity against the validated synthesis (tests/test_oracle_sht.py).
+def _phase_from_rings(maps, geom, ring_sel, mmax, wgt):
+    """Ring analysis: ``F_m(ring) = wgt[ring] sum_j f(ring, j) exp(-i m phi_j)`` -> (mmax+1, nsel, nchan)."""
+    m = np.arange(mmax + 1)
+    out = np.zeros((mmax + 1, len(ring_sel), maps.shape[0]), dtype=np.complex128)
+    for a, r in enumerate(ring_sel):
+        nph = int(geom["nph"][r])
+        start = int(geom["start"][r])
+        G = np.fft.fft(maps[:, start : start + nph], axis=1)  # (nchan, nph)
+        ph = wgt[r] * np.exp(-1j * m * geom["phi0"][r])
+        out[:, a, :] = G[:, m % nph].T * ph[:, None]
+    return out
+
+
+def _full_ring_weights(nside, ring_weights):
+    nring = 4 * nside - 1
+    w = np.ones(nring)
+    if ring_weights is not None:
+        rw = np.asarray(ring_weights, dtype=np.float64)
+        if rw.shape != (2 * nside,):
+            raise ValueError("ring_weights must have 2*nside entries")
+        i = np.arange(1, 4 * nside)
+        w = rw[np.minimum(i, 4 * nside - i) - 1]
+    return w * (4.0 * np.pi / nside2npix(nside))
+
+
+def map2alm_adjoint(maps, nside, lmax, ring_weights=None):
+    """One quadrature pass (no iteration): packed alm (nchan, nalm)."""
+    maps = np.atleast_2d(np.asarray(maps, dtype=np.float64))
+    g = ring_geometry(nside)
+    nring = 4 * nside - 1
+    F = _phase_from_rings(maps, g, np.arange(nring), lmax, _full_ring_weights(nside, ring_weights))
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    alm = np.zeros((maps.shape[0], nalm), dtype=np.complex128)
+    for m in range(lmax + 1):
+        lam = lambda_lm(lmax, m, g["cth"], g["sth"])  # (nl, nring)
+        alm[:, alm_index(lmax, m, m) : alm_index(lmax, lmax, m) + 1] = (lam @ F[m]).T
+    return alm
+
+
+def map2alm(maps, nside=None, lmax=None, iter=3, ring_weights=None):
+    """``healpy.map2alm`` restatement (scalar): quadrature + ``iter`` Jacobi refinements."""
+    maps = np.asarray(maps, dtype=np.float64)
+    single = maps.ndim == 1
+    maps = np.atleast_2d(maps)
+    if nside is None:
+        nside = int(round(np.sqrt(maps.shape[1] / 12.0)))
+    if lmax is None:
+        lmax = 3 * nside - 1
+    alm = map2alm_adjoint(maps, nside, lmax, ring_weights)
+    for _ in range(iter):
+        alm += map2alm_adjoint(maps - alm2map(alm, nside, lmax), nside, lmax, ring_weights)
+    return alm[0] if single else alm
+
+
+def anafast(map1, map2=None, lmax=None, iter=3, ring_weights=None):
+    """Cross/auto power spectrum ``C_l = (|a_l0|^2 + 2 sum_{m>0} Re a1 conj(a2)) / (2l+1)``
+    (``hputil.sph_ps``, ``hputil.py:607-619`` / ``healpy.anafast``)."""
+    map1 = np.asarray(map1, dtype=np.float64)
+    nside = int(round(np.sqrt(map1.shape[-1] / 12.0)))
+    if lmax is None:
+        lmax = 3 * nside - 1
+    a1 = map2alm(map1, nside, lmax, iter, ring_weights)
+    a2 = a1 if map2 is None else map2alm(map2, nside, lmax, iter, ring_weights)
+    cl = np.zeros(lmax + 1)
+    for m in range(lmax + 1):
+        sl = slice(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1)
+        p = (a1[..., sl] * np.conj(a2[..., sl])).real
+        cl[m:] += (1.0 if m == 0 else 2.0) * p
+    return cl / (2.0 * np.arange(lmax + 1) + 1.0)
