@@ -461,6 +461,42 @@ def run_ours(args):
     except Exception:
         traffic = None
     stage_share = {k: round(v[0] / args.steps, 4) for k, v in kernels.items() if v[1]}
+
+    # ---- per-stage roofline: algorithmic work of THIS rank's share / its event-timed stage time
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6500.0, "fallback (B200_PROFILING.md)"
+    L = lmax + 1
+    nalm = L * (L + 1) / 2.0
+    nring = 4 * nside - 1
+    sum_l1 = float(np.sum(np.arange(L)[rank::world] + 1)) if world > 1 else nalm   # sum over local l of (l+1)
+
+    def _stage(name, work, unit_scale, peak, bound, what):
+        t_ms = stage_share.get(name)
+        if not t_ms:
+            return None
+        ach = work / (t_ms * 1e-3) / unit_scale
+        return {"ms": t_ms, "bound": bound, "achieved": round(ach, 3), "peak": round(peak, 1), "frac": round(ach / peak, 4),
+                "unit": "TFLOP/s" if unit_scale == 1e12 else "GB/s", "work": what}
+
+    pk = float(peak[0])
+    zi = 2 ** wp["zromb"] + 1
+    stage_roofline = {
+        "sht_legendre": _stage("sht_legendre", sht_flops(nside, lmax, cb_local), 1e12, pk, "tensor(fp64 DMMA)",
+                               "4*ceil(nring/2)*nalm*channels flop"),
+        "sht_phase": _stage("sht_phase", cb_local * (16.0 * nring * L + 8.0 * npix), 1e9, hbm_peak, "hbm",
+                            "16*nring*L + 8*npix bytes per channel (F read + map written)"),
+        "apply": _stage("apply", 2.0 * nchan * nchan * sum_l1 * 2 / 2.0, 1e12, pk, "tensor(fp64 DMMA)",
+                        "2*nz^2*(l+1) real flop per l for complex draws, halved for the triangular (Cholesky) roots"),
+        "cholesky": _stage("cholesky", nl_local * nchan ** 3 / 3.0, 1e12, pk, "tensor(fp64 DMMA) / latency",
+                           "nz^3/3 flop per l"),
+        "draw": _stage("draw", 16.0 * nchan * sum_l1, 1e9, hbm_peak, "hbm", "16*nz*(l+1) bytes written per l"),
+        "cl_fill": _stage("cl_fill", 8.0 * L * nchan * nchan / world, 1e9, hbm_peak, "L1/L2 gather (hbm = output-write floor)",
+                          "8*L*nz^2 output bytes; %.3g evaluations of the 2-D interpolant" % (L * (zi * nchan) ** 2 / 2.0 / world)),
+    }
+    stage_roofline = {k: v for k, v in stage_roofline.items() if v}
     if world > 1 and exchange_mode == "p2p":
         sh.peers.check()
         sh.peers.close()
@@ -493,7 +529,8 @@ def run_ours(args):
                    "l2": "per-step working set (C_l %.0f MB, alm %.0f MB, maps %.0f MB per GPU) exceeds the 126 MB L2; no flush needed"
                          % (8e-6 * nl_local * nchan * nchan, 16e-6 * (lmax + 1) * (lmax + 2) / 2 * cb_local, 8e-6 * cb_local * npix),
                    "one_off_table_build_s": round(table_s, 3),
-                   "stage_ms_per_step": stage_share},
+                   "stage_ms_per_step": stage_share,
+                   "stage_roofline": stage_roofline, "hbm_peak_source": hbm_src},
         "e2e": {"value": None, "unit": UNIT, "error": e2e_error} if e2e_error else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
                 "steps": e2e_steps, "ms_each": e2e_each, "host_bound_to_gpu_numa_node": numa_bound, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
         "gpu_launches": int(launches),
