@@ -50,6 +50,36 @@ def to_host(x):
     return h.numpy()
 
 
+_stage = {}
+
+
+def stream_to_host(x, chunk_bytes=1 << 30):
+    """Copy a CUDA tensor to the host through a bounded two-slot pinned staging ring (for results
+    larger than what can be held pinned, e.g. 26 GB of maps per GPU): every byte crosses PCIe,
+    nothing but the ring is retained.  Returns the number of bytes copied."""
+    t = torch()
+    flat = x.contiguous().view(-1)
+    esz = flat.element_size()
+    n = max(1, int(chunk_bytes) // esz)
+    key = (t.cuda.current_device(), flat.dtype, n)
+    if key not in _stage:
+        _stage[key] = [t.empty((n,), dtype=flat.dtype, pin_memory=True) for _ in range(2)]
+    ring = _stage[key]
+    evs = [None, None]
+    st = t.cuda.current_stream()
+    for i, o in enumerate(range(0, flat.numel(), n)):
+        k = i & 1
+        if evs[k] is not None:
+            evs[k].synchronize()
+        m = min(n, flat.numel() - o)
+        ring[k][:m].copy_(flat[o : o + m], non_blocking=True)
+        evs[k] = t.cuda.Event()
+        evs[k].record(st)
+    st.synchronize()
+    traffic["d2h"] += flat.numel() * esz
+    return flat.numel() * esz
+
+
 def bind_host_to_gpu(index=None):
     """Pin the calling process to the CPU cores NVML reports as local to the GPU, so that pinned
     host buffers are first-touched on the GPU's NUMA node (the map D2H copy is the slowest leg of

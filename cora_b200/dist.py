@@ -314,7 +314,10 @@ class ShardedSky(object):
         st = self._p2p_setup()
         tab = self._p2p_tables(k)
         if cla is None:
-            cla = st["cla"][k].tensor((self.nl, self.nz, self.nz), t.float64) if st["pairs"] else self._buf["cla"]
+            if st["pairs"]:
+                cla = self._persistent("cla_view%d" % k, lambda: st["cla"][k].tensor((self.nl, self.nz, self.nz), t.float64))
+            else:
+                cla = self._buf["cla"]
         if roots is None:
             outb = self._persistent("root", lambda: (_dev.empty((self.nl, self.nz, self.nz), t.float64),
                                                      _dev.empty((self.nl,), t.int32), _dev.empty((self.nl,), t.int32)))
@@ -344,7 +347,7 @@ class ShardedSky(object):
         t = _dev.torch()
         st = self._p2p_setup()
         L = self.lmax + 1
-        panel = st["panel"][k].tensor((L * (L + 1) // 2, self.cb), t.complex128)
+        panel = self._persistent("panel_view%d" % k, lambda: st["panel"][k].tensor((L * (L + 1) // 2, self.cb), t.complex128))
         plan = _dev.sht_plan(self.nside, self.lmax)
         ws = self._persistent("sht_ws", lambda: _dev.sht_workspace(plan, _lib.ALM_PANEL, self.cb, reserve=(4 << 30) + 8 * self.cb * self.npix)[0])
         return hputil.alm2map_device(panel, self.nside, self.lmax, _lib.ALM_PANEL, self.cb, self.cb, out=out, ws=ws)
