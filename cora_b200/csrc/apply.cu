@@ -49,12 +49,12 @@ struct LDesc {
     int ld;           // row length (complex) of the gauss buffer for this l
 };
 
-__global__ void draw_kernel(const LDesc* __restrict__ ld, int nz, unsigned long long seed, double2* __restrict__ G) {
+__global__ void draw_kernel(const LDesc* __restrict__ ld, int nz, unsigned long long seed, double2* __restrict__ G, unsigned nu_ctr0) {
     const LDesc d = ld[blockIdx.z];
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int nu = blockIdx.y;
     if (m > d.l) return;
-    G[d.goff + (long long)nu * d.ld + m] = philox_cnormal(seed, (unsigned)d.l, (unsigned)m, (unsigned)nu);
+    G[d.goff + (long long)nu * d.ld + m] = philox_cnormal(seed, (unsigned)d.l, (unsigned)m, (unsigned)nu + nu_ctr0);
 }
 
 // ---------------------------------------------------------------------------- apply
@@ -250,7 +250,7 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
                            unsigned long long seed, const void* gauss, long long gauss_ld, void* alm_panel,
                            long long panel_stride, int chan0, int nu0, int nnu, const long long* row0_h,
                            const long long* nu_base, const int* nu_width, void* workspace, long long ws_bytes,
-                           void* stream, const void* nu_ptr = nullptr) {
+                           void* stream, const void* nu_ptr = nullptr, unsigned nu_ctr0 = 0) {
     CB_REQUIRE(root && l_list_h && (alm_panel || nu_ptr) && workspace, 1, "draw_apply: null argument");
     CB_REQUIRE(nl >= 1 && nz >= 1 && lmax >= 0 && nnu >= 1 && nu0 >= 0 && nu0 + nnu <= nz, 1, "draw_apply: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -289,7 +289,7 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
         for (auto& d : hd) lbig = std::max(lbig, d.l);
         const double2* Gsrc = (const double2*)gauss;
         if (!gauss) {
-            { KTimer kt(K_DRAW, st); draw_kernel<<<dim3(ceil_div(lbig + 1, 128), nz, nb), 128, 0, st>>>(dd, nz, seed, Gbuf); }
+            { KTimer kt(K_DRAW, st); draw_kernel<<<dim3(ceil_div(lbig + 1, 128), nz, nb), 128, 0, st>>>(dd, nz, seed, Gbuf, nu_ctr0); }
             count_launch();
             CB_LAUNCH_CHECK();
             Gsrc = Gbuf;
@@ -339,10 +339,10 @@ extern "C" int cora_b200_draw_apply_slabs(const double* root, const int* l_list_
 }
 
 extern "C" int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
-                                          int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
-                                          const void* nu_ptr, const int* nu_width, void* workspace, long long ws_bytes,
-                                          void* stream) {
-    CB_REQUIRE(nu_ptr && nu_width, 1, "draw_apply_peers: null peer description");
+                                          int lmax, unsigned long long seed, int draw_counter0, const void* gauss,
+                                          long long gauss_ld, const void* nu_ptr, const int* nu_width, void* workspace,
+                                          long long ws_bytes, void* stream) {
+    CB_REQUIRE(nu_ptr && nu_width && draw_counter0 >= 0, 1, "draw_apply_peers: bad peer description");
     return draw_apply_impl(root, l_list_h, dense_flag, nl, nz, lmax, seed, gauss, gauss_ld, nullptr, 0, 0, 0, nz, nullptr,
-                           nullptr, nu_width, workspace, ws_bytes, stream, nu_ptr);
+                           nullptr, nu_width, workspace, ws_bytes, stream, nu_ptr, (unsigned)draw_counter0);
 }

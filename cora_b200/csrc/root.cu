@@ -20,7 +20,7 @@ constexpr int CH_THREADS = 256;
 
 // jitter + copy lower triangle (upper zeroed); also per-matrix max(diag)
 __global__ void root_prepare_kernel(const double* __restrict__ cl, int nz, double jitter_rel, double* __restrict__ root,
-                                    double* __restrict__ dmax_out) {
+                                    double* __restrict__ dmax_out, const double* __restrict__ dmax_in) {
     __shared__ double red[256];
     const long long base = (long long)blockIdx.x * nz * nz;
     double mx = -1.0e308;
@@ -31,8 +31,10 @@ __global__ void root_prepare_kernel(const double* __restrict__ cl, int nz, doubl
         if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
         __syncthreads();
     }
-    const double cmax = red[0] * jitter_rel;
-    if (threadIdx.x == 0) dmax_out[blockIdx.x] = red[0];
+    // dmax_in: the diagonal maximum of a larger (block-diagonal) matrix this one is a block of
+    const double dm = dmax_in ? dmax_in[blockIdx.x] : red[0];
+    const double cmax = dm * jitter_rel;
+    if (threadIdx.x == 0) dmax_out[blockIdx.x] = dm;
     for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
         const int r = (int)(e / nz), c = (int)(e % nz);
         double v = 0.0;
@@ -356,8 +358,37 @@ extern "C" long long cora_b200_root_workspace_bytes(int nl, int nz) {
     return root_fixed_bytes(nl, nz) + 16LL * nz * nz * (long long)nl;
 }
 
+// max(diag) per matrix, optionally merged with the maxima already in dmax (merge != 0)
+__global__ void diag_max_kernel(const double* __restrict__ cl, int nz, double* __restrict__ dmax, int merge) {
+    __shared__ double red[256];
+    const long long base = (long long)blockIdx.x * nz * nz;
+    double mx = -1.0e308;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) mx = fmax(mx, cl[base + (long long)i * nz + i]);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dmax[blockIdx.x] = merge ? fmax(dmax[blockIdx.x], red[0]) : red[0];
+}
+
+extern "C" int cora_b200_diag_max(const double* cl, int nl, int nz, double* dmax, int merge, void* stream) {
+    CB_REQUIRE(cl && dmax && nl >= 1 && nz >= 1, 1, "diag_max: bad arguments");
+    diag_max_kernel<<<nl, 256, 0, (cudaStream_t)stream>>>(cl, nz, dmax, merge);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, double clip_rel, double* root,
                                       int* used_eigh, int* num_pos, void* workspace, long long ws_bytes, void* stream) {
+    return cora_b200_root_batched_block(cl, nl, nz, jitter_rel, clip_rel, nullptr, root, used_eigh, num_pos, workspace, ws_bytes, stream);
+}
+
+extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, double jitter_rel, double clip_rel,
+                                            const double* diag_max, double* root, int* used_eigh, int* num_pos,
+                                            void* workspace, long long ws_bytes, void* stream) {
     CB_REQUIRE(cl && root && used_eigh && num_pos && workspace, 1, "root_batched: null argument");
     CB_REQUIRE(nl >= 1 && nz >= 1, 1, "root_batched: bad sizes nl=%d nz=%d", nl, nz);
     CB_REQUIRE(ws_bytes >= root_fixed_bytes(nl, nz) + 16LL * nz * nz, 4,
@@ -375,7 +406,7 @@ extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double j
     double* GV = (double*)ws;
     long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
 
-    { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax); }
+    { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax, diag_max); }
     count_launch();
     CB_LAUNCH_CHECK();
     {

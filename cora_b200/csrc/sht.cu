@@ -1709,11 +1709,12 @@ static size_t phase_smem(const PhaseClass& pc) {
     return pc.P * seq * 16 + (pc.Mmax <= 512 ? (size_t)PH_MAXSLICE_ITEMS * 4 * 16 : 0);
 }
 
-static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, cudaStream_t st) {
+static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, cudaStream_t st, long long map_stride = 0) {
     KTimer kt(K_PHASE, st);
     for (const auto& pc : pl->classes) {
         PhaseParams Q;
-        Q.F = F; Q.map = map; Q.npix = pl->npix; Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
+        Q.F = F; Q.map = map; Q.npix = map_stride > 0 ? map_stride : pl->npix;   // PhaseParams::npix is the channel stride of the output
+        Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
         Q.tw = pl->d_tw; Q.chirp = pl->d_chirp; Q.bhat = pl->d_bhat;
         Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
         Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
@@ -1728,7 +1729,14 @@ static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, c
 
 extern "C" int cora_b200_alm2map(void* plan, const void* alm, int layout, long long alm_stride, int nchan, double* map,
                                  void* workspace, long long ws_bytes, void* stream) {
+    return cora_b200_alm2map_strided(plan, alm, layout, alm_stride, nchan, map, 0, workspace, ws_bytes, stream);
+}
+
+extern "C" int cora_b200_alm2map_strided(void* plan, const void* alm, int layout, long long alm_stride, int nchan, double* map,
+                                         long long map_stride, void* workspace, long long ws_bytes, void* stream) {
     CB_REQUIRE(plan && alm && map && workspace, 1, "alm2map: null argument");
+    CB_REQUIRE(map_stride == 0 || map_stride >= ((ShtPlan*)plan)->npix, 1, "alm2map: map_stride %lld < npix", map_stride);
+    const long long mstride = map_stride > 0 ? map_stride : ((ShtPlan*)plan)->npix;
     CB_REQUIRE(layout == CORA_B200_ALM_PACKED || layout == CORA_B200_ALM_PANEL, 1, "alm2map: unknown alm layout %d", layout);
     CB_REQUIRE(nchan >= 1, 1, "alm2map: nchan must be >= 1");
     ShtPlan* pl = (ShtPlan*)plan;
@@ -1757,7 +1765,7 @@ extern "C" int cora_b200_alm2map(void* plan, const void* alm, int layout, long l
         }
         int rc = run_legendre<0>(pl, almT, nullptr, stride, chan0, nb, F, nullptr, st);
         if (rc) return rc;
-        rc = run_phase(pl, F, nb, map + (long long)c0 * pl->npix, st);
+        rc = run_phase(pl, F, nb, map + (long long)c0 * mstride, st, mstride);
         if (rc) return rc;
     }
     return 0;
@@ -1765,7 +1773,15 @@ extern "C" int cora_b200_alm2map(void* plan, const void* alm, int layout, long l
 
 extern "C" int cora_b200_alm2map_spin2(void* plan, const void* almE, const void* almB, int layout, long long alm_stride, int nchan,
                                        double* mapQ, double* mapU, void* workspace, long long ws_bytes, void* stream) {
+    return cora_b200_alm2map_spin2_strided(plan, almE, almB, layout, alm_stride, nchan, mapQ, mapU, 0, workspace, ws_bytes, stream);
+}
+
+extern "C" int cora_b200_alm2map_spin2_strided(void* plan, const void* almE, const void* almB, int layout, long long alm_stride,
+                                               int nchan, double* mapQ, double* mapU, long long map_stride, void* workspace,
+                                               long long ws_bytes, void* stream) {
     CB_REQUIRE(plan && almE && almB && mapQ && mapU && workspace, 1, "alm2map_spin2: null argument");
+    CB_REQUIRE(map_stride == 0 || map_stride >= ((ShtPlan*)plan)->npix, 1, "alm2map_spin2: map_stride %lld < npix", map_stride);
+    const long long mstride = map_stride > 0 ? map_stride : ((ShtPlan*)plan)->npix;
     CB_REQUIRE(layout == CORA_B200_ALM_PACKED || layout == CORA_B200_ALM_PANEL, 1, "alm2map_spin2: unknown alm layout %d", layout);
     CB_REQUIRE(nchan >= 1, 1, "alm2map_spin2: nchan must be >= 1");
     ShtPlan* pl = (ShtPlan*)plan;
@@ -1799,9 +1815,9 @@ extern "C" int cora_b200_alm2map_spin2(void* plan, const void* almE, const void*
         }
         int rc = run_legendre<2>(pl, pE, pB, stride, chan0, nb, FQ, FU, st);
         if (rc) return rc;
-        rc = run_phase(pl, FQ, nb, mapQ + (long long)c0 * pl->npix, st);
+        rc = run_phase(pl, FQ, nb, mapQ + (long long)c0 * mstride, st, mstride);
         if (rc) return rc;
-        rc = run_phase(pl, FU, nb, mapU + (long long)c0 * pl->npix, st);
+        rc = run_phase(pl, FU, nb, mapU + (long long)c0 * mstride, st, mstride);
         if (rc) return rc;
     }
     return 0;

@@ -339,7 +339,7 @@ class ShardedSky(object):
             ws = _dev.workspace(64 * self.nl + 4096)
             gptr, gld = _lib.ptr(gauss), int(gauss.shape[-1])
         _lib.call("cora_b200_draw_apply_peers", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
-                  self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(tab["nu_ptr"]), _lib.ptr(st["nu_width"]),
+                  self.lmax, ctypes.c_ulonglong(int(seed)), 0, gptr, gld, _lib.ptr(tab["nu_ptr"]), _lib.ptr(st["nu_width"]),
                   _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr())
 
     def p2p_sht(self, k, out=None):
@@ -416,3 +416,160 @@ def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, parti
         recv = exchange(send, sh.plan, rank, group)
         sky = sh.synthesize(recv)
     return sky if device_out else _dev.to_host(sky)
+
+
+class ShardedPolSky(object):
+    """``cora-makesky gaussianfg --pol full`` sharded over GPUs ("shard (pol-block, l)
+    for roots, channels for SHT").
+
+    The reference builds the dense block-diagonal covariance ``blockdiag(T, E, B, V)`` of size
+    ``(4 nfreq)^2`` per l (``cora/scripts/makesky.py:368-382``; 206 GB at nside 512 x 1024
+    channels) and roots it whole.  Here the blocks are kept apart: T = ``FullSkySynchrotron``,
+    E = B = ``FullSkyPolarisedSynchrotron`` (one root, applied to two independent draw streams),
+    V = 0.  What is preserved: the jitter ``1e-14 max(diag)`` is taken over the whole matrix'
+    diagonal (``cora_b200_root_batched_block``), the Philox counters of block b are offset by
+    ``b nfreq`` -- the same draws the dense formulation consumes -- and the output layout
+    ``float64[freq, 4, pix]``.  What differs, at the level of the regulariser only: the Cholesky
+    / eigen decision and the eigenvalue clip act per block (the reference's act on the whole
+    matrix), and Stokes V is exactly 0 (the reference's V is ``sqrt(cmax) g`` on the Cholesky
+    branch, <= 1e-7 of T, and 0 on the eigen branch).
+
+    Exchange: apply stores straight into the PANEL buffers (T, E, B) of the GPU owning each
+    channel (``cora_b200.peer``); one flag barrier per step.  With one rank the same code runs on
+    local pointers."""
+
+    def __init__(self, nside, frequencies, lmax=None, zromb=3, group=None, partition="interleaved", rank=None, size=None,
+                 peers=None, models=None):
+        from . import galaxy, skysim
+        from . import peer as _peer
+
+        t = _dev.torch()
+        dist = _dist()
+        if size is None:
+            size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if size > 1 else 0
+        self.rank, self.size, self.group = int(rank), int(size), group
+        self.nside = int(nside)
+        self.freq = np.asarray(frequencies, dtype=np.float64)
+        self.nz = len(self.freq)
+        self.lmax = 3 * self.nside if lmax is None else int(lmax)   # makesky.py:367
+        self.plan = ShardPlan(self.lmax, self.nz, self.size, partition)
+        self.l_list = self.plan.l_lists[self.rank]
+        self.nl = len(self.l_list)
+        self.cb = int(self.plan.cb[self.rank])
+        self.npix = 12 * self.nside**2
+        self.models = models if models is not None else (galaxy.FullSkySynchrotron(), galaxy.FullSkyPolarisedSynchrotron())
+        za, self.zint = skysim._sample_frequencies(self.freq, zromb, None)
+        w = skysim.romberg_weights(zromb)
+        self.fill_inputs = [m._b200_fill_inputs(za, w) for m in self.models]
+        if peers is None:
+            peers = _peer.PeerGroup(self.rank, self.size, group) if self.size > 1 else _peer.LocalPeers(1).view(0)
+        self.peers = peers
+        L = self.lmax + 1
+        self.nalm = L * (L + 1) // 2
+        # PANEL buffers: [buffer set k][field T, E, B]
+        self.panel, self.panel_ptrs = [], []
+        for _ in range(2):
+            own, ptrs = zip(*[peers.alloc(16 * self.nalm * max(1, self.cb)) for _ in range(3)])
+            self.panel.append(own)
+            self.panel_ptrs.append(ptrs)
+        width = np.empty(self.nz, dtype=np.int32)
+        for s_ in range(self.size):
+            width[int(self.plan.chan_lo[s_]):int(self.plan.chan_hi[s_])] = int(self.plan.cb[s_])
+        self.nu_width = _dev.to_device(width, t.int32)
+        self._tables = [None, None]
+        self._buf = {}
+        self._k = 0
+
+    def _persistent(self, name, make):
+        if name not in self._buf:
+            self._buf[name] = make()
+        return self._buf[name]
+
+    def _nu_ptr(self, k):
+        from . import peer as _peer
+
+        t = _dev.torch()
+        if self._tables[k] is None:
+            tabs = []
+            for f in range(3):
+                pp = _peer.resolve(self.panel_ptrs[k][f])
+                nu_ptr = np.empty(self.nz, dtype=np.uint64)
+                for s_ in range(self.size):
+                    lo, hi = int(self.plan.chan_lo[s_]), int(self.plan.chan_hi[s_])
+                    nu_ptr[lo:hi] = np.uint64(pp[s_]) + np.uint64(16) * np.arange(hi - lo, dtype=np.uint64)
+                tabs.append(_dev.to_device(nu_ptr.view(np.int64), t.int64))
+            self._tables[k] = tabs
+        return self._tables[k]
+
+    def alm_phase(self, k, seed=0):
+        """fill (T, P) -> global diagonal maxima -> block roots -> draw + apply (T, E, B) with the
+        a_lm stored into the owners' PANEL buffers of set k."""
+        t = _dev.torch()
+        lib = _lib.load()
+        nl, nz = self.nl, self.nz
+        if nl == 0:
+            return
+        l0 = int(self.l_list[0])
+        step = self.size if self.plan.partition == "interleaved" else 1
+        cl = self._persistent("cl", lambda: [_dev.empty((nl, nz, nz), t.float64) for _ in range(2)])
+        roots = self._persistent("root", lambda: [(_dev.empty((nl, nz, nz), t.float64), _dev.empty((nl,), t.int32),
+                                                   _dev.empty((nl,), t.int32)) for _ in range(2)])
+        dmax = self._persistent("dmax", lambda: _dev.empty((nl,), t.float64))
+        for b in range(2):
+            self.models[b]._b200_fill(self.fill_inputs[b], l0, step, nl, nz, self.zint, cl[b])
+            _lib.call("cora_b200_diag_max", _lib.ptr(cl[b]), nl, nz, _lib.ptr(dmax), int(b > 0), _lib.stream_ptr())
+        rws = self._persistent("root_ws", lambda: nputil.root_workspace(nl, nz, max_eigh=nl if 16 * nz * nz * nl <= _dev.free_bytes() // 8
+                                                                        else max(4, nl // 8)))
+        for b in range(2):
+            root, used, npos = roots[b]
+            _lib.call("cora_b200_root_batched_block", _lib.ptr(cl[b]), nl, nz, 1e-14, 1e-16, _lib.ptr(dmax), _lib.ptr(root),
+                      _lib.ptr(used), _lib.ptr(npos), _lib.ptr(rws), int(rws.numel()), _lib.stream_ptr())
+        lmax_loc = int(self.l_list.max())
+
+        def mk():
+            full = lib.cora_b200_draw_apply_workspace_bytes(nz, lmax_loc, nl)
+            one = lib.cora_b200_draw_apply_workspace_bytes(nz, lmax_loc, 1)
+            return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
+
+        ws = self._persistent("draw_ws", mk)
+        tabs = self._nu_ptr(k)
+        for f, b in ((0, 0), (1, 1), (2, 1)):      # field -> block: T <- T root, E and B <- the polarised root
+            root, used, _ = roots[b]
+            _lib.call("cora_b200_draw_apply_peers", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), nl, nz, self.lmax,
+                      ctypes.c_ulonglong(int(seed)), f * nz, None, 0, _lib.ptr(tabs[f]), _lib.ptr(self.nu_width),
+                      _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr())
+
+    def sht_phase(self, k, out=None):
+        """T scalar, (E, B) -> (Q, U) spin-2, V = 0 -> ``float64[cb, 4, npix]``."""
+        t = _dev.torch()
+        lib = _lib.load()
+        cb, npix = self.cb, self.npix
+        if out is None:
+            out = self._persistent("out", lambda: _dev.zeros((cb, 4, npix), t.float64))
+        if cb == 0:
+            return out
+        plan = _dev.sht_plan(self.nside, self.lmax)
+
+        def mkws():
+            need = lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, cb) * 2
+            per = lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, 16) * 2
+            return _dev.workspace(min(need, max(per, _dev.free_bytes() - (4 << 30))))
+
+        ws = self._persistent("sht_ws", mkws)
+        pT, pE, pB = (self.panel[k][f] for f in range(3))
+        base = out.data_ptr()
+        _lib.call("cora_b200_alm2map_strided", plan, _lib.ptr(pT), _lib.ALM_PANEL, cb, cb, ctypes.c_void_p(base), 4 * npix,
+                  _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr())
+        _lib.call("cora_b200_alm2map_spin2_strided", plan, _lib.ptr(pE), _lib.ptr(pB), _lib.ALM_PANEL, cb, cb,
+                  ctypes.c_void_p(base + 8 * npix), ctypes.c_void_p(base + 16 * npix), 4 * npix, _lib.ptr(ws), int(ws.numel()),
+                  _lib.stream_ptr())
+        return out
+
+    def step(self, seed=0, out=None):
+        k = self._k & 1
+        self._k += 1
+        self.alm_phase(k, seed=seed)
+        self.peers.barrier()
+        return self.sht_phase(k, out=out)

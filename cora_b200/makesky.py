@@ -66,14 +66,30 @@ def make_21cm(fstate, nside, pol="full", eor=False, oversample=None):
     return cr.getpolsky() if pol == "full" else cr.getsky()
 
 
-def make_gaussianfg(fstate, nside, pol="full", rng=None, seed=None):
+def make_gaussianfg(fstate, nside, pol="full", rng=None, seed=None, blocked=None):
     """Full-sky Gaussian random field for synchrotron emission (``makesky.py:349-390``).
 
     The polarised case builds the block-diagonal ``(npol*nfreq)^2`` covariance exactly as the
     reference does (T = FullSkySynchrotron, E = B = FullSkyPolarisedSynchrotron, V = 0,
     ``lmax = 3*nside``) so that the global jitter / eigenvalue clip of the root acts on the whole
-    matrix.  Returns ``float64[nfreq, npol, npix]``."""
+    matrix.  Returns ``float64[nfreq, npol, npix]``.
+
+    ``blocked``: keep the T / E / B blocks apart instead of forming the dense ``(4 nfreq)^2``
+    matrices (``dist.ShardedPolSky``; same draws, global jitter, per-block Cholesky/eigen decision,
+    V = 0).  Default: only when the dense array would not fit comfortably (> 8 GB) -- the dense
+    path is the one with the reference's exact regulariser semantics."""
     from . import _dev, galaxy, hputil, skysim
+
+    if blocked is None:
+        blocked = pol == "full" and rng is None and 8.0 * (3 * nside + 1) * (4 * len(fstate.frequencies)) ** 2 > 8e9
+    if blocked:
+        if pol != "full" or rng is not None:
+            raise ValueError("blocked=True needs pol='full' and the device generator (rng=None)")
+        from . import dist as cdist
+
+        sh = cdist.ShardedPolSky(nside, fstate.frequencies, rank=0, size=1)
+        sky = sh.step(seed=int(np.random.randint(0, 2**31 - 1)) if seed is None else seed)
+        return _dev.to_host(sky)
 
     t = _dev.torch()
     fsyn = galaxy.FullSkySynchrotron()

@@ -67,11 +67,21 @@ long long cora_b200_alm2map_workspace_bytes(void* plan, int layout, int nchan_ba
 int cora_b200_alm2map(void* plan, const void* alm, int layout, long long alm_stride, int nchan,
                       double* map, void* workspace, long long ws_bytes, void* stream);
 
+/* As cora_b200_alm2map with an explicit channel stride of the output (map[chan * map_stride + pix],
+ * map_stride >= npix; 0 = npix): lets T, Q, U, V be written straight into the reference's
+ * [freq][pol][pix] layout (cora/util/hputil.py:516-521) with map_stride = npol * npix.       */
+int cora_b200_alm2map_strided(void* plan, const void* alm, int layout, long long alm_stride, int nchan,
+                              double* map, long long map_stride, void* workspace, long long ws_bytes, void* stream);
+
 /* Spin-2 synthesis (E,B) -> (Q,U), HEALPix sign convention.
  * replaces: the polarised part of healpy.alm2map([T,E,B]) at cora/util/hputil.py:419-423. */
 int cora_b200_alm2map_spin2(void* plan, const void* almE, const void* almB, int layout,
                             long long alm_stride, int nchan, double* mapQ, double* mapU,
                             void* workspace, long long ws_bytes, void* stream);
+
+int cora_b200_alm2map_spin2_strided(void* plan, const void* almE, const void* almB, int layout,
+                                    long long alm_stride, int nchan, double* mapQ, double* mapU,
+                                    long long map_stride, void* workspace, long long ws_bytes, void* stream);
 
 /* PANEL -> cora dense alm[chan][l][m] (complex128[nchan, L, L], zeros for m > l)
  * replaces: the layout mkfullsky(alms=True) returns (cora/core/skysim.py:108-125).     */
@@ -142,6 +152,17 @@ long long cora_b200_root_workspace_bytes(int nl, int nz);
 int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, double clip_rel,
                            double* root, int* used_eigh, int* num_pos, void* workspace,
                            long long ws_bytes, void* stream);
+
+/* Root of one diagonal block of a block-diagonal covariance (makesky gaussianfg --pol full builds
+ * blockdiag(T, E, B, V), cora/scripts/makesky.py:368-382): the jitter is jitter_rel * diag_max[l]
+ * with diag_max the maximum over the WHOLE matrix' diagonal (cora/core/skysim.py:116-117), given
+ * per l in `diag_max` (device float64[nl]; NULL = this block's own maximum).  The Cholesky /
+ * eigen decision and the eigenvalue clip act per block.  cora_b200_diag_max computes
+ * dmax[l] = max_i cl[l][i][i], merged (max) with the values already in dmax when merge != 0.   */
+int cora_b200_diag_max(const double* cl, int nl, int nz, double* dmax, int merge, void* stream);
+int cora_b200_root_batched_block(const double* cl, int nl, int nz, double jitter_rel, double clip_rel,
+                                 const double* diag_max, double* root, int* used_eigh, int* num_pos,
+                                 void* workspace, long long ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ draw + apply - */
 /* alm[nu, l, m] = sum_nu' M_l[nu, nu'] g_l[nu', m], written in PANEL layout.
@@ -233,12 +254,14 @@ int cora_b200_cl_fill_21cm_pairs(const double* tab, const double* chi, const dou
 /* draw + apply for the local l's with the exchange fused into the epilogue: element (l, m, nu)
  * is stored at nu_ptr[nu][idx(l, m) * nu_width[nu]] (complex elements), where nu_ptr[nu] (device
  * array [nz] of pointers) is the PANEL buffer of the GPU owning channel nu advanced to that
- * channel's column and nu_width[nu] that GPU's channel count.  Other arguments as
- * cora_b200_draw_apply.                                                                     */
+ * channel's column and nu_width[nu] that GPU's channel count.  draw_counter0 offsets the nu'
+ * word of the Philox counter (block b of a block-diagonal covariance draws with b * nz, so the
+ * blocks see independent streams -- the same draws as the dense (npol nz)^2 formulation).  Other
+ * arguments as cora_b200_draw_apply.                                                                     */
 int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
-                               int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
-                               const void* nu_ptr, const int* nu_width, void* workspace, long long ws_bytes,
-                               void* stream);
+                               int lmax, unsigned long long seed, int draw_counter0, const void* gauss,
+                               long long gauss_ld, const void* nu_ptr, const int* nu_width, void* workspace,
+                               long long ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

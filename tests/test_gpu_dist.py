@@ -211,3 +211,80 @@ def test_p2p_two_processes():
         for name in ("sck", "21cm"):
             a, b = got[r][name]
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-13 * np.abs(b).max())
+
+
+# --------------------------------------------------------------------------- polarised, block-sharded
+def _run_virtual_pol(nside, freq, size, partition, seed, steps=1):
+    import torch
+    from cora_b200 import dist as cdist
+    from cora_b200 import peer
+
+    lp = peer.LocalPeers(size)
+    shards = [cdist.ShardedPolSky(nside, freq, rank=r, size=size, partition=partition, peers=lp.view(r)) for r in range(size)]
+    out = None
+    for it in range(steps):
+        k = it & 1
+        for sh in shards:
+            sh.alm_phase(k, seed=seed + it)
+        torch.cuda.synchronize()
+        out = torch.cat([sh.sht_phase(k).clone() for sh in shards])
+    return out
+
+
+def test_pol_blocked_equals_dense_makesky():
+    """gaussianfg --pol full: the block formulation (T, E, B roots apart, Philox counters offset per
+    block, global jitter) reproduces the dense (4 nfreq)^2 formulation of makesky.py:368-387 on the
+    Cholesky branch (few channels), where both are defined without eigen-degeneracy freedom."""
+    from cora_b200 import makesky
+
+    fs = makesky.FreqState()
+    fs.freq = (800.0, 700.0, 4)
+    nside = 8
+    dense = makesky.make_gaussianfg(fs, nside, pol="full", seed=11, blocked=False)
+    blk = makesky.make_gaussianfg(fs, nside, pol="full", seed=11, blocked=True)
+    assert blk.shape == dense.shape == (4, 4, 12 * nside**2)
+    for p in range(3):
+        scale = np.abs(dense[:, p]).max()
+        assert np.max(np.abs(blk[:, p] - dense[:, p])) / scale < 1e-7, p   # own roots of ill-conditioned SCK blocks
+    assert np.all(blk[:, 3] == 0) and np.abs(dense[:, 3]).max() < 1e-4 * np.abs(dense[:, 0]).max()
+
+
+@pytest.mark.parametrize("size,partition", [(2, "interleaved"), (3, "block")])
+def test_pol_sharded_equals_single(size, partition):
+    nside, nz = 8, 7
+    freq = np.linspace(800.0, 600.0, nz, endpoint=False)
+    ref = _run_virtual_pol(nside, freq, 1, "interleaved", seed=4, steps=2).cpu().numpy()
+    got = _run_virtual_pol(nside, freq, size, partition, seed=4, steps=2).cpu().numpy()
+    assert got.shape == ref.shape == (nz, 4, 12 * nside**2)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13 * np.abs(ref).max())
+    assert np.abs(ref[:, 1]).max() > 0 and np.abs(ref[:, 2]).max() > 0
+
+
+def test_pol_blocked_eigen_branch_statistics():
+    """Many channels -> both blocks take the eigen branch.  T: the GPU anafast of the maps follows
+    C_l(nu, nu) within cosmic variance; Q/U: <Q^2 + U^2> follows sum (2l+1)/(4 pi) (C_EE + C_BB)
+    (dominated by l = 2..4, hence the wide band); V = 0."""
+    import torch
+    from cora_b200 import galaxy, hputil, skysim
+
+    nside, nz = 16, 24
+    freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+    sky_d = _run_virtual_pol(nside, freq, 1, "interleaved", seed=5)
+    sky = sky_d.cpu().numpy()
+    lmax = 3 * nside
+    la = 2 * nside
+    clT = skysim.clarray(galaxy.FullSkySynchrotron().angular_powerspectrum, lmax, freq)
+    alm = hputil.panel_to_dense(hputil.map2alm_device(sky_d[:, 0].contiguous(), nside, la, iter=3), la, nz).cpu().numpy()
+    l = np.arange(6, la + 1)
+    for i in (0, nz // 2, nz - 1):
+        prod = np.abs(alm[i]) ** 2
+        est = (prod[:, 0] + 2.0 * prod[:, 1:].sum(axis=1)) / (2.0 * np.arange(la + 1) + 1.0)
+        want = clT[l, i, i] * (2.0 * l + 0.5) / (2.0 * l + 1.0)
+        assert np.all(np.abs(est[l] - want) < 6.0 * want * np.sqrt(2.0 / (2.0 * l + 1.0))), i
+    clP = skysim.clarray(galaxy.FullSkyPolarisedSynchrotron().angular_powerspectrum, lmax, freq)
+    ll = np.arange(lmax + 1)
+    for i in (0, nz - 1):
+        var = 2 * np.sum(((2 * ll + 1) * clP[:, i, i])[2:]) / (4 * np.pi)
+        got = (sky[i, 1] ** 2 + sky[i, 2] ** 2).mean()
+        assert 0.25 < got / var < 4.0, (i, got / var)
+    assert np.all(sky[:, 3] == 0)
