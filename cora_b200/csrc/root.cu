@@ -231,6 +231,14 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int npl = nz + (nz & 1);          // players in the round-robin (pad to even)
     const int nsteps = npl - 1, npairs = npl / 2;
+    {   // an all-zero matrix (C_0 of the l^-beta foreground spectra) is already diagonal: skip the sweep
+        int nonzero = 0;
+        for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) nonzero |= (G[e] != 0.0);
+        if (!__syncthreads_or(nonzero)) {
+            if (threadIdx.x == 0) sweeps_out[blockIdx.x] = 0;
+            return;
+        }
+    }
     int sweep = 0;
     for (; sweep < max_sweeps; sweep++) {
         if (threadIdx.x == 0) s_rot = 0;

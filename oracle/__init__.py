@@ -17,4 +17,6 @@ algorithm, citing the reference ``file:line`` it follows.  Parity status:
   nor installable here, and the reference's tests hold no golden at that boundary:
   **parity unpinned**.  ``sht.py`` restates the published HEALPix RING synthesis and is
   validated analytically (scipy ``sph_harm_y`` direct sums, closed forms).
+* forward SHT (``sht.py: map2alm / anafast``; ``healpy.map2alm``): **parity unpinned** for the
+  same reason; pinned to the synthesis through the adjoint identity and a band-limited round trip.
 """
