@@ -276,35 +276,44 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
             for (int e0 = 0; e0 < npair; e0 += FILL_EB) {
                 const int ne = min(FILL_EB, npair - e0);
                 __syncthreads();   // previous batch fully consumed
-                // one x per thread, all sample pairs of the batch: the 6 * ne row reads are independent,
-                // so they are all in flight together (this phase is L2 / HBM latency bound)
-                for (int xi = tid; xi < W; xi += 256) {
+                // band rows R[el][x] = y-interpolated, coefficient-weighted table rows (L2 latency bound);
+                // items (sample pair, x) dealt evenly over the CTA: W is rarely a multiple of 256, and a
+                // per-x deal would leave most threads idle in its last pass
+                const int nitems = W * ne;
+#pragma unroll 4
+                for (int w = tid; w < nitems; w += 256) {
+                    const int el = w / W, xi = w - el * W;
                     const int x = xbase + xi;
-#pragma unroll 3
-                    for (int el = 0; el < ne; el++) {
-                        const PairPre p = pre[e0 + el];
-                        const double u0 = 1.0 - p.wy, u1 = p.wy;
-                        const double dd = u0 * __ldg(tab + tab_idx(0, p.y0, x)) + u1 * __ldg(tab + tab_idx(0, p.y1, x));
-                        const double dv = u0 * __ldg(tab + tab_idx(1, p.y0, x)) + u1 * __ldg(tab + tab_idx(1, p.y1, x));
-                        const double vv = u0 * __ldg(tab + tab_idx(2, p.y0, x)) + u1 * __ldg(tab + tab_idx(2, p.y1, x));
-                        R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
-                    }
+                    const PairPre p = pre[e0 + el];
+                    const double u0 = 1.0 - p.wy, u1 = p.wy;
+                    const double dd = u0 * __ldg(tab + tab_idx(0, p.y0, x)) + u1 * __ldg(tab + tab_idx(0, p.y1, x));
+                    const double dv = u0 * __ldg(tab + tab_idx(1, p.y0, x)) + u1 * __ldg(tab + tab_idx(1, p.y1, x));
+                    const double vv = u0 * __ldg(tab + tab_idx(2, p.y0, x)) + u1 * __ldg(tab + tab_idx(2, p.y1, x));
+                    R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
                 }
                 __syncthreads();
+                // x-interpolation of the band rows.  floor() through the 2^52 trick (three FP64 adds, no
+                // conversion instructions): rint(x - 1/2) equals floor(x) except at exact integers, where it
+                // may pick x - 1 with weight 1 -- the same interpolated value.
+                const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51
+                for (int el = 0; el < ne; el++) {
+                    const double sh = pre[e0 + el].shift;
+                    const double* Re = R + el * FILL_WMAX - xbase;
 #pragma unroll
-                for (int q = 0; q < FILL_LPT; q++) {
-                    if (lv[q] < 1) continue;
-                    double a = acc[q];
-                    for (int el = 0; el < ne; el++) {
-                        double x = (lx[q] - pre[e0 + el].shift) * xscale;
+                    for (int q = 0; q < FILL_LPT; q++) {
+                        double x = (lx[q] - sh) * xscale;
                         x = fmin(fmax(x, 0.0), xtopclip);
-                        const int x0 = (int)x;
-                        const double wx = x - (double)x0;
-                        const double* Rr = R + el * FILL_WMAX + (x0 - xbase);
-                        const int up = (x0 < NKPERP - 1) ? 1 : 0;
-                        a += (1.0 - wx) * Rr[0] + wx * Rr[up];
+                        const double tm = (x - 0.5) + MAGIC;
+                        const int x0 = __double2loint(tm);
+                        double wx = x - (tm - MAGIC);
+                        // x0 == xtop happens only on the table's last column (x clipped to NKPERP - 1e-5), where
+                        // both corners are that column: weight 1 on R[xtop].  Lanes without an l (lv < 1)
+                        // interpolate at a clamped in-band position and are discarded.
+                        if (x0 >= xtop) wx = 1.0;
+                        const int xs = min(max(x0, xbase), xtop - 1);
+                        const double r0 = Re[xs], r1 = Re[xs + 1];
+                        acc[q] += fma(wx, r1 - r0, r0);
                     }
-                    acc[q] = a;
                 }
             }
         } else {
