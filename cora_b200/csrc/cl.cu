@@ -292,28 +292,22 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
                     R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
                 }
                 __syncthreads();
-                // x-interpolation of the band rows.  floor() through the 2^52 trick (three FP64 adds, no
-                // conversion instructions): rint(x - 1/2) equals floor(x) except at exact integers, where it
-                // may pick x - 1 with weight 1 -- the same interpolated value.
-                const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51
-                for (int el = 0; el < ne; el++) {
-                    const double sh = pre[e0 + el].shift;
-                    const double* Re = R + el * FILL_WMAX - xbase;
+                // x-interpolation of the band rows (measured: a conversion-free floor and an el-outer /
+                // q-inner order are not faster than this form -- profiles/README.md)
 #pragma unroll
-                    for (int q = 0; q < FILL_LPT; q++) {
-                        double x = (lx[q] - sh) * xscale;
+                for (int q = 0; q < FILL_LPT; q++) {
+                    if (lv[q] < 1) continue;
+                    double a = acc[q];
+                    for (int el = 0; el < ne; el++) {
+                        double x = (lx[q] - pre[e0 + el].shift) * xscale;
                         x = fmin(fmax(x, 0.0), xtopclip);
-                        const double tm = (x - 0.5) + MAGIC;
-                        const int x0 = __double2loint(tm);
-                        double wx = x - (tm - MAGIC);
-                        // x0 == xtop happens only on the table's last column (x clipped to NKPERP - 1e-5), where
-                        // both corners are that column: weight 1 on R[xtop].  Lanes without an l (lv < 1)
-                        // interpolate at a clamped in-band position and are discarded.
-                        if (x0 >= xtop) wx = 1.0;
-                        const int xs = min(max(x0, xbase), xtop - 1);
-                        const double r0 = Re[xs], r1 = Re[xs + 1];
-                        acc[q] += fma(wx, r1 - r0, r0);
+                        const int x0 = (int)x;
+                        const double wx = x - (double)x0;
+                        const double* Rr = R + el * FILL_WMAX + (x0 - xbase);
+                        const int up = (x0 < NKPERP - 1) ? 1 : 0;
+                        a += (1.0 - wx) * Rr[0] + wx * Rr[up];
                     }
+                    acc[q] = a;
                 }
             }
         } else {
