@@ -50,6 +50,8 @@ SIGNATURES = {
     "cora_b200_alm_slabs_to_panel": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _vp]),
     "cora_b200_map2alm_workspace_bytes": (_ll, [_vp, _i]),
     "cora_b200_map2alm": (_i, [_vp, _vp, _i, _vp, _i, _vp, _ll, _i, _vp, _ll, _vp]),
+    "cora_b200_map2alm_spin2_workspace_bytes": (_ll, [_vp, _i]),
+    "cora_b200_map2alm_spin2": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _ll, _i, _vp, _ll, _vp]),
     "cora_b200_map_sub": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "cora_b200_peer_alloc": (_i, [_ll, _c.POINTER(_vp), _c.c_char_p]),
     "cora_b200_peer_free": (_i, [_vp]),

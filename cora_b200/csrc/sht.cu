@@ -1436,6 +1436,195 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdj
     }
 }
 
+
+// Spin-2 analysis: (Q, U) ring spectra -> (aE, aB), the Hermitian adjoint of sht_legendre_kernel<2>:
+//   aE = -sum_r (X1 Q_m + i X2 U_m),  aB = -sum_r (X1 U_m - i X2 Q_m)      (weights are in F)
+// GEMM form, 4 real columns per channel: C = X1^T B1 + X2^T B2 with B1 = -(Q_re, Q_im, U_re, U_im),
+// B2 = (U_im, -U_re, -Q_im, Q_re) = +-B1 at the mirrored column of the group of four; X2 has the
+// opposite theta-parity of X1, so it contracts with the other north/south combination.
+constexpr int ADJ2_RT = 256;      // north rings per CTA (one set of 32 per warp)
+constexpr int ADJ2_NCH = 4;       // channels per CTA (16 real columns)
+
+struct LegAdj2Params {
+    const double2 *FQ, *FU;   // [nring][ncg][L][4]
+    double2 *almE, *almB;     // PANEL
+    long long alm_stride;
+    int chan0, nb;
+    const double *cth, *sth;
+    const double* nm_mant;
+    const int* nm_exp;
+    const double2* rc;
+    int nside, lmax, nrn, nrb, ncb, ncg, accumulate;
+};
+
+__global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj2_kernel(LegAdj2Params P) {
+    extern __shared__ __align__(16) double smem[];
+    double* Bs = smem;                                   // [2 parities][RT][BLD]   (B1)
+    double* As = Bs + 2 * ADJ2_RT * ADJ_BLD;             // [8 warps][X1, X2][2 parities][8 l][ALD]
+    double* Cs = As + 8 * 2 * 2 * 8 * ADJ_ALD;           // [8 warps][256]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bid = blockIdx.x;
+    const int cb = bid % P.ncb; bid /= P.ncb;
+    const int rb = bid % P.nrb;
+    const int m = bid / P.nrb;
+    const int lmax = P.lmax, L = lmax + 1;
+    const int nk = lmax - m + 1;
+    const int nring_tot = 4 * P.nside - 1;
+
+    // ---- B1 tile
+    for (int el = tid; el < ADJ2_RT * ADJ2_NCH * 2; el += ADJ_THREADS) {
+        const int rr = el / (ADJ2_NCH * 2), c2 = el % (ADJ2_NCH * 2);
+        const int c = c2 >> 1, isU = c2 & 1;
+        const int rn = rb * ADJ2_RT + rr;
+        const int ch = cb * ADJ2_NCH + c;
+        double2 ev = make_double2(0.0, 0.0), od = ev;
+        if (rn < P.nrn && ch < P.nb) {
+            const double2* F = isU ? P.FU : P.FQ;
+            const int cg = ch >> 2, cc = ch & 3;
+            const double2 fn = F[(((long long)rn * P.ncg + cg) * L + m) * 4 + cc];
+            const int rs = nring_tot - 1 - rn;
+            if (rs != rn) {
+                const double2 fs = F[(((long long)rs * P.ncg + cg) * L + m) * 4 + cc];
+                ev = make_double2(fn.x + fs.x, fn.y + fs.y);
+                od = make_double2(fn.x - fs.x, fn.y - fs.y);
+            } else {
+                // equator: X1 vanishes for odd l - m (keep the even combination), X2 for even l - m
+                // (it contracts with the "odd" slot): both slots hold the ring itself
+                ev = fn; od = fn;
+            }
+        }
+        const int col = 4 * c + 2 * isU;
+        Bs[(size_t)rr * ADJ_BLD + col] = -ev.x;
+        Bs[(size_t)rr * ADJ_BLD + col + 1] = -ev.y;
+        Bs[(size_t)(ADJ2_RT + rr) * ADJ_BLD + col] = -od.x;
+        Bs[(size_t)(ADJ2_RT + rr) * ADJ_BLD + col + 1] = -od.y;
+    }
+
+    // ---- recurrence seed (one ring per lane)
+    double x = 0.0, p_cur = 0.0, p_prev = 0.0, is2 = 0.0, cs2 = 0.0;
+    int e = -(1 << 20);
+    {
+        const int rn = rb * ADJ2_RT + warp * 32 + lane;
+        if (rn < P.nrn) {
+            x = P.cth[rn];
+            double bm = P.sth[rn];
+            is2 = 1.0 / (bm * bm); cs2 = x * is2;
+            long long be = 0;
+            norm_frexp(bm, be);
+            double rm = 1.0;
+            long long re = 0;
+            int n = m;
+            while (n) {
+                if (n & 1) { rm *= bm; re += be; norm_frexp(rm, re); }
+                bm *= bm; be *= 2; norm_frexp(bm, be);
+                n >>= 1;
+            }
+            rm *= P.nm_mant[m];
+            re += P.nm_exp[m];
+            norm_frexp(rm, re);
+            if (m & 1) rm = -rm;
+            long long q = (re >= 0) ? 0 : -((-re) / 256);
+            e = (int)(q * 256);
+            p_cur = ldexp(rm, (int)(re - (long long)e));
+        }
+    }
+    __syncthreads();
+
+    const long long row0 = (long long)m * (2 * lmax + 1 - m) / 2 + m;
+    double* Aw = As + warp * (2 * 2 * 8 * ADJ_ALD);
+    const int gperm = (g & 4) + 3 - (g & 3);
+    const double gsign = ((g & 3) == 0 || (g & 3) == 3) ? -1.0 : 1.0;
+    const double mm = (double)m;
+    const int ngroups = (nk + 15) / 16;
+    for (int gi = 0; gi < ngroups; gi++) {
+        const int kbase = gi * 16;
+        double acc[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        // spin factors of the group's 16 l's: lane j < 16 computes those of l = m + kbase + j
+        double tn_l = 0.0, tg_l = 0.0;
+        {
+            const double l = (double)(m + kbase + (lane & 15));
+            if (kbase + (lane & 15) < nk && l >= 2.0) {
+                tn_l = 2.0 / sqrt((l + 2.0) * (l + 1.0) * l * (l - 1.0));
+                tg_l = tn_l * sqrt((2.0 * l + 1.0) / (2.0 * l - 1.0) * (l * l - mm * mm));
+            }
+        }
+        const bool live = (e == 0);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int k = kbase + j;
+            const double tn = __shfl_sync(0xffffffffu, tn_l, j), tg = __shfl_sync(0xffffffffu, tg_l, j);
+            const double l = (double)(m + k);
+            const double al = tn * (l - mm * mm), be = 0.5 * tn * l * (l - 1.0), de = tn * mm * (l - 1.0);
+            const double x1 = -(al * is2 + be) * p_cur + tg * cs2 * p_prev;
+            const double x2 = -de * cs2 * p_cur + mm * tg * is2 * p_prev;
+            const bool ok = live && k < nk;
+            const int arow = (j & 1) * 8 + (j >> 1);
+            Aw[arow * ADJ_ALD + lane] = ok ? x1 : 0.0;
+            Aw[(16 + arow) * ADJ_ALD + lane] = ok ? x2 : 0.0;
+            const double2 c = (k < nk) ? P.rc[row0 + k] : make_double2(0.0, 0.0);
+            const double pn = fma(c.x * x, p_cur, -c.y * p_prev);
+            p_prev = p_cur;
+            p_cur = pn;
+            if ((j & 7) == 7 && e < 0 && ((__double2hiint(p_cur) >> 20) & 0x7ff) > 1023 + 128) {
+                p_cur *= 0x1p-256;
+                p_prev *= 0x1p-256;
+                e += 256;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        __syncwarp();
+        if (bal) {
+            const int ring0 = warp * 32;
+#pragma unroll
+            for (int par = 0; par < 2; par++) {
+#pragma unroll
+                for (int jb = 0; jb < 8; jb++) {
+                    if (!((bal >> (4 * jb)) & 0xfu)) continue;
+                    const double a1 = Aw[(par * 8 + g) * ADJ_ALD + 4 * jb + t];
+                    const double a2 = Aw[(16 + par * 8 + g) * ADJ_ALD + 4 * jb + t];
+                    const double* b1row = Bs + (size_t)(par * ADJ2_RT + ring0 + 4 * jb + t) * ADJ_BLD;          // X1: same parity
+                    const double* b2row = Bs + (size_t)((par ^ 1) * ADJ2_RT + ring0 + 4 * jb + t) * ADJ_BLD;    // X2: opposite
+                    dmma884(acc[par][0][0], acc[par][0][1], a1, b1row[g]);
+                    dmma884(acc[par][1][0], acc[par][1][1], a1, b1row[8 + g]);
+                    dmma884(acc[par][0][0], acc[par][0][1], a2, gsign * b2row[gperm]);
+                    dmma884(acc[par][1][0], acc[par][1][1], a2, gsign * b2row[8 + gperm]);
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int par = 0; par < 2; par++)
+#pragma unroll
+            for (int nb = 0; nb < 2; nb++) {
+                Cs[warp * 256 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t] = acc[par][nb][0];
+                Cs[warp * 256 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t + 1] = acc[par][nb][1];
+            }
+        __syncthreads();
+        {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) v += Cs[w * 256 + tid];
+            const int c8 = tid & 7, gg = (tid >> 3) & 7, nb = (tid >> 6) & 1, par = tid >> 7;
+            const int k = kbase + 2 * gg + par;
+            const int col = nb * 8 + c8;                  // 4 * channel + (aE_re, aE_im, aB_re, aB_im)
+            const int ch = cb * ADJ2_NCH + (col >> 2);
+            if (k < nk && ch < P.nb) {
+                double2* base = (col & 2) ? P.almB : P.almE;
+                double* dst = (double*)(base + (row0 + k) * P.alm_stride + P.chan0 + ch) + (col & 1);
+                if (P.nrb > 1) atomicAdd(dst, v);
+                else if (P.accumulate) *dst += v;
+                else *dst = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // out = a - b  (residual map of the Jacobi refinement)
 __global__ void map_sub_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, double* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1892,5 +2081,76 @@ extern "C" int cora_b200_map_sub(const double* a, const double* b, long long n, 
     map_sub_kernel<<<(unsigned)std::min<long long>(ceil_div(n, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
     count_launch();
     CB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int run_ring_analysis(const ShtPlan* pl, const double* map, int nb, const double* ring_weights, double2* F, cudaStream_t st) {
+    KTimer kt(K_PHASE, st);
+    for (const auto& pc : pl->classes) {
+        AnaParams Q;
+        Q.map = map; Q.npix = pl->npix; Q.F = F; Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
+        Q.tw = pl->d_tw; Q.chirp = pl->d_chirp; Q.bhat = pl->d_bhat;
+        Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
+        Q.wring = ring_weights; Q.wscale = 4.0 * 3.14159265358979323846 / (double)pl->npix; Q.nside = pl->nside;
+        Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
+        dim3 grid(pc.nrings, Q.ncg * (2 / pc.P));
+        if (pc.threads == 256) sht_ring_analysis_kernel<256><<<grid, 256, phase_smem(pc), st>>>(Q);
+        else sht_ring_analysis_kernel<512><<<grid, 512, phase_smem(pc), st>>>(Q);
+        count_launch();
+        CB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" long long cora_b200_map2alm_spin2_workspace_bytes(void* plan, int nchan_batch) {
+    if (!plan) return -1;
+    const ShtPlan* pl = (const ShtPlan*)plan;
+    return 2 * (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16 * round4(nchan_batch) + 256;
+}
+
+extern "C" int cora_b200_map2alm_spin2(void* plan, const double* mapQ, const double* mapU, int nchan, const double* ring_weights,
+                                       int accumulate, void* almE_panel, void* almB_panel, long long panel_stride, int chan0,
+                                       void* workspace, long long ws_bytes, void* stream) {
+    CB_REQUIRE(plan && mapQ && mapU && almE_panel && almB_panel && workspace, 1, "map2alm_spin2: null argument");
+    CB_REQUIRE(nchan >= 1 && chan0 >= 0 && panel_stride >= chan0 + nchan, 1, "map2alm_spin2: bad sizes");
+    ShtPlan* pl = (ShtPlan*)plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long fbytes = (long long)(4 * pl->nside - 1) * (pl->lmax + 1) * 16;
+    long long cap = ((ws_bytes - 256) / (2 * fbytes)) & ~3LL;
+    CB_REQUIRE(cap >= 4, 4, "map2alm_spin2: workspace too small (%lld B; need %lld B per 4 channels)", ws_bytes, 8 * fbytes);
+    int nbmax = (int)std::min<long long>(cap, nchan);
+    if (nbmax < nchan && nbmax >= 8) nbmax -= nbmax % 8;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t smem = sizeof(double) * (2 * (size_t)ADJ2_RT * ADJ_BLD + 8 * 2 * 2 * 8 * ADJ_ALD + 8 * 256);
+    CB_CUDA(cudaFuncSetAttribute(sht_legendre_adj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int c0 = 0; c0 < nchan; c0 += nbmax) {
+        const int nb = std::min(nbmax, nchan - c0);
+        double2* FQ = (double2*)ws;
+        double2* FU = (double2*)(ws + fbytes * round4(nbmax));
+        int rc = run_ring_analysis(pl, mapQ + (long long)c0 * pl->npix, nb, ring_weights, FQ, st);
+        if (rc) return rc;
+        rc = run_ring_analysis(pl, mapU + (long long)c0 * pl->npix, nb, ring_weights, FU, st);
+        if (rc) return rc;
+        LegAdj2Params P;
+        P.FQ = FQ; P.FU = FU; P.almE = (double2*)almE_panel; P.almB = (double2*)almB_panel; P.alm_stride = panel_stride;
+        P.chan0 = chan0 + c0; P.nb = nb;
+        P.cth = pl->d_cth; P.sth = pl->d_sth; P.nm_mant = pl->d_nm_mant; P.nm_exp = pl->d_nm_exp; P.rc = pl->d_rc;
+        P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
+        P.nrb = ceil_div(pl->nrn, ADJ2_RT); P.ncb = ceil_div(nb, ADJ2_NCH); P.ncg = ceil_div(nb, 4);
+        P.accumulate = accumulate;
+        if (P.nrb > 1 && !accumulate) {
+            panel_zero_kernel<<<ceil_div(pl->nalm * nb, 256), 256, 0, st>>>((double2*)almE_panel, pl->nalm, panel_stride, chan0 + c0, nb);
+            panel_zero_kernel<<<ceil_div(pl->nalm * nb, 256), 256, 0, st>>>((double2*)almB_panel, pl->nalm, panel_stride, chan0 + c0, nb);
+            count_launch(2);
+            CB_LAUNCH_CHECK();
+        }
+        const long long grid = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
+        CB_REQUIRE(grid < 2147483647LL, 3, "map2alm_spin2: Legendre grid too large (%lld)", grid);
+        { KTimer kt(K_LEGENDRE, st); sht_legendre_adj2_kernel<<<(unsigned)grid, ADJ_THREADS, smem, st>>>(P); }
+        count_launch();
+        CB_LAUNCH_CHECK();
+    }
     return 0;
 }

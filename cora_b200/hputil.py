@@ -251,6 +251,44 @@ def map2alm_device(maps_dev, nside, lmax=None, iter=None, ring_weights=None, pan
     return panel
 
 
+def map2alm_spin2_device(mapQ_dev, mapU_dev, nside, lmax=None, iter=None, ring_weights=None):
+    """Batched polarised analysis on device: (Q, U) CUDA float64 ``[nchan, npix]`` -> PANEL
+    (aE, aB) ``complex128[nalm, nchan]``; quadrature pass + ``iter`` Jacobi refinements."""
+    t = _dev.torch()
+    nchan = int(mapQ_dev.shape[0])
+    lmax = 3 * nside - 1 if lmax is None else int(lmax)
+    iter = _iter if iter is None else int(iter)
+    plan = _dev.sht_plan(nside, lmax)
+    lib = _lib.load()
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    pE, pB = _dev.empty((nalm, nchan), t.complex128), _dev.empty((nalm, nchan), t.complex128)
+    rw = None
+    if ring_weights is not None:
+        rw = np.asarray(ring_weights, dtype=np.float64)
+        if rw.shape != (2 * nside,):
+            raise ValueError("ring_weights must have 2*nside entries")
+        rw = _dev.to_device(rw, t.float64)
+    need = max(lib.cora_b200_map2alm_spin2_workspace_bytes(plan, nchan), 2 * lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, nchan))
+    per16 = max(lib.cora_b200_map2alm_spin2_workspace_bytes(plan, 16), 2 * lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, 16))
+    nbytes = min(need, max(per16, _dev.free_bytes() - (2 << 30)))
+    ws = _dev.workspace(nbytes)
+
+    def analyse(q, u, accumulate):
+        _lib.call("cora_b200_map2alm_spin2", plan, _lib.ptr(q), _lib.ptr(u), nchan, _lib.ptr(rw), int(accumulate), _lib.ptr(pE),
+                  _lib.ptr(pB), nchan, 0, _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+
+    analyse(mapQ_dev, mapU_dev, 0)
+    if iter > 0:
+        rq, ru = _dev.empty(tuple(mapQ_dev.shape), t.float64), _dev.empty(tuple(mapU_dev.shape), t.float64)
+        for _ in range(iter):
+            _lib.call("cora_b200_alm2map_spin2", plan, _lib.ptr(pE), _lib.ptr(pB), _lib.ALM_PANEL, nchan, nchan, _lib.ptr(rq),
+                      _lib.ptr(ru), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+            _lib.call("cora_b200_map_sub", _lib.ptr(mapQ_dev), _lib.ptr(rq), int(rq.numel()), _lib.ptr(rq), _lib.stream_ptr())
+            _lib.call("cora_b200_map_sub", _lib.ptr(mapU_dev), _lib.ptr(ru), int(ru.numel()), _lib.ptr(ru), _lib.stream_ptr())
+            analyse(rq, ru, 1)
+    return pE, pB
+
+
 def _nside_of(npix):
     nside = int(round(np.sqrt(npix / 12.0)))
     if 12 * nside * nside != npix:
@@ -283,15 +321,53 @@ def sphtrans_complex(hpmap, lmax=None, centered=False, lside=None):
     return alm
 
 
+def _pol_analysis(maps, nside, lmax, ring_weights):
+    """maps: CUDA float64 [nfreq, npol (3 or 4), npix] -> dense alms CUDA complex128 [nfreq, npol, L, L]."""
+    t = _dev.torch()
+    nfreq, npol = int(maps.shape[0]), int(maps.shape[1])
+    L = lmax + 1
+    out = _dev.empty((nfreq, npol, L, L), t.complex128)
+    for p in ([0, 3] if npol == 4 else [0]):    # T (and V): scalar transforms
+        out[:, p] = panel_to_dense(map2alm_device(maps[:, p].contiguous(), nside, lmax, ring_weights=ring_weights), lmax, nfreq)
+    pE, pB = map2alm_spin2_device(maps[:, 1].contiguous(), maps[:, 2].contiguous(), nside, lmax, ring_weights=ring_weights)
+    out[:, 1] = panel_to_dense(pE, lmax, nfreq)
+    out[:, 2] = panel_to_dense(pB, lmax, nfreq)
+    return out
+
+
+def sphtrans_real_pol(hpmaps, lmax=None, lside=None, ring_weights=None):
+    """Transform of real T, Q, U (and optionally V) maps -> ``alms[npol, l, m]`` (T, E, B, V),
+    m >= 0 (``hputil.py:274-323``)."""
+    t = _dev.torch()
+    hpmaps = np.ascontiguousarray(hpmaps, dtype=np.float64)
+    npol = len(hpmaps)
+    if npol not in (3, 4):
+        raise Exception("hpmaps must hold 3 or 4 polarisations.")
+    nside = _nside_of(hpmaps[0].size)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    if lside is None or lside < lmax:
+        lside = lmax
+    dense = _pol_analysis(_dev.to_device(hpmaps[np.newaxis], t.float64), nside, lmax, ring_weights)[0].cpu().numpy()
+    alms = np.zeros([npol, lside + 1, lside + 1], dtype=np.complex128)
+    alms[:, : lmax + 1, : lmax + 1] = dense
+    return alms
+
+
 def sphtrans_sky(skymap, lmax=None, device_out=False, ring_weights=None):
     """Transform a 3-D sky map channel by channel (``hputil.py:460-497``), all channels batched.
 
-    ``skymap[freq, pixel]`` -> ``alms[freq, l, m]``.  The polarised branch of the reference
-    (``skymap[freq, pol >= 3, pixel]`` through ``healpy.map2alm([T, Q, U])``) needs the spin-2
-    analysis, which is not built yet: it raises ``NotImplementedError`` rather than fall back."""
+    ``skymap[freq, pixel]`` -> ``alms[freq, l, m]``; polarised if there are three dimensions and
+    3 or 4 polarisations: ``skymap[freq, pol, pixel]`` -> ``alms[freq, pol, l, m]`` (T, E, B, V)."""
     t = _dev.torch()
     if len(skymap.shape) == 3 and skymap.shape[1] >= 3:
-        raise NotImplementedError("polarised sphtrans_sky (spin-2 analysis) is not implemented in cora_b200 yet")
+        if skymap.shape[1] > 4:
+            raise Exception("skymap wrong shape.")
+        nside = _nside_of(skymap.shape[-1])
+        if lmax is None:
+            lmax = 3 * nside - 1
+        dense = _pol_analysis(_dev.to_device(skymap, t.float64), nside, lmax, ring_weights)
+        return dense if device_out else _dev.to_host(dense)
     if len(skymap.shape) == 3:
         raise Exception("skymap wrong shape.")   # [freq, pol < 3, pix]: the reference hands a 2-D block to healpy and fails there
     nside = _nside_of(skymap.shape[-1])

@@ -218,6 +218,14 @@ long long cora_b200_map2alm_workspace_bytes(void* plan, int nchan_batch);
 int cora_b200_map2alm(void* plan, const double* map, int nchan, const double* ring_weights, int accumulate,
                       void* alm_panel, long long panel_stride, int chan0, void* workspace, long long ws_bytes,
                       void* stream);
+/* Polarised analysis (Q, U) -> (aE, aB), the adjoint of cora_b200_alm2map_spin2 times 4 pi / npix:
+ *   aE = -sum_r w (X1 Q_m + i X2 U_m),  aB = -sum_r w (X1 U_m - i X2 Q_m).
+ * replaces: the E/B part of healpy.map2alm([T, Q, U]) at cora/util/hputil.py:310-312
+ * (sphtrans_real_pol); T and V go through cora_b200_map2alm.                                   */
+long long cora_b200_map2alm_spin2_workspace_bytes(void* plan, int nchan_batch);
+int cora_b200_map2alm_spin2(void* plan, const double* mapQ, const double* mapU, int nchan,
+                            const double* ring_weights, int accumulate, void* almE_panel, void* almB_panel,
+                            long long panel_stride, int chan0, void* workspace, long long ws_bytes, void* stream);
 /* out[i] = a[i] - b[i], i < n (the residual map of the refinement) */
 int cora_b200_map_sub(const double* a, const double* b, long long n, double* out, void* stream);
 

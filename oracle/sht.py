@@ -328,3 +328,59 @@ def anafast(map1, map2=None, lmax=None, iter=3, ring_weights=None):
         p = (a1[..., sl] * np.conj(a2[..., sl])).real
         cl[m:] += (1.0 if m == 0 else 2.0) * p
     return cl / (2.0 * np.arange(lmax + 1) + 1.0)
+
+
+# ------------------------------------------------------------------- spin-2 analysis
+def _spin2_X(lmax, m, c, s):
+    """X1, X2 of SURVEY App. A.9 for l = m..lmax at every ring, shapes (nl, nring)."""
+    nring = c.shape[0]
+    s2 = s * s
+    lam = lambda_lm(lmax, m, c, s)
+    l = np.arange(m, lmax + 1, dtype=np.float64)
+    lam_prev = np.vstack([np.zeros((1, nring)), lam[:-1]])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nl = np.where(l >= 2, 1.0 / np.sqrt((l + 2) * (l + 1) * l * (l - 1)), 0.0)
+    glm = np.sqrt((2 * l + 1) / np.maximum(2 * l - 1, 1.0) * (l * l - m * m))
+    X1 = (2 * nl)[:, None] * (
+        -((l - m * m)[:, None] / s2[None, :] + (l * (l - 1) / 2)[:, None]) * lam + (c / s2)[None, :] * glm[:, None] * lam_prev
+    )
+    X2 = (2 * nl)[:, None] * (m / s2)[None, :] * (-(l - 1)[:, None] * c[None, :] * lam + glm[:, None] * lam_prev)
+    return X1, X2
+
+
+def map2alm_spin2_adjoint(Q, U, nside, lmax, ring_weights=None):
+    """One quadrature pass of the polarised analysis, the Hermitian adjoint of ``alm2map_spin2``
+    times 4 pi / npix:  ``aE = -sum_r w (X1 Q_m + i X2 U_m)``, ``aB = -sum_r w (X1 U_m - i X2 Q_m)``
+    (``healpy.map2alm([T, Q, U])`` at ``cora/util/hputil.py:310-312``, E and B parts)."""
+    Q = np.atleast_2d(np.asarray(Q, dtype=np.float64))
+    U = np.atleast_2d(np.asarray(U, dtype=np.float64))
+    g = ring_geometry(nside)
+    nring = 4 * nside - 1
+    w = _full_ring_weights(nside, ring_weights)
+    rs = np.arange(nring)
+    FQ = _phase_from_rings(Q, g, rs, lmax, w)
+    FU = _phase_from_rings(U, g, rs, lmax, w)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    aE = np.zeros((Q.shape[0], nalm), dtype=np.complex128)
+    aB = np.zeros_like(aE)
+    for m in range(lmax + 1):
+        X1, X2 = _spin2_X(lmax, m, g["cth"], g["sth"])
+        sl = slice(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1)
+        aE[:, sl] = -(X1 @ FQ[m] + 1j * (X2 @ FU[m])).T
+        aB[:, sl] = -(X1 @ FU[m] - 1j * (X2 @ FQ[m])).T
+    return aE, aB
+
+
+def map2alm_spin2(Q, U, nside, lmax=None, iter=3, ring_weights=None):
+    """(Q, U) -> (aE, aB): quadrature + ``iter`` Jacobi refinements, as ``healpy.map2alm`` does."""
+    Q = np.atleast_2d(np.asarray(Q, dtype=np.float64))
+    U = np.atleast_2d(np.asarray(U, dtype=np.float64))
+    if lmax is None:
+        lmax = 3 * nside - 1
+    aE, aB = map2alm_spin2_adjoint(Q, U, nside, lmax, ring_weights)
+    for _ in range(iter):
+        q, u = alm2map_spin2(aE, aB, nside, lmax)
+        dE, dB = map2alm_spin2_adjoint(Q - q, U - u, nside, lmax, ring_weights)
+        aE += dE
+        aB += dB
+    return aE, aB

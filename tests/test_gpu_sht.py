@@ -241,8 +241,8 @@ def test_sphtrans_real_sky_and_sph_ps_vs_oracle():
     assert _relerr(hputil.pack_alm(alms[1]), osht.map2alm(sky[1], nside, lmax, iter=2)) < 1e-11
     cl = hputil.sph_ps(m)
     assert _relerr(cl, osht.anafast(m, lmax=lmax, iter=2)) < 1e-10
-    with pytest.raises(NotImplementedError):
-        hputil.sphtrans_sky(np.zeros((2, 4, 12 * nside**2)))
+    with pytest.raises(Exception, match="wrong shape"):
+        hputil.sphtrans_sky(np.zeros((2, 2, 12 * nside**2)))
     with pytest.raises(ValueError):
         hputil.sphtrans_real(np.zeros(100))
 
@@ -272,3 +272,63 @@ def test_mkfullsky_reproduces_cl_via_anafast():
             assert np.all(np.abs(est[l] - want) < 6.0 * sig), (i, j)
             # and on average over l the estimator is unbiased at the few-percent level
             assert abs(np.mean((est[l] - want) / sig)) < 0.5
+
+
+# ------------------------------------------------------------------ polarised analysis
+@pytest.mark.parametrize("nside,lmax,nchan", [(2, 5, 1), (4, 11, 5), (8, 23, 3), (8, 14, 9), (16, 47, 2), (6, 17, 4)])
+def test_map2alm_spin2_pass_vs_oracle(nside, lmax, nchan):
+    import torch
+    from cora_b200 import hputil
+
+    rng = np.random.default_rng(nside * 31 + lmax)
+    Q, U = rng.standard_normal((2, nchan, 12 * nside**2))
+    pE, pB = hputil.map2alm_spin2_device(torch.from_numpy(Q).cuda(), torch.from_numpy(U).cuda(), nside, lmax, iter=0)
+    rE, rB = osht.map2alm_spin2_adjoint(Q, U, nside, lmax)
+    scale = max(np.abs(rE).max(), np.abs(rB).max())
+    assert np.abs(_panel_to_packed(pE) - rE).max() / scale < 1e-12
+    assert np.abs(_panel_to_packed(pB) - rB).max() / scale < 1e-12
+
+
+def test_sphtrans_real_pol_and_sky_vs_oracle():
+    from cora_b200 import hputil
+
+    rng = np.random.default_rng(21)
+    nside = 8
+    lmax = 3 * nside - 1
+    maps = rng.standard_normal((4, 12 * nside**2))
+    alms = hputil.sphtrans_real_pol(maps)
+    assert alms.shape == (4, lmax + 1, lmax + 1)
+    rE, rB = osht.map2alm_spin2(maps[1], maps[2], nside, lmax, iter=2)
+    assert _relerr(hputil.pack_alm(alms[0]), osht.map2alm(maps[0], nside, lmax, iter=2)) < 1e-11
+    assert _relerr(hputil.pack_alm(alms[3]), osht.map2alm(maps[3], nside, lmax, iter=2)) < 1e-11
+    scale = max(np.abs(rE).max(), np.abs(rB).max())
+    assert np.abs(hputil.pack_alm(alms[1]) - rE[0]).max() / scale < 1e-11
+    assert np.abs(hputil.pack_alm(alms[2]) - rB[0]).max() / scale < 1e-11
+    sky = rng.standard_normal((2, 3, 12 * nside**2))
+    a = hputil.sphtrans_sky(sky, lmax=12)
+    assert a.shape == (2, 3, 13, 13)
+    rE, rB = osht.map2alm_spin2(sky[1, 1], sky[1, 2], nside, 12, iter=2)
+    assert np.abs(hputil.pack_alm(a[1, 1]) - rE[0]).max() / np.abs(rE).max() < 1e-11
+    with pytest.raises(Exception):
+        hputil.sphtrans_real_pol(maps[:2])
+
+
+def test_pol_roundtrip_band_limited_gpu():
+    """alm (T,E,B) -> maps (GPU synthesis) -> alm (GPU analysis, iter=3) for a band-limited field."""
+    from cora_b200 import hputil
+
+    rng = np.random.default_rng(22)
+    nside, lmax = 16, 20
+    L = lmax + 1
+    alm = np.zeros((1, 3, L, L), dtype=np.complex128)
+    for l in range(2, L):
+        alm[0, :, l, : l + 1] = rng.standard_normal((3, l + 1)) + 1j * rng.standard_normal((3, l + 1))
+        alm[0, :, l, 0] = alm[0, :, l, 0].real
+    sky = hputil.sphtrans_inv_sky(alm, nside)
+    old = hputil._iter
+    try:
+        hputil._iter = 3
+        back = hputil.sphtrans_sky(sky, lmax=lmax)
+    finally:
+        hputil._iter = old
+    assert np.abs(back - alm).max() / np.abs(alm).max() < 2e-3

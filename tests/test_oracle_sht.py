@@ -215,3 +215,42 @@ def test_anafast_recovers_spectrum():
     est = sht.anafast(sht.alm2map(a, nside, lmax), lmax=lmax, iter=3)
     l = np.arange(2, lmax + 1)
     assert np.all(np.abs(est[l] - cl[l]) < 6 * cl[l] * np.sqrt(2.0 / (2 * l + 1)))
+
+
+@pytest.mark.parametrize("nside,lmax", [(4, 11), (8, 17)])
+def test_map2alm_spin2_adjoint_identity(nside, lmax):
+    """<(Q,U), S2(aE,aB)> 4 pi/npix = sum_lm w_m Re(conj(aE) AE + conj(aB) AB): the polarised
+    quadrature pass is the adjoint of the (closed-form validated) spin-2 synthesis."""
+    rng = np.random.default_rng(8)
+    npix = 12 * nside**2
+    Q, U = rng.standard_normal((2, 2, npix))
+    aE, aB = _rand_packed(rng, lmax, 2), _rand_packed(rng, lmax, 2)
+    for a in (aE, aB):   # l < 2 carries no spin-2 power
+        for mm in range(2):
+            for ll in range(mm, 2):
+                a[:, sht.alm_index(lmax, ll, mm)] = 0
+    AE, AB = sht.map2alm_spin2_adjoint(Q, U, nside, lmax)
+    q, u = sht.alm2map_spin2(aE, aB, nside, lmax)
+    lhs = ((Q * q).sum(axis=1) + (U * u).sum(axis=1)) * 4.0 * np.pi / npix
+    w = np.full(aE.shape[1], 2.0)
+    w[: lmax + 1] = 1.0
+    rhs = (w * ((np.conj(aE) * AE).real + (np.conj(aB) * AB).real)).sum(axis=1)
+    np.testing.assert_allclose(lhs, rhs, rtol=1e-11)
+    # l = 0, 1 rows of the analysis are identically zero
+    for mm in range(2):
+        for ll in range(mm, 2):
+            assert np.all(AE[:, sht.alm_index(lmax, ll, mm)] == 0) and np.all(AB[:, sht.alm_index(lmax, ll, mm)] == 0)
+
+
+def test_map2alm_spin2_roundtrip():
+    rng = np.random.default_rng(9)
+    nside, lmax = 8, 12
+    aE, aB = _rand_packed(rng, lmax, 1), _rand_packed(rng, lmax, 1)
+    for a in (aE, aB):
+        for mm in range(2):
+            for ll in range(mm, 2):
+                a[:, sht.alm_index(lmax, ll, mm)] = 0
+    q, u = sht.alm2map_spin2(aE, aB, nside, lmax)
+    e0 = max(np.abs(x - y).max() for x, y in zip(sht.map2alm_spin2(q, u, nside, lmax, iter=0), (aE, aB)))
+    e4 = max(np.abs(x - y).max() for x, y in zip(sht.map2alm_spin2(q, u, nside, lmax, iter=4), (aE, aB)))
+    assert e0 < 0.2 and e4 < e0 * 1e-2
