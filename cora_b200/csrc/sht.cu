@@ -1275,11 +1275,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_ring_anal
 }
 
 constexpr int ADJ_THREADS = 256;
-constexpr int ADJ_RPL = 2;                   // ring sets (of 32) per warp
+constexpr int ADJ_RPL = 1;                   // ring sets (of 32) per warp
 constexpr int ADJ_RT = 32 * 8 * ADJ_RPL;     // north rings per CTA
 constexpr int ADJ_NCH = 8;                   // complex channels per CTA (16 real columns)
-constexpr int ADJ_BLD = 20;                  // Bs[ring][20]: (t * 20 + g) conflict-free per half-warp
+constexpr int ADJ_BLD = 16;                  // Bs[ring][16], column c stored at c ^ 4 (ring & 3): fragment reads conflict-free
 constexpr int ADJ_ALD = 36;                  // As[row][36]:  (g * 36 + t)
+// shared memory: B 64 KB + A 36.9 KB (the C staging of the cross-warp reduction aliases the A tiles)
+// = 101 KB -> two CTAs per SM, so one CTA's recurrence / barrier phases overlap the other's DMMAs
+__device__ __forceinline__ int adj_bcol(int ring, int col) { return col ^ ((ring & 3) << 2); }
 
 struct LegAdjParams {
     const double2* F;         // [nring][ncg][L][4]
@@ -1293,11 +1296,11 @@ struct LegAdjParams {
     int nside, lmax, nrn, nrb, ncb, ncg, accumulate;
 };
 
-__global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdjParams P) {
+__global__ void __launch_bounds__(ADJ_THREADS, 2) sht_legendre_adj_kernel(LegAdjParams P) {
     extern __shared__ __align__(16) double smem[];
     double* Bs = smem;                                  // [2 parities][RT][BLD]
-    double* As = Bs + 2 * ADJ_RT * ADJ_BLD;             // [8 warps][2 parities][8 l][ALD]
-    double* Cs = As + 8 * 2 * 8 * ADJ_ALD;              // [8 warps][256]
+    double* As = Bs + 2 * ADJ_RT * ADJ_BLD;             // [8 warps][2 parities][8 l][ALD]  (576 doubles per warp)
+    double* Cs = As;                                    // [8 warps][256] staged in each warp's own A tile after its DMMAs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     int bid = blockIdx.x;
@@ -1326,10 +1329,10 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdj
                 ev = fn;   // equator: lambda vanishes for odd l - m
             }
         }
-        Bs[(size_t)rr * ADJ_BLD + 2 * c] = ev.x;
-        Bs[(size_t)rr * ADJ_BLD + 2 * c + 1] = ev.y;
-        Bs[(size_t)(ADJ_RT + rr) * ADJ_BLD + 2 * c] = od.x;
-        Bs[(size_t)(ADJ_RT + rr) * ADJ_BLD + 2 * c + 1] = od.y;
+        Bs[(size_t)rr * ADJ_BLD + adj_bcol(rr, 2 * c)] = ev.x;
+        Bs[(size_t)rr * ADJ_BLD + adj_bcol(rr, 2 * c + 1)] = ev.y;
+        Bs[(size_t)(ADJ_RT + rr) * ADJ_BLD + adj_bcol(rr, 2 * c)] = od.x;
+        Bs[(size_t)(ADJ_RT + rr) * ADJ_BLD + adj_bcol(rr, 2 * c + 1)] = od.y;
     }
 
     // ---- recurrence seeds: lane owns ring (set s, lane) of the warp's ADJ_RPL sets
@@ -1401,8 +1404,8 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdj
                         if (!((bal >> (4 * jb)) & 0xfu)) continue;   // four dead rings: nothing to add
                         const double af = Aw[(par * 8 + g) * ADJ_ALD + 4 * jb + t];
                         const double* brow = Bs + (size_t)(par * ADJ_RT + ring0 + 4 * jb + t) * ADJ_BLD;
-                        dmma884(acc[par][0][0], acc[par][0][1], af, brow[g]);
-                        dmma884(acc[par][1][0], acc[par][1][1], af, brow[8 + g]);
+                        dmma884(acc[par][0][0], acc[par][0][1], af, brow[g ^ (t << 2)]);          // ring & 3 == t
+                        dmma884(acc[par][1][0], acc[par][1][1], af, brow[(8 + g) ^ (t << 2)]);
                     }
                 }
             }
@@ -1413,14 +1416,14 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdj
         for (int par = 0; par < 2; par++)
 #pragma unroll
             for (int nb = 0; nb < 2; nb++) {
-                Cs[warp * 256 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t] = acc[par][nb][0];
-                Cs[warp * 256 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t + 1] = acc[par][nb][1];
+                Cs[warp * 576 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t] = acc[par][nb][0];
+                Cs[warp * 576 + ((par * 2 + nb) * 8 + g) * 8 + 2 * t + 1] = acc[par][nb][1];
             }
         __syncthreads();
         {
             double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) v += Cs[w * 256 + tid];
+            for (int w = 0; w < 8; w++) v += Cs[w * 576 + tid];
             const int c8 = tid & 7, gg = (tid >> 3) & 7, nb = (tid >> 6) & 1, par = tid >> 7;
             const int k = kbase + 2 * gg + par;
             const int col = nb * 8 + c8;
@@ -1444,6 +1447,7 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj_kernel(LegAdj
 // opposite theta-parity of X1, so it contracts with the other north/south combination.
 constexpr int ADJ2_RT = 256;      // north rings per CTA (one set of 32 per warp)
 constexpr int ADJ2_NCH = 4;       // channels per CTA (16 real columns)
+constexpr int ADJ2_BLD = 20;      // Bs[ring][20]: (t * 20 + g) conflict-free per half-warp
 
 struct LegAdj2Params {
     const double2 *FQ, *FU;   // [nring][ncg][L][4]
@@ -1460,7 +1464,7 @@ struct LegAdj2Params {
 __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj2_kernel(LegAdj2Params P) {
     extern __shared__ __align__(16) double smem[];
     double* Bs = smem;                                   // [2 parities][RT][BLD]   (B1)
-    double* As = Bs + 2 * ADJ2_RT * ADJ_BLD;             // [8 warps][X1, X2][2 parities][8 l][ALD]
+    double* As = Bs + 2 * ADJ2_RT * ADJ2_BLD;             // [8 warps][X1, X2][2 parities][8 l][ALD]
     double* Cs = As + 8 * 2 * 2 * 8 * ADJ_ALD;           // [8 warps][256]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -1495,10 +1499,10 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj2_kernel(LegAd
             }
         }
         const int col = 4 * c + 2 * isU;
-        Bs[(size_t)rr * ADJ_BLD + col] = -ev.x;
-        Bs[(size_t)rr * ADJ_BLD + col + 1] = -ev.y;
-        Bs[(size_t)(ADJ2_RT + rr) * ADJ_BLD + col] = -od.x;
-        Bs[(size_t)(ADJ2_RT + rr) * ADJ_BLD + col + 1] = -od.y;
+        Bs[(size_t)rr * ADJ2_BLD + col] = -ev.x;
+        Bs[(size_t)rr * ADJ2_BLD + col + 1] = -ev.y;
+        Bs[(size_t)(ADJ2_RT + rr) * ADJ2_BLD + col] = -od.x;
+        Bs[(size_t)(ADJ2_RT + rr) * ADJ2_BLD + col + 1] = -od.y;
     }
 
     // ---- recurrence seed (one ring per lane)
@@ -1587,8 +1591,8 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) sht_legendre_adj2_kernel(LegAd
                     if (!((bal >> (4 * jb)) & 0xfu)) continue;
                     const double a1 = Aw[(par * 8 + g) * ADJ_ALD + 4 * jb + t];
                     const double a2 = Aw[(16 + par * 8 + g) * ADJ_ALD + 4 * jb + t];
-                    const double* b1row = Bs + (size_t)(par * ADJ2_RT + ring0 + 4 * jb + t) * ADJ_BLD;          // X1: same parity
-                    const double* b2row = Bs + (size_t)((par ^ 1) * ADJ2_RT + ring0 + 4 * jb + t) * ADJ_BLD;    // X2: opposite
+                    const double* b1row = Bs + (size_t)(par * ADJ2_RT + ring0 + 4 * jb + t) * ADJ2_BLD;          // X1: same parity
+                    const double* b2row = Bs + (size_t)((par ^ 1) * ADJ2_RT + ring0 + 4 * jb + t) * ADJ2_BLD;    // X2: opposite
                     dmma884(acc[par][0][0], acc[par][0][1], a1, b1row[g]);
                     dmma884(acc[par][1][0], acc[par][1][1], a1, b1row[8 + g]);
                     dmma884(acc[par][0][0], acc[par][0][1], a2, gsign * b2row[gperm]);
@@ -2033,7 +2037,7 @@ extern "C" int cora_b200_map2alm(void* plan, const double* map, int nchan, const
     int nbmax = (int)std::min<long long>(cap, nchan);
     if (nbmax < nchan && nbmax >= 8) nbmax -= nbmax % 8;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const size_t adj_smem = sizeof(double) * (2 * (size_t)ADJ_RT * ADJ_BLD + 8 * 2 * 8 * ADJ_ALD + 8 * 256);
+    const size_t adj_smem = sizeof(double) * (2 * (size_t)ADJ_RT * ADJ_BLD + 8 * 2 * 8 * ADJ_ALD);
     CB_CUDA(cudaFuncSetAttribute(sht_legendre_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
     CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2121,7 +2125,7 @@ extern "C" int cora_b200_map2alm_spin2(void* plan, const double* mapQ, const dou
     int nbmax = (int)std::min<long long>(cap, nchan);
     if (nbmax < nchan && nbmax >= 8) nbmax -= nbmax % 8;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const size_t smem = sizeof(double) * (2 * (size_t)ADJ2_RT * ADJ_BLD + 8 * 2 * 2 * 8 * ADJ_ALD + 8 * 256);
+    const size_t smem = sizeof(double) * (2 * (size_t)ADJ2_RT * ADJ2_BLD + 8 * 2 * 2 * 8 * ADJ_ALD + 8 * 256);
     CB_CUDA(cudaFuncSetAttribute(sht_legendre_adj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CB_CUDA(cudaFuncSetAttribute(sht_ring_analysis_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

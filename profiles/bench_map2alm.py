@@ -46,4 +46,23 @@ out["legendre_adj_tflops"] = flops / (leg * 1e-3) / 1e12
 out["dmma_peak_tflops"] = peak[0]
 out["frac"] = out["legendre_adj_tflops"] / peak[0]
 out["shape"] = {"nside": nside, "lmax": lmax, "nchan": nchan}
+# polarised analysis (Q, U) -> (aE, aB), quadrature pass
+lib.cora_b200_timing_enable(0)
+Q, U = maps[: nchan // 2].contiguous(), maps[nchan // 2 :].contiguous()
+hputil.map2alm_spin2_device(Q, U, nside, lmax, iter=0)
+torch.cuda.synchronize()
+e0.record()
+hputil.map2alm_spin2_device(Q, U, nside, lmax, iter=0)
+e1.record()
+torch.cuda.synchronize()
+out["spin2_iter0_ms_%dch" % (nchan // 2)] = e0.elapsed_time(e1)
+# CPU side by side: the oracle's quadrature pass (numpy, one process) on 2 channels, scaled to nchan
+if os.environ.get("CPU", "1") == "1":
+    import time
+    from oracle import sht as osht
+    sub = maps[:2].cpu().numpy()
+    t0 = time.time()
+    osht.map2alm_adjoint(sub, nside, lmax)
+    out["cpu_oracle_iter0_s_extrapolated"] = (time.time() - t0) * nchan / 2.0
+    out["cpu_note"] = "oracle/sht.py map2alm_adjoint on 2 channels x nchan/2 (numpy; restatement, not healpy)"
 print(json.dumps(out))
