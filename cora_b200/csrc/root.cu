@@ -34,8 +34,11 @@ __global__ void root_prepare_kernel(const double* __restrict__ cl, int nz, doubl
     // dmax_in: the diagonal maximum of a larger (block-diagonal) matrix this one is a block of
     const double dm = dmax_in ? dmax_in[blockIdx.x] : red[0];
     const double cmax = dm * jitter_rel;
-    if (threadIdx.x == 0) dmax_out[blockIdx.x] = dm;
-    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
+    if (threadIdx.x == 0 && blockIdx.y == 0) dmax_out[blockIdx.x] = dm;
+    // the copy is split over gridDim.y CTAs per matrix (each recomputes the cheap diagonal maximum)
+    const long long n2 = (long long)nz * nz;
+    const long long e0 = n2 * blockIdx.y / gridDim.y, e1 = n2 * (blockIdx.y + 1) / gridDim.y;
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int r = (int)(e / nz), c = (int)(e % nz);
         double v = 0.0;
         if (c <= r) v = cl[base + e] + (r == c ? cmax : 0.0);
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restr
     double* stage = ch_smem;                              // [2][CH_STAGE]
     double (*Ld)[CH_NB + 1] = (double (*)[CH_NB + 1])(ch_smem + 2 * CH_STAGE);   // diagonal block
     __shared__ int s_fail;
+    __shared__ double Linv[CH_NB];                        // reciprocals of the diagonal block's pivots
     double* A = root + (long long)blockIdx.x * nz * nz;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -146,23 +150,40 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restr
         }
         __syncthreads();
         if (warp == 0) {
-            for (int jj = 0; jj < nbk; jj++) {
-                const double d = Ld[jj][jj];
-                if (!(d > 0.0)) {   // same value in every lane: uniform exit
-                    if (lane == 0) s_fail = 1;
-                    break;
+            // lane = row, the row lives in registers; column jj of L is broadcast by shuffles
+            // (no shared-memory read-modify-write chain: that loop was 60 % of a 256^2 factorisation)
+            double r[CH_NB];
+#pragma unroll
+            for (int c = 0; c < CH_NB; c++) r[c] = Ld[lane][c];
+            bool bad = false;
+            double myinv = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < CH_NB; jj++) {
+                const double d = __shfl_sync(0xffffffffu, r[jj], jj);
+                if (jj < nbk && !bad) {                       // warp-uniform
+                    if (!(d > 0.0)) {
+                        bad = true;
+                    } else {
+                        // one reciprocal square root per pivot (the divide and the square root are each a
+                        // ~250-cycle software sequence on the critical path of all 32 pivots)
+                        const double dinv = rsqrt(d);
+                        const double dj = d * dinv;
+                        double lij = r[jj] * dinv;            // rows above jj hold 0 here and stay 0
+                        if (lane == jj) { lij = dj; myinv = dinv; }
+                        r[jj] = lij;
+#pragma unroll
+                        for (int c = jj + 1; c < CH_NB; c++) {
+                            const double lc = __shfl_sync(0xffffffffu, lij, c);   // L[c][jj]
+                            r[c] -= lij * lc;                 // meaningful for lane >= c (lower triangle)
+                        }
+                    }
                 }
-                const double dj = sqrt(d);
-                __syncwarp();
-                if (lane == jj) Ld[jj][jj] = dj;
-                double lij = 0.0;
-                if (lane > jj && lane < nbk) { lij = Ld[lane][jj] / dj; Ld[lane][jj] = lij; }
-                __syncwarp();
-                // row `lane` of the trailing block: A[lane][c] -= L[lane][jj] L[c][jj], jj < c <= lane
-                if (lane > jj && lane < nbk)
-                    for (int c = jj + 1; c <= lane; c++) Ld[lane][c] -= lij * Ld[c][jj];
-                __syncwarp();
             }
+            if (bad && lane == 0) s_fail = 1;
+#pragma unroll
+            for (int c = 0; c < CH_NB; c++)
+                if (c <= lane) Ld[lane][c] = r[c];
+            Linv[lane] = myinv;
         }
         __syncthreads();
         if (s_fail) break;
@@ -170,25 +191,26 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restr
             const int rr = e >> 5, cc = e & 31;
             if (rr < nbk && cc <= rr) A[(long long)(kb + rr) * nz + kb + cc] = Ld[rr][cc];
         }
-        // ---- (3) triangular solve for the rows below: X L_kk^T = B, one row per thread
+        // ---- (3) triangular solve for the rows below: X L_kk^T = B, one row per thread, right-looking
+        // (every finished x_p updates all later columns at once: independent FMAs instead of one
+        // dependent chain per column; the pivots enter through their reciprocals)
         for (int r = kb + nbk + tid; r < nz; r += CH_THREADS) {
             double* Ar = A + (long long)r * nz + kb;
-            double xrow[CH_NB];
+            double v[CH_NB];
 #pragma unroll
-            for (int cc = 0; cc < CH_NB; cc++) xrow[cc] = (cc < nbk) ? Ar[cc] : 0.0;
+            for (int cc = 0; cc < CH_NB; cc++) v[cc] = (cc < nbk) ? Ar[cc] : 0.0;
 #pragma unroll
-            for (int cc = 0; cc < CH_NB; cc++) {
-                if (cc < nbk) {
-                    double v = xrow[cc];
+            for (int pp = 0; pp < CH_NB; pp++) {
+                if (pp < nbk) {
+                    const double xp = v[pp] * Linv[pp];
+                    v[pp] = xp;
 #pragma unroll
-                    for (int pp = 0; pp < CH_NB; pp++)
-                        if (pp < cc) v -= xrow[pp] * Ld[cc][pp];
-                    xrow[cc] = v / Ld[cc][cc];
+                    for (int cc = pp + 1; cc < CH_NB; cc++) v[cc] -= xp * Ld[cc][pp];   // Ld rows >= nbk are zero
                 }
             }
 #pragma unroll
             for (int cc = 0; cc < CH_NB; cc++)
-                if (cc < nbk) Ar[cc] = xrow[cc];
+                if (cc < nbk) Ar[cc] = v[cc];
         }
         __syncthreads();
     }
@@ -414,7 +436,7 @@ extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, do
     double* GV = (double*)ws;
     long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
 
-    { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<nl, 256, 0, st>>>(cl, nz, jitter_rel, root, dmax, diag_max); }
+    { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<dim3(nl, nl >= 1024 ? 2 : 8), 256, 0, st>>>(cl, nz, jitter_rel, root, dmax, diag_max); }
     count_launch();
     CB_LAUNCH_CHECK();
     {
