@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
                                                             const int* __restrict__ fail_list, int nz, double clip_rel,
                                                             double* __restrict__ root, int* __restrict__ num_pos,
                                                             double* __restrict__ evals_ws, int* __restrict__ rank_ws,
-                                                            const int* __restrict__ nfail_ptr) {
+                                                            const int* __restrict__ nfail_ptr,
+                                                            double* __restrict__ evals_sorted = nullptr) {
+    // evals_sorted != nullptr: plain eigen-decomposition (scipy.linalg.eigh layout): column k of `root` is the
+    // unit eigenvector of the k-th smallest eigenvalue, evals_sorted[l][k] that eigenvalue; no clipping
     __shared__ double s_max;
     __shared__ int s_npos;
     if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
@@ -353,10 +356,12 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
     for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
         const int i = (int)(e / nz), r = (int)(e % nz);     // eigenpair i, row r of the root
         const double lam = ev[i];
-        const double sc = (lam < thr) ? 0.0 : sqrt(fmax(lam, 0.0));
+        const double sc = evals_sorted ? 1.0 : ((lam < thr) ? 0.0 : sqrt(fmax(lam, 0.0)));
         R[(long long)r * nz + rank[i]] = V[(long long)i * nz + r] * sc;
     }
-    if (threadIdx.x == 0) num_pos[l] = s_npos;
+    if (evals_sorted)
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) evals_sorted[(long long)l * nz + rank[i]] = ev[i];
+    if (threadIdx.x == 0 && num_pos) num_pos[l] = s_npos;
 }
 
 __global__ void root_flags_kernel(const int* __restrict__ fail, int nl, int nz, int* __restrict__ used_eigh,
@@ -484,6 +489,49 @@ extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, do
     for (int f0 = 0; f0 < nfail; f0 += (int)slots) {
         const int nb = (int)std::min<long long>(slots, nfail - f0);
         if (int rc = wave(f0, nb, nullptr)) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- plain eigh
+__global__ void iota_kernel(int* p, int n, int base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = base + i;
+}
+
+extern "C" long long cora_b200_eigh_workspace_bytes(int nl, int nz) {
+    return 4LL * nl + 8LL * nl + 12LL * nl * nz + 4LL * nl + 8 * 256 + 16LL * nz * nz * (long long)nl;
+}
+
+extern "C" int cora_b200_eigh_batched(const double* a, int nl, int nz, double* evecs, double* evals, void* workspace,
+                                      long long ws_bytes, void* stream) {
+    CB_REQUIRE(a && evecs && evals && workspace && nl >= 1 && nz >= 1, 1, "eigh_batched: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    auto take = [&](long long bytes) { char* p = ws; ws = (char*)(((uintptr_t)(ws + bytes) + 255) & ~(uintptr_t)255); return p; };
+    int* list = (int*)take(4LL * nl);
+    double* dzero = (double*)take(8LL * nl);
+    double* ev_ws = (double*)take(8LL * nl * nz);
+    int* rank = (int*)take(4LL * nl * nz);
+    int* sweeps = (int*)take(4LL * nl);
+    double* GV = (double*)ws;
+    const long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
+    CB_REQUIRE(slots >= 1, 4, "eigh_batched: workspace too small (%lld B)", ws_bytes);
+    iota_kernel<<<ceil_div(nl, 256), 256, 0, st>>>(list, nl, 0);
+    CB_CUDA(cudaMemsetAsync(dzero, 0, 8LL * nl, st));
+    count_launch();
+    CB_LAUNCH_CHECK();
+    const int threads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
+    KTimer kt(K_EIGH, st);
+    for (int f0 = 0; f0 < nl; f0 += (int)slots) {
+        const int nb = (int)std::min<long long>(slots, nl - f0);
+        double* G = GV;
+        double* V = GV + (long long)nb * nz * nz;
+        jacobi_init_kernel<<<nb, 256, 0, st>>>(a, list + f0, nz, 0.0, dzero, G, V, nullptr);
+        jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0, nullptr);
+        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, list + f0, nz, 0.0, evecs, nullptr, ev_ws, rank, nullptr, evals);
+        count_launch(3);
+        CB_LAUNCH_CHECK();
     }
     return 0;
 }

@@ -26,6 +26,22 @@ def root_batched_device(cl_dev, jitter_rel=0.0, clip_rel=1e-16, stream=None, out
     return root, used, npos
 
 
+def eigh_batched_device(a_dev):
+    """Batched ``scipy.linalg.eigh`` on device: CUDA float64 ``[nl, nz, nz]`` -> ``(evals[nl, nz]``
+    ascending, ``evecs[nl, nz, nz]`` with eigenvectors in columns``)`` (``cora_b200_eigh_batched``)."""
+    t = _dev.torch()
+    lib = _lib.load()
+    nl, nz = int(a_dev.shape[0]), int(a_dev.shape[1])
+    evecs = _dev.empty((nl, nz, nz), t.float64)
+    evals = _dev.empty((nl, nz), t.float64)
+    full = lib.cora_b200_eigh_workspace_bytes(nl, nz)
+    one = lib.cora_b200_eigh_workspace_bytes(1, nz) + 32 * nl * (nz + 4)
+    ws = _dev.workspace(min(full, max(one, _dev.free_bytes() - (2 << 30))))
+    _lib.call("cora_b200_eigh_batched", _lib.ptr(a_dev), nl, nz, _lib.ptr(evecs), _lib.ptr(evals), _lib.ptr(ws), int(ws.numel()),
+              _lib.stream_ptr())
+    return evals, evecs
+
+
 def root_workspace(nl, nz, max_eigh=None):
     """Workspace for ``root_batched_device``: room for ``max_eigh`` simultaneous eigen fallbacks
     (default: all nl matrices, bounded by free memory)."""

@@ -179,3 +179,44 @@ def mkfullsky(corr, nside, alms=False, rng=None, *, seed=None, roots=None, gauss
     if not device_out:
         return hputil.alm2map_to_host(panel, nside, maxl, numz)
     return hputil.alm2map_device(panel, nside, maxl, _lib.ALM_PANEL, numz, numz)
+
+
+def mkconstrained(corr, constraints, nside, device_out=False):
+    """Construct a set of Healpix maps satisfying given constraints on specified frequency
+    slices, by using the lowest eigenmodes (``cora/core/skysim.py:139-201``).
+
+    ``corr``: ``float64[lmax+1, numz, numz]``; ``constraints``: ``[[frequency_index, healpix map], ...]``.
+    Per l the ``nmodes = len(constraints)`` eigenvectors of the largest eigenvalues are found
+    (batched Jacobi eigh on the GPU), the constraint maps go to harmonic space
+    (``healpy.map2alm`` defaults: no ring weights, 3 refinements), the mode amplitudes that
+    reproduce the constrained slices are solved for and projected across all frequencies
+    (``cv = trans^T solve(tmat^T, cmap)``, l = 0 set to zero), and the batched inverse SHT makes
+    the maps.  The small ``nmodes x nmodes`` solves run on the host; everything that scales with
+    the map or with ``numz^2`` runs in the CUDA kernels.  Returns ``float64[numz, npix]``."""
+    t = _dev.torch()
+    numz = corr.shape[1]
+    maxl = corr.shape[0] - 1
+    if corr.shape[2] != numz:
+        raise Exception("Correlation matrix is incorrect shape.")
+    nmodes = len(constraints)
+    f_ind = [int(c[0]) for c in constraints]
+    L = maxl + 1
+    cl = _dev.to_device(corr, t.float64)
+    _, evecs = nputil.eigh_batched_device(cl)                      # columns ascending: the last nmodes are the largest
+    trans = evecs[:, :, numz - nmodes:].transpose(1, 2).contiguous().cpu().numpy()   # [L, nmodes, numz]
+    del evecs
+    tmat = trans[:, :, f_ind]                                      # [L, nmodes, nmodes]
+    # W_l = trans_l^T inv(tmat_l^T): cv[:, (l, m)] = W_l cmap[(l, m), :]
+    W = np.zeros((L, numz, numz))
+    for l in range(1, L):
+        W[l, :, :nmodes] = np.linalg.solve(tmat[l], trans[l]).T     # (inv(tmat) trans)^T = trans^T inv(tmat^T)
+    cmaps = _dev.to_device(np.ascontiguousarray([np.asarray(c[1], dtype=np.float64) for c in constraints]), t.float64)
+    cpanel = hputil.map2alm_device(cmaps, nside, maxl, iter=3)     # PANEL [nalm, nmodes]
+    cdense = hputil.panel_to_dense(cpanel, maxl, nmodes)           # [nmodes, L, L]
+    gauss = _dev.zeros((L, numz, L), t.complex128)
+    gauss[:, :nmodes, :] = cdense.permute(1, 0, 2)
+    nalm = L * (L + 1) // 2
+    panel = _dev.empty((nalm, numz), t.complex128)
+    draw_apply_device(_dev.to_device(W, t.float64), np.arange(L), None, numz, maxl, panel, gauss=gauss)
+    sky = hputil.alm2map_device(panel, nside, maxl, _lib.ALM_PANEL, numz, numz)
+    return sky if device_out else _dev.to_host(sky)

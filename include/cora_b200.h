@@ -164,6 +164,14 @@ int cora_b200_root_batched_block(const double* cl, int nl, int nz, double jitter
                                  const double* diag_max, double* root, int* used_eigh, int* num_pos,
                                  void* workspace, long long ws_bytes, void* stream);
 
+/* Batched symmetric eigen-decomposition in scipy.linalg.eigh's layout (lower triangle read):
+ * evals[l][k] ascending, column k of evecs[l] the unit eigenvector of evals[l][k].
+ * replaces: la.eigh(corr[i]) in mkconstrained (cora/core/skysim.py:183-185).  One-sided Jacobi,
+ * one CTA per matrix; a smaller workspace is processed in waves.                           */
+long long cora_b200_eigh_workspace_bytes(int nl, int nz);
+int cora_b200_eigh_batched(const double* a, int nl, int nz, double* evecs, double* evals, void* workspace,
+                           long long ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ draw + apply - */
 /* alm[nu, l, m] = sum_nu' M_l[nu, nu'] g_l[nu', m], written in PANEL layout.
  * replaces: complex_std_normal + np.dot + scatter (cora/core/skysim.py:119-121,

@@ -72,3 +72,35 @@ def mkfullsky(corr, nside, alms=False, rng=None, record=None):
     if alms:
         return alm_array
     return hputil.sphtrans_inv_sky(alm_array, nside)[:, 0]
+
+
+def mkconstrained(corr, constraints, nside):
+    """Restatement of ``cora/core/skysim.py:139-201`` with the oracle transforms in place of healpy
+    (``map2alm`` defaults: no ring weights, ``iter=3``)."""
+    import scipy.linalg as la
+
+    from . import sht
+
+    numz = corr.shape[1]
+    maxl = corr.shape[0] - 1
+    nmodes = len(constraints)
+    f_ind = [c[0] for c in constraints]
+    if corr.shape[2] != numz:
+        raise Exception("Correlation matrix is incorrect shape.")
+    nalm = (maxl + 1) * (maxl + 2) // 2
+    larr = np.concatenate([np.arange(m, maxl + 1) for m in range(maxl + 1)])   # healpy.Alm.getlm order
+    trans = np.zeros((corr.shape[0], nmodes, numz))
+    tmat = np.zeros((corr.shape[0], nmodes, nmodes))
+    cmap = np.zeros((nalm, nmodes), dtype=np.complex128)
+    cv = np.zeros((numz, nalm), dtype=np.complex128)
+    for i in range(maxl + 1):
+        trans[i] = la.eigh(corr[i])[1][:, -nmodes:].T
+        tmat[i] = trans[i][:, f_ind]
+    for i, cons in enumerate(constraints):
+        cmap[:, i] = sht.map2alm(cons[1], nside, maxl, iter=3)
+    for i, l in enumerate(larr):
+        if l == 0:
+            cv[:, i] = 0.0
+        else:
+            cv[:, i] = np.dot(trans[l].T, la.solve(tmat[l].T, cmap[i]))
+    return sht.alm2map(cv, nside, maxl)

@@ -8,6 +8,7 @@ from conftest import golden
 from oracle import hputil as ohp
 from oracle import nputil as onp
 from oracle import skysim as osk
+from oracle import spectra as osp
 
 pytestmark = pytest.mark.gpu
 
@@ -250,3 +251,55 @@ def test_getsky_and_makesky_drivers():
     cr.nside, cr.frequencies = 8, fs.frequencies
     a = cr.getalms(23)
     assert a.shape == (4, 1, 24, 24)
+
+
+def test_eigh_batched_vs_scipy():
+    import scipy.linalg as la
+    import torch
+    from cora_b200 import nputil
+
+    rng = np.random.default_rng(31)
+    for nl, nz in ((5, 7), (3, 32), (2, 65)):
+        a = rng.standard_normal((nl, nz, nz))
+        a = a + a.transpose(0, 2, 1)
+        evals, evecs = nputil.eigh_batched_device(torch.from_numpy(a).cuda())
+        evals, evecs = evals.cpu().numpy(), evecs.cpu().numpy()
+        for i in range(nl):
+            w = la.eigh(a[i])[0]
+            np.testing.assert_allclose(evals[i], w, rtol=0, atol=1e-12 * np.abs(w).max())
+            # A V = V diag(w), V orthonormal
+            assert np.abs(a[i] @ evecs[i] - evecs[i] * evals[i]).max() < 1e-11 * np.abs(w).max()
+            assert np.abs(evecs[i].T @ evecs[i] - np.eye(nz)).max() < 1e-12
+
+
+def test_mkconstrained_vs_oracle():
+    """mkconstrained (skysim.py:139-201): the constrained slices reproduce the (band-limited) constraint
+    maps and every channel matches the oracle restatement."""
+    from cora_b200 import galaxy, skysim
+
+    nside, nz = 8, 6
+    lmax = 3 * nside - 1
+    freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+    cl = osk.clarray(osp.full_sky_synchrotron().angular_powerspectrum, lmax, freq)
+    cl[0] = cl[1]    # l = 0 of the SCK spectrum is zero (degenerate eigenproblem); its result is discarded anyway
+    rng = np.random.default_rng(41)
+    # band-limited constraint maps so that map2alm -> alm2map returns them
+    maps = []
+    for _ in range(2):
+        nalm = (lmax // 2 + 1) * (lmax // 2 + 2) // 2
+        a = rng.standard_normal(nalm) + 1j * rng.standard_normal(nalm)
+        a[: lmax // 2 + 1] = a[: lmax // 2 + 1].real
+        maps.append(osht_alm2map(a, nside, lmax // 2))
+    cons = [[1, maps[0]], [4, maps[1]]]
+    ref = osk.mkconstrained(cl, cons, nside)
+    got = skysim.mkconstrained(cl, cons, nside)
+    assert got.shape == ref.shape == (nz, 12 * nside**2)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-8
+    with pytest.raises(Exception, match="incorrect shape"):
+        skysim.mkconstrained(np.zeros((4, 3, 2)), cons, nside)
+
+
+def osht_alm2map(a, nside, lmax):
+    from oracle import sht
+
+    return sht.alm2map(a, nside, lmax)

@@ -2,6 +2,7 @@
 reference (tests/golden/make_golden.py)."""
 
 import numpy as np
+import pytest
 
 from conftest import golden
 from oracle import hputil, nputil, skysim
@@ -112,3 +113,30 @@ def test_partition_matches_caput_rule():
         sizes = [b - a for a, b in blocks]
         assert sizes == [n // P + (1 if r < n % P else 0) for r in range(P)]
         assert all(blocks[r][1] == blocks[r + 1][0] for r in range(P - 1))
+
+
+def test_oracle_mkconstrained_reproduces_constraints():
+    """Restatement of skysim.py:139-201: the constrained frequency slices come back as the
+    (monopole-free, band-limited) constraint maps."""
+    from oracle import sht
+    from oracle import spectra as osp2
+
+    nside, nz = 8, 5
+    lmax = 3 * nside - 1
+    freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+    cl = skysim.clarray(osp2.full_sky_synchrotron().angular_powerspectrum, lmax, freq)
+    cl[0] = cl[1]
+    rng = np.random.default_rng(3)
+    maps = []
+    for _ in range(2):
+        lb = lmax // 2
+        nalm = (lb + 1) * (lb + 2) // 2
+        a = rng.standard_normal(nalm) + 1j * rng.standard_normal(nalm)
+        a[: lb + 1] = a[: lb + 1].real
+        maps.append(sht.alm2map(a, nside, lb))
+    out = skysim.mkconstrained(cl, [[0, maps[0]], [3, maps[1]]], nside)
+    assert out.shape == (nz, 12 * nside**2)
+    for idx, mp in ((0, maps[0]), (3, maps[1])):
+        assert np.abs(out[idx] - (mp - mp.mean())).max() / np.abs(mp).max() < 2e-2
+    with pytest.raises(Exception, match="incorrect shape"):
+        skysim.mkconstrained(np.zeros((4, 3, 2)), [[0, maps[0]]], nside)
