@@ -364,6 +364,109 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
     if (threadIdx.x == 0 && num_pos) num_pos[l] = s_npos;
 }
 
+
+// ----------------------------------------------------------------- pivoted-Cholesky fallback
+// For large matrices the Jacobi eigen fallback is hopeless (11 s for one 1024^2 matrix: every
+// rotation streams whole rows through L2), while the matrices that need a fallback are the
+// numerically rank-deficient foreground covariances (rank ~50 of 1024).  A diagonally pivoted
+// Cholesky with the reference's relative clip gives a root with the same defining property,
+// M M^T = C + jitter to within clip_rel * trace element-wise, in O(nz^2 rank):
+//   p = argmax d;  stop when d[p] <= clip_rel * trace;  L[:,k] = (A[:,p] - L[:, :k] L[p, :k]^T) / sqrt(d[p]);
+//   d -= L[:,k]^2.
+// Columns are stored like the eigen branch stores its own: discarded (zero) columns first, the
+// retained ones last with the strongest in the last column; num_pos = rank.  One CTA per matrix.
+// Lws: [slot][k][i] (column k of L contiguous in i).
+__global__ void __launch_bounds__(1024) pchol_kernel(const double* __restrict__ cl, const int* __restrict__ fail_list, int nz,
+                                                     double jitter_rel, const double* __restrict__ dmax, double clip_rel,
+                                                     double* __restrict__ Lws_all, double* __restrict__ root,
+                                                     int* __restrict__ num_pos, const int* __restrict__ nfail_ptr) {
+    extern __shared__ __align__(16) double pc_smem[];
+    double* d = pc_smem;              // [nz] residual diagonal (-1 once a row has been a pivot)
+    double* Lp = d + nz;              // [nz] row p of L
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_piv, s_tau;
+    __shared__ int s_p;
+    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
+    const int l = fail_list[blockIdx.x];
+    const double* A = cl + (long long)l * nz * nz;
+    double* Lws = Lws_all + (long long)blockIdx.x * nz * nz;
+    const double cmax = dmax[l] * jitter_rel;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+
+    double tr = 0.0;
+    for (int i = tid; i < nz; i += blockDim.x) {
+        const double v = A[(long long)i * nz + i] + cmax;
+        d[i] = v;
+        tr += v;
+    }
+    tr = warp_sum(tr);
+    if (lane == 0) s_val[warp] = tr;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < nwarp; w++) t += s_val[w];
+        s_tau = clip_rel * fmax(t, 0.0);
+    }
+    __syncthreads();
+    int k = 0;
+    for (; k < nz; k++) {
+        // ---- pivot: largest residual diagonal entry, lowest index on ties
+        double bv = -1.0e308;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < nz; i += blockDim.x) {
+            const double v = d[i];
+            if (v > bv) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double v = s_val[0];
+            int ix = s_idx[0];
+            for (int w = 1; w < nwarp; w++)
+                if (s_val[w] > v || (s_val[w] == v && s_idx[w] < ix)) { v = s_val[w]; ix = s_idx[w]; }
+            s_p = ix;
+            s_piv = v;
+        }
+        __syncthreads();
+        const int p = s_p;
+        const double dp = s_piv;
+        if (!(dp > s_tau) || !(dp > 0.0)) break;      // uniform
+        const double piv = sqrt(dp);
+        for (int j = tid; j < k; j += blockDim.x) Lp[j] = Lws[(long long)j * nz + p];
+        __syncthreads();
+        for (int i = tid; i < nz; i += blockDim.x) {
+            double lik = 0.0;
+            if (i == p) {
+                lik = piv;
+            } else if (d[i] >= 0.0) {                 // rows that were pivots before stay exactly zero
+                // LAPACK-style: only the lower triangle of the input is read
+                double v = (i < p) ? A[(long long)p * nz + i] : A[(long long)i * nz + p];
+                for (int j = 0; j < k; j++) v = fma(-Lws[(long long)j * nz + i], Lp[j], v);
+                lik = v / piv;
+            }
+            Lws[(long long)k * nz + i] = lik;
+            if (i == p) d[i] = -1.0;
+            else if (d[i] >= 0.0) d[i] = fmax(d[i] - lik * lik, 0.0);
+        }
+        __syncthreads();
+    }
+    // ---- root[i][nz - 1 - kk] = L[i][kk]; zero columns first
+    double* R = root + (long long)l * nz * nz;
+    for (long long e = tid; e < (long long)nz * nz; e += blockDim.x) {
+        const int i = (int)(e / nz), c = (int)(e % nz);
+        const int kk = nz - 1 - c;
+        R[e] = (kk < k) ? Lws[(long long)kk * nz + i] : 0.0;
+    }
+    if (tid == 0) num_pos[l] = k;
+}
+
 __global__ void root_flags_kernel(const int* __restrict__ fail, int nl, int nz, int* __restrict__ used_eigh,
                                   int* __restrict__ num_pos, int* __restrict__ fail_list, int* __restrict__ nfail) {
     // single thread block: compact the failed indices (order preserved)
@@ -386,6 +489,10 @@ using namespace cb;
 static long long root_fixed_bytes(int nl, int nz) {
     return 8LL * nl + 4LL * nl * 3 + 64 + 12LL * nl * nz + 10 * 256;
 }
+
+// Matrices up to this size take the Jacobi eigen fallback (the reference's exact eigen semantics);
+// larger ones the pivoted Cholesky.  CORA_B200_JACOBI_MAX_NZ overrides (e.g. a huge value forces Jacobi).
+static int g_jacobi_max_nz = [] { const char* e = getenv("CORA_B200_JACOBI_MAX_NZ"); return e ? atoi(e) : 128; }();
 
 extern "C" long long cora_b200_root_workspace_bytes(int nl, int nz) {
     // room for every matrix to take the eigh path (2 nz^2 doubles each); a smaller workspace is
@@ -465,6 +572,15 @@ extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, do
         double* G = GV;
         double* V = GV + (long long)nb * nz * nz;
         KTimer kt(K_EIGH, st);
+        if (nz > g_jacobi_max_nz) {
+            const size_t smem = sizeof(double) * 2 * (size_t)nz;
+            CB_CUDA(cudaFuncSetAttribute(pchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            pchol_kernel<<<nb, nz >= 512 ? 1024 : 512, smem, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, clip_rel, G, root,
+                                                                   num_pos, guard);
+            count_launch();
+            CB_LAUNCH_CHECK();
+            return 0;
+        }
         jacobi_init_kernel<<<nb, 256, 0, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, G, V, guard);
         count_launch();
         CB_LAUNCH_CHECK();

@@ -303,3 +303,42 @@ def osht_alm2map(a, nside, lmax):
     from oracle import sht
 
     return sht.alm2map(a, nside, lmax)
+
+
+def test_root_large_rank_deficient_pivoted_cholesky():
+    """nz > 128: matrices on which Cholesky meets a non-positive pivot take the pivoted-Cholesky
+    fallback (same clip, O(nz^2 rank)): M M^T = C to 1e-12 element-wise, zero columns first,
+    num_pos = numerical rank; positive-definite matrices still take the plain Cholesky."""
+    import torch
+    from cora_b200 import galaxy, nputil, skysim
+
+    rng = np.random.default_rng(5)
+    nz = 200
+    mats = []
+    for rank in (3, 40, 199):
+        a = rng.standard_normal((nz, rank))
+        mats.append(a @ a.T)
+    mats.append(np.zeros((nz, nz)))
+    b = rng.standard_normal((nz, 2 * nz))
+    mats.append(b @ b.T / nz)           # well conditioned: Cholesky branch
+    mats = np.array(mats)
+    root, used, npos = nputil.root_batched_device(torch.from_numpy(mats).cuda(), jitter_rel=0.0, clip_rel=1e-16)
+    root, used, npos = root.cpu().numpy(), used.cpu().numpy(), npos.cpu().numpy()
+    assert list(used) == [1, 1, 1, 1, 0]
+    for k, rank in enumerate((3, 40, 199)):
+        assert _mmt_err(root[k], mats[k]) < 1e-12
+        assert rank <= npos[k] <= rank + 2          # round-off may leave a pivot or two above the clip
+        assert np.all(root[k][:, : nz - npos[k]] == 0)
+        # strongest column last
+        norms = np.linalg.norm(root[k], axis=0)
+        assert norms[-1] == norms.max()
+    assert npos[3] == 0 and np.all(root[3] == 0)
+    assert np.all(np.triu(root[4], 1) == 0) and _mmt_err(root[4], mats[4]) < 1e-12
+    # the foreground covariance at 256 channels with the reference's jitter
+    freq = np.linspace(800.0, 400.0, 256, endpoint=False)
+    cl = skysim.clarray(galaxy.FullSkySynchrotron().angular_powerspectrum, 12, freq)
+    cl[1:] *= 1.0 - 1e-13     # make sure some l fail the plain Cholesky
+    root, used, npos = nputil.root_batched_device(torch.from_numpy(cl).cuda(), jitter_rel=1e-14, clip_rel=1e-16)
+    root = root.cpu().numpy()
+    for l in range(1, 13):
+        assert _mmt_err(root[l], cl[l]) < 1e-12
