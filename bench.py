@@ -35,12 +35,14 @@ WORKLOADS = {
     "c1": ("gaussianfg", 64, 32, 800.0, 400.0),
     "c2": ("21cm", 256, 256, 800.0, 400.0),
     "c3": ("21cm", 512, 1024, 800.0, 400.0),
+    "c4": ("gaussianfg_pol", 512, 1024, 800.0, 400.0),
     "c5": ("21cm", 1024, 2048, 800.0, 400.0),
 }
 WORKLOAD_TEXT = {
     "c1": "cora-makesky gaussianfg nside=64, 32 channels 400-800 MHz, unpolarised",
     "c2": "cora-makesky 21cm (Corr21cm) nside=256, 256 channels 400-800 MHz",
     "c3": "cora-makesky 21cm nside=512, 1024 channels 400-800 MHz",
+    "c4": "cora-makesky gaussianfg --pol full (T/E/B, spin-2 SHT) nside=512, 1024 channels 400-800 MHz",
     "c5": "cora-makesky 21cm nside=1024, 2048 channels 400-800 MHz",
 }
 METRIC = "full-sky map voxels/sec (pixels x channels)"
@@ -49,7 +51,7 @@ UNIT = "voxels/s"
 
 def workload_params(name):
     model, nside, nchan, f0, f1 = WORKLOADS[name]
-    lmax = 3 * nside if model == "gaussianfg" else 3 * nside - 1
+    lmax = 3 * nside if model.startswith("gaussianfg") else 3 * nside - 1
     freq = np.linspace(f0, f1, nchan, endpoint=False)
     return dict(model=model, nside=nside, nchan=nchan, lmax=lmax, freq=freq, npix=12 * nside * nside, zromb=3)
 
@@ -351,9 +353,17 @@ def run_ours(args):
     model.nside = nside
     model.frequencies = wp["freq"]
     model.oversample = wp["zromb"]
+    pol = wp["model"] == "gaussianfg_pol"
+    npol = 4 if pol else 1
+    sht_equiv = 5.0 if pol else 1.0    # T scalar + the (E,B)->(Q,U) pair = 4 scalar-equivalents; V is identically 0
 
-    sh = cdist.ShardedSky(model, nside, wp["freq"], lmax=lmax, zromb=wp["zromb"], rank=rank, size=world)
-    out = torch.empty((sh.cb, npix), dtype=torch.float64, device="cuda")
+    if pol:
+        sh = cdist.ShardedPolSky(nside, wp["freq"], lmax=lmax, zromb=wp["zromb"], rank=rank, size=world)
+        sh.exchange = "p2p"
+        out = torch.zeros((sh.cb, 4, npix), dtype=torch.float64, device="cuda")
+    else:
+        sh = cdist.ShardedSky(model, nside, wp["freq"], lmax=lmax, zromb=wp["zromb"], rank=rank, size=world)
+        out = torch.empty((sh.cb, npix), dtype=torch.float64, device="cuda")
 
     def barrier():
         if world > 1:
@@ -394,7 +404,7 @@ def run_ours(args):
         lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
-    voxels = float(npix) * nchan
+    voxels = float(npix) * nchan * npol
     value = voxels * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API, host buffers in / host maps out ("e2e")
@@ -402,7 +412,7 @@ def run_ours(args):
     exchange_mode = sh.exchange
     if world > 1 and sh.exchange == "p2p":
         sh.peers.check()             # a timed-out peer barrier would have produced garbage: fail loudly
-    if world == 1:
+    if world == 1 and not pol:
         del sh                       # the resident-path buffers go back to the allocator first
     del out
     torch.cuda.empty_cache()
@@ -410,10 +420,11 @@ def run_ours(args):
     _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
 
     def e2e_once(seed):
-        if world == 1:
+        if world == 1 and not pol:
             np.random.seed(seed)
             return model.getsky()  # Sky3d.getsky(): clarray + mkfullsky -> numpy float64[nfreq, npix]
         sky = sh.step(seed=seed)
+        sky = sky.reshape(sky.shape[0], -1)
         if sky.numel() * 8 > (4 << 30):          # too large to hold pinned: stream it through a staging ring
             _dev.stream_to_host(sky)
             return sky[:, :0].cpu().numpy().reshape(sky.shape[0], 0)
@@ -423,7 +434,7 @@ def run_ours(args):
     e2e_each = []
     try:
         e2e_once(99)  # warm the pinned-buffer cache (two passes: the first one allocates the host block,
-        if float(npix) * cb_local * 8 < (4 << 30):
+        if float(npix) * cb_local * 8 * npol < (4 << 30):
             e2e_once(98)  # the second confirms torch's host allocator hands the same block back)
         _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
         barrier()
@@ -431,7 +442,7 @@ def run_ours(args):
         for i in range(e2e_steps):
             ts = time.perf_counter()
             res = e2e_once(i)
-            assert res.shape[0] == (cb_local if world > 1 else nchan) and res.shape[1] in (npix, 0)
+            assert res.shape[0] == (cb_local if world > 1 else nchan) and res.shape[1] in (npix * npol, 0)
             del res
             e2e_each.append(round(1e3 * (time.perf_counter() - ts), 2))
         barrier()
@@ -456,7 +467,7 @@ def run_ours(args):
     peak = (ctypes_double * 1)()
     _lib.call("cora_b200_fp64_peak", 50.0, peak, _lib.stream_ptr())
     leg_ms, leg_n = kernels["sht_legendre"]
-    flops_per_launch = sht_flops(nside, lmax, cb_local) * args.steps / max(1, leg_n)
+    flops_per_launch = sht_equiv * sht_flops(nside, lmax, cb_local) * args.steps / max(1, leg_n)
     achieved = flops_per_launch / (leg_ms / max(1, leg_n) * 1e-3) / 1e12 if leg_ms > 0 else 0.0
     step_ms = ms / args.steps
     traffic = None   # DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture
@@ -490,20 +501,22 @@ def run_ours(args):
     pk = float(peak[0])
     zi = 2 ** wp["zromb"] + 1
     stage_roofline = {
-        "sht_legendre": _stage("sht_legendre", sht_flops(nside, lmax, cb_local), 1e12, pk, "tensor(fp64 DMMA)",
+        "sht_legendre": _stage("sht_legendre", sht_equiv * sht_flops(nside, lmax, cb_local), 1e12, pk, "tensor(fp64 DMMA)",
                                "4*ceil(nring/2)*nalm*channels flop"),
-        "sht_phase": _stage("sht_phase", cb_local * (16.0 * nring * L + 8.0 * npix), 1e9, hbm_peak, "hbm",
+        "sht_phase": _stage("sht_phase", (3 if pol else 1) * cb_local * (16.0 * nring * L + 8.0 * npix), 1e9, hbm_peak,
+                            "hbm floor (measured: FP64 issue-bound FFT butterflies)",
                             "16*nring*L + 8*npix bytes per channel (F read + map written)"),
-        "apply": _stage("apply", 2.0 * nchan * nchan * sum_l1 * 2 / 2.0, 1e12, pk, "tensor(fp64 DMMA)",
+        "apply": _stage("apply", (3 if pol else 1) * 2.0 * nchan * nchan * sum_l1 * 2 / 2.0, 1e12, pk, "tensor(fp64 DMMA)",
                         "2*nz^2*(l+1) real flop per l for complex draws, halved for the triangular (Cholesky) roots"),
-        "cholesky": _stage("cholesky", nl_local * nchan ** 3 / 3.0, 1e12, pk, "tensor(fp64 DMMA) / latency",
+        "cholesky": _stage("cholesky", (2 if pol else 1) * nl_local * nchan ** 3 / 3.0, 1e12, pk, "tensor(fp64 DMMA) / latency",
                            "nz^3/3 flop per l"),
-        "draw": _stage("draw", 16.0 * nchan * sum_l1, 1e9, hbm_peak, "hbm", "16*nz*(l+1) bytes written per l"),
-        "cl_fill": _stage("cl_fill", 8.0 * L * nchan * nchan / world, 1e9, hbm_peak, "L1/L2 gather (hbm = output-write floor)",
+        "draw": _stage("draw", (3 if pol else 1) * 16.0 * nchan * sum_l1, 1e9, hbm_peak, "hbm (measured: FP64 ALU-bound Box-Muller)",
+                       "16*nz*(l+1) bytes written per l"),
+        "cl_fill": _stage("cl_fill", (2 if pol else 1) * 8.0 * L * nchan * nchan / world, 1e9, hbm_peak, "L1/L2 gather (hbm = output-write floor)",
                           "8*L*nz^2 output bytes; %.3g evaluations of the 2-D interpolant" % (L * (zi * nchan) ** 2 / 2.0 / world)),
     }
     stage_roofline = {k: v for k, v in stage_roofline.items() if v}
-    if world > 1 and exchange_mode == "p2p":
+    if (world > 1 or pol) and exchange_mode == "p2p":
         sh.peers.check()
         sh.peers.close()
 
@@ -513,7 +526,7 @@ def run_ours(args):
         return
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not pol:
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup",
                                 "0", "--workload", args.workload], capture_output=True, text=True, timeout=900,
@@ -538,7 +551,7 @@ def run_ours(args):
                    "stage_ms_per_step": stage_share,
                    "stage_roofline": stage_roofline, "hbm_peak_source": hbm_src},
         "e2e": {"value": None, "unit": UNIT, "error": e2e_error} if e2e_error else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-                "steps": e2e_steps, "ms_each": e2e_each, "host_bound_to_gpu_numa_node": numa_bound, "api": "Corr21cm.getsky() -> numpy" if world == 1 else "dist.ShardedSky.step() -> host"},
+                "steps": e2e_steps, "ms_each": e2e_each, "host_bound_to_gpu_numa_node": numa_bound, "api": "Corr21cm.getsky() -> numpy" if (world == 1 and not pol) else "dist.Sharded%sSky.step() -> host" % ("Pol" if pol else "")},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "sht_legendre_kernel<0> (FP64 DMMA)", "achieved": achieved,
