@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
         const int xtop = min(NKPERP - 1, (int)xb + 2);
         const int W = xtop - xbase + 1;
         const bool banded = (W <= FILL_WMAX);
+        // no l >= 1 of this block is clipped, and none reaches the table's last column
+        const double xa_raw = (log10((double)lfirst) - smax) * xscale, xb_raw = (log10((double)llast) - smin) * xscale;
+        const bool noclip = (xa_raw >= 0.0) && (xb_raw < (double)(NKPERP - 1) - 1e-3);
 
         double lx[FILL_LPT], acc[FILL_LPT];
         int lv[FILL_LPT];
@@ -292,22 +295,40 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
                     R[el * FILL_WMAX + xi] = p.cdd * dd + p.cdv * dv + p.cvv * vv;
                 }
                 __syncthreads();
-                // x-interpolation of the band rows (measured: a conversion-free floor and an el-outer /
-                // q-inner order are not faster than this form -- profiles/README.md)
+                // x-interpolation of the band rows.  An FP64 fmin/fmax pair costs ~16 instructions (NaN-aware
+                // select sequences) -- a third of this loop -- so the clip of bilinearmap.pyx:44-45 is only
+                // executed when some l of this block can actually reach it (CTA-uniform test on the band ends;
+                // same arithmetic and bit-identical results for in-range x).
+                if (noclip) {
 #pragma unroll
-                for (int q = 0; q < FILL_LPT; q++) {
-                    if (lv[q] < 1) continue;
-                    double a = acc[q];
-                    for (int el = 0; el < ne; el++) {
-                        double x = (lx[q] - pre[e0 + el].shift) * xscale;
-                        x = fmin(fmax(x, 0.0), xtopclip);
-                        const int x0 = (int)x;
-                        const double wx = x - (double)x0;
-                        const double* Rr = R + el * FILL_WMAX + (x0 - xbase);
-                        const int up = (x0 < NKPERP - 1) ? 1 : 0;
-                        a += (1.0 - wx) * Rr[0] + wx * Rr[up];
+                    for (int q = 0; q < FILL_LPT; q++) {
+                        if (lv[q] < 1) continue;
+                        double a = acc[q];
+                        for (int el = 0; el < ne; el++) {
+                            const double x = (lx[q] - pre[e0 + el].shift) * xscale;
+                            const int x0 = (int)x;
+                            const double wx = x - (double)x0;
+                            const double* Rr = R + el * FILL_WMAX + (x0 - xbase);
+                            a += (1.0 - wx) * Rr[0] + wx * Rr[1];
+                        }
+                        acc[q] = a;
                     }
-                    acc[q] = a;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < FILL_LPT; q++) {
+                        if (lv[q] < 1) continue;
+                        double a = acc[q];
+                        for (int el = 0; el < ne; el++) {
+                            double x = (lx[q] - pre[e0 + el].shift) * xscale;
+                            x = fmin(fmax(x, 0.0), xtopclip);
+                            const int x0 = (int)x;
+                            const double wx = x - (double)x0;
+                            const double* Rr = R + el * FILL_WMAX + (x0 - xbase);
+                            const int up = (x0 < NKPERP - 1) ? 1 : 0;
+                            a += (1.0 - wx) * Rr[0] + wx * Rr[up];
+                        }
+                        acc[q] = a;
+                    }
                 }
             }
         } else {
