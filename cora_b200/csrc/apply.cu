@@ -163,17 +163,28 @@ __global__ void __launch_bounds__(256, 2) apply_kernel(ApplyParams P) {
         stage_load(it + AP_STAGES - 1, (it + AP_STAGES - 1) % AP_STAGES);
         const double* As = ap_smem + (it % AP_STAGES) * AP_STAGE_DOUBLES;
         const double* Bs = As + AP_TM * AP_ALD;
+        // Triangular (Cholesky) roots: an 8-row block needs only the columns k <= its last row; everything
+        // to the right is exact zeros.  The DMMA pipe is what bounds this kernel (82 % busy in ncu), so the
+        // zero blocks are skipped per 8 rows x 4 columns -- warp-uniform tests, bit-identical sums.
+        // (Measured alternatives: interleaving the 8-row blocks over the warps to even out the work is slower,
+        // 2.02 ms vs 1.75 ms; re-pairing row groups over SM sub-partitions changes nothing.)
+        const int kk0 = it * AP_KC;
+        const int rw = r0 + wm * 32;                     // first row of this warp's 32
+        if (tri && kk0 > rw + 31) continue;              // the whole chunk lies right of this warp's rows
 #pragma unroll
         for (int k4 = 0; k4 < AP_KC / 4; k4++) {
+            const int kk = kk0 + 4 * k4;
             double af[4], bf[4];
 #pragma unroll
             for (int mb = 0; mb < 4; mb++) af[mb] = As[(wm * 32 + 8 * mb + g) * AP_ALD + k4 * 4 + t];
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) bf[nb] = Bs[(k4 * 4 + t) * AP_BLD + wn * 32 + 8 * nb + g];
 #pragma unroll
-            for (int mb = 0; mb < 4; mb++)
+            for (int mb = 0; mb < 4; mb++) {
+                if (tri && kk > rw + 8 * mb + 7) continue;
 #pragma unroll
                 for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+            }
         }
     }
     cp_async_wait<0>();
