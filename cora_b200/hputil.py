@@ -390,3 +390,52 @@ def sph_ps(map1, map2=None, lmax=None):
     prod = alm1 * alm2.conj()
     s = prod[:, 0] + 2 * prod[:, 1:].sum(axis=1).real
     return s / (2.0 * np.arange(lmax + 1) + 1.0)
+
+
+# ------------------------------------------------------------------ small helpers of the reference module
+def ang_positions(nside):
+    """(theta, phi) of every RING pixel, ``float64[npix, 2]`` (``hputil.py:53-73``; the HEALPix ring
+    geometry is evaluated here instead of through ``healpy.pix2ang``)."""
+    n = int(nside)
+    npix = 12 * n * n
+    angpos = np.empty([npix, 2], dtype=np.float64)
+    ring = np.arange(1, 4 * n)
+    north = np.minimum(ring, 4 * n - ring).astype(np.float64)
+    cap = north < n
+    z = np.where(cap, 1.0 - north**2 / (3.0 * n * n), 4.0 / 3.0 - 2.0 * north / (3.0 * n))
+    z = np.where(ring > 2 * n, -z, z)
+    nph = np.where(cap, 4 * north, 4 * n).astype(np.int64)
+    shifted = cap | ((north.astype(np.int64) - n) % 2 == 0)
+    start = 0
+    for r in range(4 * n - 1):
+        k = int(nph[r])
+        angpos[start : start + k, 0] = np.arccos(z[r])
+        angpos[start : start + k, 1] = (np.arange(k) + (0.5 if shifted[r] else 0.0)) * (2.0 * np.pi / k)
+        start += k
+    return angpos
+
+
+def nside_for_lmax(lmax, accuracy_boost=1):
+    """A power-of-two nside appropriate for a decomposition up to ``lmax`` (``hputil.py:76-90``)."""
+    return int(2 ** (accuracy_boost + np.ceil(np.log((lmax + 1) / 3.0) / np.log(2.0))))
+
+
+def sphtrans_complex_pol(hpmaps, lmax=None, centered=False, lside=None):
+    """Transform of complex T, Q, U (V) maps: real and imaginary parts separately, full-m layout
+    (``hputil.py:326-366``)."""
+    hpmaps = np.asarray(hpmaps)
+    if lmax is None:
+        lmax = 3 * _nside_of(hpmaps[0].size) - 1
+    alm = _make_full_alm(sphtrans_real_pol(hpmaps.real, lmax=lmax, lside=lside), centered=centered)
+    alm = alm + 1.0j * _make_full_alm(sphtrans_real_pol(hpmaps.imag, lmax=lmax, lside=lside), centered=centered)
+    return alm
+
+
+def sphtrans_inv_complex(alm, nside):
+    """Inverse transform onto a complex field; ``alm[l, all m]`` in the wrapped layout
+    (``hputil.py:435-457``)."""
+    if alm.shape[1] != (2 * alm.shape[0] - 1):
+        raise Exception("a_lm array wrong shape: " + repr(alm.shape))
+    almr = _make_half_alm(alm)
+    almi = 1.0j * (alm[:, : almr.shape[1]] - almr)
+    return sphtrans_inv_real(almr, nside) + 1.0j * sphtrans_inv_real(almi, nside)

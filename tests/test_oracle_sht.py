@@ -254,3 +254,16 @@ def test_map2alm_spin2_roundtrip():
     e0 = max(np.abs(x - y).max() for x, y in zip(sht.map2alm_spin2(q, u, nside, lmax, iter=0), (aE, aB)))
     e4 = max(np.abs(x - y).max() for x, y in zip(sht.map2alm_spin2(q, u, nside, lmax, iter=4), (aE, aB)))
     assert e0 < 0.2 and e4 < e0 * 1e-2
+
+
+def test_ang_positions_and_nside_for_lmax_host_helpers():
+    """cora_b200.hputil helpers that need no device: pixel angles equal the oracle geometry."""
+    from cora_b200 import hputil as bh
+
+    for nside in (1, 2, 8):
+        theta, phi = sht.pix2ang_ring(nside)
+        ang = bh.ang_positions(nside)
+        assert ang.shape == (12 * nside**2, 2)
+        np.testing.assert_allclose(ang[:, 0], theta, atol=1e-14)
+        np.testing.assert_allclose(ang[:, 1], phi, atol=1e-14)
+    assert bh.nside_for_lmax(767) == 512 and bh.nside_for_lmax(95, accuracy_boost=0) == 32
