@@ -351,7 +351,9 @@ def test_complex_field_roundtrip_and_full_size_adjoint():
     old = hputil._iter
     try:
         hputil._iter = 4
-        back = hputil.sphtrans_complex(field, lmax=lmax)
+        # reference quirk (hputil.py:455): almi = +1j (alm - almr) = -a^imag, so sphtrans_inv_complex returns
+        # the complex conjugate of the field whose transform is `alm`; mirrored, not fixed
+        back = hputil.sphtrans_complex(np.conj(field), lmax=lmax)
     finally:
         hputil._iter = old
     assert np.abs(back - full).max() / np.abs(full).max() < 2e-3
