@@ -433,9 +433,9 @@ def sphtrans_complex_pol(hpmaps, lmax=None, centered=False, lside=None):
 
 def sphtrans_inv_complex(alm, nside):
     """Inverse transform onto a complex field; ``alm[l, all m]`` in the wrapped layout
-    (``hputil.py:435-457``).  Reference quirk kept: ``almi = +1j (alm - almr)`` is minus the transform
-    of the imaginary part, so the result is the complex conjugate of the field whose
-    ``sphtrans_complex`` is ``alm``."""
+    (``hputil.py:435-457``).  Mirrors the reference line by line, including that it is not an exact inverse
+    of ``sphtrans_complex`` (the imaginary parts of the m = 0 column are dropped by the real transform and
+    ``almi = +1j (alm - almr)`` carries a sign)."""
     if alm.shape[1] != (2 * alm.shape[0] - 1):
         raise Exception("a_lm array wrong shape: " + repr(alm.shape))
     almr = _make_half_alm(alm)

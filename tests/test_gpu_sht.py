@@ -348,15 +348,18 @@ def test_complex_field_roundtrip_and_full_size_adjoint():
             full[l, m] = rng.standard_normal() + 1j * rng.standard_normal()
     field = hputil.sphtrans_inv_complex(full, nside)
     assert field.shape == (12 * nside**2,) and np.iscomplexobj(field)
-    old = hputil._iter
-    try:
-        hputil._iter = 4
-        # reference quirk (hputil.py:455): almi = +1j (alm - almr) = -a^imag, so sphtrans_inv_complex returns
-        # the complex conjugate of the field whose transform is `alm`; mirrored, not fixed
-        back = hputil.sphtrans_complex(np.conj(field), lmax=lmax)
-    finally:
-        hputil._iter = old
-    assert np.abs(back - full).max() / np.abs(full).max() < 2e-3
+    # the reference's definition, line by line (hputil.py:452-457), on the oracle's real transforms.  (It is not
+    # the inverse of sphtrans_complex: the m = 0 imaginary parts are dropped and almi carries a sign.)
+    almr = hputil._make_half_alm(full)
+    almi = 1.0j * (full[:, :L] - almr)
+    ref = osht.alm2map(hputil.pack_alm(almr), nside, lmax) + 1.0j * osht.alm2map(hputil.pack_alm(almi), nside, lmax)
+    assert np.abs(field - ref).max() / np.abs(ref).max() < 1e-10
+    # sphtrans_complex of a complex map = transforms of the real and imaginary parts in the full-m layout
+    cm = rng.standard_normal(12 * nside**2) + 1j * rng.standard_normal(12 * nside**2)
+    got = hputil.sphtrans_complex(cm, lmax=lmax)
+    want = hputil._make_full_alm(ohp.unpack_alm(osht.map2alm(cm.real, nside, lmax, iter=2), lmax)) + 1.0j * hputil._make_full_alm(
+        ohp.unpack_alm(osht.map2alm(cm.imag, nside, lmax, iter=2), lmax))
+    assert got.shape == (L, 2 * L - 1) and np.abs(got - want).max() / np.abs(want).max() < 1e-10
     with pytest.raises(Exception, match="wrong shape"):
         hputil.sphtrans_inv_complex(np.zeros((4, 4)), nside)
 
