@@ -155,12 +155,34 @@ class ShardedSky(object):
         self.row0 = self.plan.send_row0(rank)
         self._buf = {}
         self.peers = peers
+        requested = exchange
         if exchange == "auto":
             exchange = "p2p" if (size > 1 and (peers is not None or (dist.is_available() and dist.is_initialized()
                                                                       and dist.get_backend(group) == "nccl"))) else "collective"
         self.exchange = exchange if size > 1 else "collective"
         self._p2p = None
         self._k = 0
+        if self.exchange == "p2p" and self.peers is None:
+            # set the peer group up now and make the ranks agree: if any of them cannot map its peers'
+            # memory (no peer access between some pair of GPUs), everybody takes the collective path
+            import torch
+
+            from . import peer as _peer
+
+            ok = 1
+            try:
+                self.peers = _peer.PeerGroup(self.rank, self.size, self.group)
+            except Exception as exc:  # noqa: BLE001 -- any failure means "no p2p here"
+                ok, self._p2p_error = 0, exc
+            flag = torch.tensor([ok], dtype=torch.int32, device=_dev.device())
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                if self.peers is not None and requested != "p2p":
+                    self.peers = None
+                if requested == "p2p":
+                    raise _lib.CoraB200Error("exchange='p2p' requested but peer memory could not be set up on every rank: %r"
+                                             % (getattr(self, "_p2p_error", None),))
+                self.exchange = "collective"
 
     def _persistent(self, name, make):
         """Buffers reused from step to step (no allocator traffic inside a step)."""
@@ -366,6 +388,15 @@ class ShardedSky(object):
         self.p2p_alm(k, seed=seed)
         self.peers.barrier()
         return self.p2p_sht(k, out=out)
+
+    def close(self):
+        """Check the barrier status and release the peer buffers (collective when a real PeerGroup is used)."""
+        if self.exchange == "p2p" and self.peers is not None:
+            self.peers.check()
+            self._p2p = None
+            self._buf = {k: v for k, v in self._buf.items() if not k.startswith(("cla_view", "panel_view"))}
+            self.peers.close()
+            self.peers = None
 
     def step(self, seed=0, out=None):
         if self.exchange == "p2p":
