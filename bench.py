@@ -35,6 +35,7 @@ WORKLOADS = {
     "c1": ("gaussianfg", 64, 32, 800.0, 400.0),
     "c2": ("21cm", 256, 256, 800.0, 400.0),
     "c3": ("21cm", 512, 1024, 800.0, 400.0),
+    "c3fg": ("gaussianfg", 512, 1024, 800.0, 400.0),
     "c4": ("gaussianfg_pol", 512, 1024, 800.0, 400.0),
     "c5": ("21cm", 1024, 2048, 800.0, 400.0),
 }
@@ -42,6 +43,7 @@ WORKLOAD_TEXT = {
     "c1": "cora-makesky gaussianfg nside=64, 32 channels 400-800 MHz, unpolarised",
     "c2": "cora-makesky 21cm (Corr21cm) nside=256, 256 channels 400-800 MHz",
     "c3": "cora-makesky 21cm nside=512, 1024 channels 400-800 MHz",
+    "c3fg": "cora-makesky gaussianfg --pol none nside=512, 1024 channels 400-800 MHz (the foreground half of config 3)",
     "c4": "cora-makesky gaussianfg --pol full (T/E/B, spin-2 SHT) nside=512, 1024 channels 400-800 MHz",
     "c5": "cora-makesky 21cm nside=1024, 2048 channels 400-800 MHz",
 }
