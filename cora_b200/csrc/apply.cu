@@ -98,7 +98,11 @@ __global__ void __launch_bounds__(256, 2) apply_kernel(ApplyParams P) {
     const double* M = P.root + (long long)li * nz * nz;
     const double* Gd = (const double*)(P.G + d.goff);    // rows nu', 2*ld doubles each
     const int gld = 2 * d.ld;
-    const bool tri = P.dense ? (P.dense[li] == 0) : false;
+    // root kind (cora_b200_root_batched's used_eigh): 0 = lower triangular (Cholesky); v >= 1 = dense fallback
+    // root whose first v - 1 columns are zero (clipped modes / beyond the numerical rank): those are skipped
+    const int dflag = P.dense ? P.dense[li] : 1;
+    const bool tri = (dflag == 0);
+    const int kbeg = (dflag > 1) ? (min(dflag - 1, nz) & ~(AP_KC - 1)) : 0;
     const int kend = tri ? min(nz, r0 + AP_TM) : nz;
     const int ncols = 2 * (d.l + 1);                      // valid real columns
 
@@ -112,11 +116,11 @@ __global__ void __launch_bounds__(256, 2) apply_kernel(ApplyParams P) {
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    const int nit = (kend + AP_KC - 1) / AP_KC;
+    const int nit = (kend - kbeg + AP_KC - 1) / AP_KC;
     auto stage_load = [&](int it, int slot) {
         double* As = ap_smem + slot * AP_STAGE_DOUBLES;
         double* Bs = As + AP_TM * AP_ALD;
-        const int k0 = it * AP_KC;
+        const int k0 = kbeg + it * AP_KC;
         if (FAST) {
             // A tile 128 x 16: 1024 pieces of 2 doubles
 #pragma unroll
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(256, 2) apply_kernel(ApplyParams P) {
         // zero blocks are skipped per 8 rows x 4 columns -- warp-uniform tests, bit-identical sums.
         // (Measured alternatives: interleaving the 8-row blocks over the warps to even out the work is slower,
         // 2.02 ms vs 1.75 ms; re-pairing row groups over SM sub-partitions changes nothing.)
-        const int kk0 = it * AP_KC;
+        const int kk0 = kbeg + it * AP_KC;
         const int rw = r0 + wm * 32;                     // first row of this warp's 32
         if (tri && kk0 > rw + 31) continue;              // the whole chunk lies right of this warp's rows
 #pragma unroll

@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
                                                             double* __restrict__ root, int* __restrict__ num_pos,
                                                             double* __restrict__ evals_ws, int* __restrict__ rank_ws,
                                                             const int* __restrict__ nfail_ptr,
-                                                            double* __restrict__ evals_sorted = nullptr) {
+                                                            double* __restrict__ evals_sorted = nullptr,
+                                                            int* __restrict__ used = nullptr) {
     // evals_sorted != nullptr: plain eigen-decomposition (scipy.linalg.eigh layout): column k of `root` is the
     // unit eigenvector of the k-th smallest eigenvalue, evals_sorted[l][k] that eigenvalue; no clipping
     __shared__ double s_max;
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
     if (evals_sorted)
         for (int i = threadIdx.x; i < nz; i += blockDim.x) evals_sorted[(long long)l * nz + rank[i]] = ev[i];
     if (threadIdx.x == 0 && num_pos) num_pos[l] = s_npos;
+    if (threadIdx.x == 0 && used) used[l] = 1 + (nz - s_npos);     // 1 + number of leading zero columns
 }
 
 
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
 __global__ void __launch_bounds__(1024) pchol_kernel(const double* __restrict__ cl, const int* __restrict__ fail_list, int nz,
                                                      double jitter_rel, const double* __restrict__ dmax, double clip_rel,
                                                      double* __restrict__ Lws_all, double* __restrict__ root,
-                                                     int* __restrict__ num_pos, const int* __restrict__ nfail_ptr) {
+                                                     int* __restrict__ num_pos, const int* __restrict__ nfail_ptr,
+                                                     int* __restrict__ used) {
     extern __shared__ __align__(16) double pc_smem[];
     double* d = pc_smem;              // [nz] residual diagonal (-1 once a row has been a pivot)
     double* Lp = d + nz;              // [nz] row p of L
@@ -464,7 +467,10 @@ __global__ void __launch_bounds__(1024) pchol_kernel(const double* __restrict__ 
         const int kk = nz - 1 - c;
         R[e] = (kk < k) ? Lws[(long long)kk * nz + i] : 0.0;
     }
-    if (tid == 0) num_pos[l] = k;
+    if (tid == 0) {
+        num_pos[l] = k;
+        if (used) used[l] = 1 + (nz - k);                          // 1 + number of leading zero columns
+    }
 }
 
 __global__ void root_flags_kernel(const int* __restrict__ fail, int nl, int nz, int* __restrict__ used_eigh,
@@ -576,7 +582,7 @@ extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, do
             const size_t smem = sizeof(double) * 2 * (size_t)nz;
             CB_CUDA(cudaFuncSetAttribute(pchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             pchol_kernel<<<nb, nz >= 512 ? 1024 : 512, smem, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, clip_rel, G, root,
-                                                                   num_pos, guard);
+                                                                   num_pos, guard, used_eigh);
             count_launch();
             CB_LAUNCH_CHECK();
             return 0;
@@ -587,7 +593,8 @@ extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, do
         jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0, guard);
         count_launch();
         CB_LAUNCH_CHECK();
-        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, fail_list + f0, nz, clip_rel, root, num_pos, evals, rank, guard);
+        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, fail_list + f0, nz, clip_rel, root, num_pos, evals, rank, guard, nullptr,
+                                                 used_eigh);
         count_launch();
         CB_LAUNCH_CHECK();
         return 0;

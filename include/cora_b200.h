@@ -146,7 +146,9 @@ int cora_b200_ps_table_21cm_gather(const double* tab, const int* x, const int* y
  * diagonal (cora/core/skysim.py:116-117), try Cholesky (lower), and where a pivot is not
  * positive fall back to a symmetric eigen-decomposition with eigenvalues below
  * clip_rel * max set to zero, root = evecs * sqrt(evals) (cora/util/nputil.py:51-101,
- * truncate=False).  cl / root: [nl][nz][nz].  used_eigh / num_pos: int[nl].
+ * truncate=False).  cl / root: [nl][nz][nz].  used_eigh / num_pos: int[nl]: used_eigh[l] = 0 for a
+ * Cholesky (lower-triangular) root, else 1 + the number of leading all-zero columns of the fallback root
+ * (= 1 + nz - num_pos[l]; the apply kernel skips those columns).
  * workspace: cora_b200_root_workspace_bytes(nl, nz).                                      */
 long long cora_b200_root_workspace_bytes(int nl, int nz);
 int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, double clip_rel,
@@ -178,8 +180,9 @@ int cora_b200_eigh_batched(const double* a, int nl, int nz, double* evecs, doubl
  * cora/util/nputil.py:104-125).
  *   root[nl][nz][nz]   roots in the order of l_list_h
  *   l_list_h[nl]       HOST array: global l of each root (any subset -> l-sharding)
- *   dense_flag[nl]     device int per root: 0 = lower-triangular (Cholesky) so the zero half
- *                      of the contraction is skipped, 1 = dense (eigh); NULL = all dense
+ *   dense_flag[nl]     device int per root (cora_b200_root_batched's used_eigh): 0 = lower-triangular
+ *                      (Cholesky), the zero half of the contraction is skipped; 1 = dense; v > 1 = dense
+ *                      with v - 1 leading zero columns, which are skipped; NULL = all dense
  *   gauss == NULL      draws come from Philox4x32-10 keyed by `seed`, counter (l, m, nu', 0),
  *                      Box-Muller, (N + iN)/sqrt(2)
  *   gauss != NULL      injected draws, complex128 gauss[i][nu'][gauss_ld] (i = position in
