@@ -2,6 +2,7 @@
 fixtures computed by the real reference (tests/golden/make_golden.py)."""
 
 import numpy as np
+import pytest
 
 from conftest import golden
 from oracle import skysim, spectra
@@ -88,3 +89,32 @@ def test_21cm_fixture_planck2018(oracle_corr21cm):
         norm = np.sqrt(np.abs(np.einsum("lii->li", ref)))
         scale = norm[:, :, None] * norm[:, None, :] + 1e-300
         assert np.max(np.abs(cl - ref) / scale) < 1e-12
+
+
+# ---------------------------------------------------------------- reference tests/test_cubicspline.py (LogInterpolater)
+def _log_spline(x, y):
+    from oracle import spectra
+
+    return spectra.LogSpline(np.dstack((x, y))[0])
+
+
+def test_logspline_constant_kat():
+    """tests/test_cubicspline.py:31-48 (LogInterpolater branch): f(x) = 1 inter- and extrapolated."""
+    p = _log_spline(np.arange(1, 8), np.ones(7))
+    assert (p(np.asarray([0.025, 1, 2.5, 4, 5.55, 7.01, 19])) == 1).all()
+
+
+def test_logspline_linear_kat():
+    """tests/test_cubicspline.py:51-71: f(x) = 10 x at and between the knots (and below the first one)."""
+    p = _log_spline(np.arange(1, 5), np.asarray([10, 20, 30, 40]))
+    for x_, want in ((0.5, 5), (1, 10), (1.75, 17.5), (2, 20), (2.2, 22), (3, 30), (4, 40)):
+        assert p(x_) == pytest.approx(want)
+
+
+def test_logspline_random_knots_kat():
+    """tests/test_cubicspline.py:74-85: the spline passes through its knots to 1e-13."""
+    x = np.arange(1, 5)
+    y = np.asarray([1.67, 1.99, 0.465, 0.234])
+    p = _log_spline(x, y)
+    for i, x_ in enumerate(x):
+        assert p(x_) == pytest.approx(y[i], rel=1e-13)
