@@ -1079,25 +1079,26 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_phase_ker
         const int kk = n - k;
         const bool twin = (k != 0 && kk != k);
         if (has1) {
-            // (-1)^q of the aliased copy q (m = k + q n) on shifted rings
+            // (-1)^q of the aliased copy q (m = k + q n) on shifted rings.  The bin and its twin (n - k >= k, so
+            // its copies are a subset of the bin's) are walked together: the four F loads of an iteration are
+            // independent and in flight at once (the fold is load-latency bound: 19 % of the kernel's stall
+            // samples sat on the DFMAs consuming them one bin at a time).
             for (int q = sl; k + q * n <= Q.lmax; q += nsl) {
-                const int m = k + q * n;
+                const int m = k + q * n, m2 = kk + q * n;
+                const bool v2 = twin && (m2 <= Q.lmax);
                 double2 f1 = Fr[m * 4 + c];
                 double2 f2 = has2 ? Fr[m * 4 + c + 1] : make_double2(0, 0);
+                const double2 g1 = v2 ? Fr[m2 * 4 + c] : make_double2(0, 0);
+                const double2 g2 = (v2 && has2) ? Fr[m2 * 4 + c + 1] : make_double2(0, 0);
                 if (m == 0) { f1.y = 0.0; f2.y = 0.0; }
                 double sg = (m == 0) ? 1.0 : 2.0;
                 if (rd.shifted && (q & 1)) sg = -sg;
                 a1.x += sg * f1.x; a1.y += sg * f1.y;
                 a2.x += sg * f2.x; a2.y += sg * f2.y;
-            }
-            if (twin) {
-                for (int q = sl; kk + q * n <= Q.lmax; q += nsl) {
-                    const int m = kk + q * n;
-                    const double2 f1 = Fr[m * 4 + c];
-                    const double2 f2 = has2 ? Fr[m * 4 + c + 1] : make_double2(0, 0);
-                    const double sg = (rd.shifted && (q & 1)) ? -2.0 : 2.0;
-                    b1.x += sg * f1.x; b1.y += sg * f1.y;
-                    b2.x += sg * f2.x; b2.y += sg * f2.y;
+                if (v2) {
+                    const double sg2 = (rd.shifted && (q & 1)) ? -2.0 : 2.0;
+                    b1.x += sg2 * g1.x; b1.y += sg2 * g1.y;
+                    b2.x += sg2 * g2.x; b2.y += sg2 * g2.y;
                 }
             }
         }
