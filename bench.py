@@ -191,6 +191,12 @@ def run_reference(args):
     wp = workload_params(args.workload)
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ncores = min(ncores, 32)
+    try:   # torchrun exports OMP_NUM_THREADS=1 to its workers: give the BLAS legs all host cores anyway
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=ncores)
+    except Exception:
+        pass
     oneoff = cpu_reference_setup(wp)
     pool = mp.get_context("fork").Pool(ncores)
     try:
