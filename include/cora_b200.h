@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - every function returns int: 0 = OK, non-zero = error (text via cora_b200_last_error);
- *     nothing throws, nothing allocates caller-visible memory except the opaque plans;
+ *     nothing throws; the only allocations are the opaque SHT plans, the peer buffers handed out
+ *     by cora_b200_peer_alloc and a small library-owned cache of descriptor tables;
  *   - all data pointers are DEVICE pointers on the current CUDA device unless the name ends
  *     in _h (host); `stream` is a cudaStream_t passed as void*;
  *   - complex numbers are interleaved (re, im) float64 pairs ("complex128");
