@@ -59,6 +59,12 @@ def matrix_root_manynull(mat, threshold=1e-16, truncate=True):
     The eigen branch returns columns in ascending-eigenvalue order; with ``truncate`` only the
     last ``num_pos`` columns are kept and -- reference quirk preserved -- the array then has
     shape ``(1, N, num_pos)`` (``nputil.py:92-96``).
+
+    For matrices larger than 128 x 128 the fallback is a diagonally pivoted Cholesky with the same
+    relative clip instead of an eigen-decomposition (``csrc/root.cu: pchol_kernel``): the result has
+    the same defining property (``root @ root.T == mat`` to the clip, zero columns first, ``num_pos``
+    = numerical rank) but its columns are not eigenvectors.  ``CORA_B200_JACOBI_MAX_NZ`` (environment,
+    read when the library loads) moves the switch, e.g. to force the eigen path everywhere.
     """
     t = _dev.torch()
     mat = np.asarray(mat, dtype=np.float64)
