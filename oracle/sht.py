@@ -384,3 +384,150 @@ def map2alm_spin2(Q, U, nside, lmax=None, iter=3, ring_weights=None):
         aE += dE
         aB += dB
     return aE, aB
+
+
+# ------------------------------------------------------------------- ring subsets at production sizes
+# The per-m routines above loop over l in Python once per m: O(lmax^2) interpreter iterations, minutes at
+# lmax = 3071.  For parity checks of the CUDA transforms at nside 256 / 512 / 1024 the same arithmetic is
+# swept l-major over all m at once for a *subset of rings* (poles, cap/belt boundary, equator): lmax + 1
+# interpreter iterations.  ``lambda_sweep`` performs the operations of ``lambda_lm`` (same seed, same recurrence,
+# same rescaling); the two agree to a few ulp (the seed's log-sum is accumulated in a different order), which
+# tests/test_oracle_sht.py checks together with the ring-subset transforms against the full ones.
+def lambda_sweep(lmax, cth, sth):
+    """Generator over l = 0..lmax yielding ``(l, lam, lam_prev)`` with ``lam[m, ring] = lambda_lm`` and
+    ``lam_prev[m, ring] = lambda_{l-1,m}`` (0 for m >= l) for m = 0..l, at the given rings."""
+    cth = np.asarray(cth, dtype=np.float64)
+    sth = np.asarray(sth, dtype=np.float64)
+    nr = cth.shape[0]
+    ms = np.arange(lmax + 1)
+    k = np.arange(1, lmax + 1, dtype=np.float64)
+    csum = np.concatenate([[0.0], np.cumsum(np.log1p(-1.0 / (2.0 * k)))])
+    logn = 0.5 * (np.log((2 * ms + 1) / (4.0 * np.pi)) + csum)
+    p_cur = np.zeros((lmax + 1, nr))
+    p_prev = np.zeros((lmax + 1, nr))
+    scale = np.zeros((lmax + 1, nr), dtype=np.int64)
+    a_prev = np.ones(lmax + 1)
+    lam_last = np.zeros((0, nr))
+    with np.errstate(divide="ignore"):
+        logs = np.log(sth)
+    for l in range(lmax + 1):
+        if l > 0:
+            m = np.arange(l, dtype=np.float64)
+            a_l = np.sqrt((4.0 * l * l - 1.0) / (l * l - m * m))
+            pc, pp = p_cur[:l], p_prev[:l]
+            p_new = a_l[:, None] * (cth[None, :] * pc - pp / a_prev[:l, None])
+            # row m = l - 1 is the first step of its recurrence: a_l * cth * p_cur exactly (p_prev = 0)
+            p_new[l - 1] = a_l[l - 1] * cth * pc[l - 1]
+            p_prev[:l] = pc
+            p_cur[:l] = p_new
+            a_prev[:l] = a_l
+            big = np.abs(p_cur[:l]) > 2.0**64
+            if big.any():
+                p_cur[:l] = np.where(big, p_cur[:l] * 2.0**-64, p_cur[:l])
+                p_prev[:l] = np.where(big, p_prev[:l] * 2.0**-64, p_prev[:l])
+                scale[:l] = np.where(big, scale[:l] + 64, scale[:l])
+        # seed of row m = l (lambda_mm), exactly as lambda_lm does it
+        if l == 0:
+            p_cur[0] = np.sqrt(1.0 / (4.0 * np.pi))
+            scale[0] = 0
+        else:
+            loglam = logn[l] + l * logs
+            e = np.floor(loglam / np.log(2.0))
+            e = np.where(np.isfinite(e), e, -1e9)
+            mant = np.exp(loglam - e * np.log(2.0)) * (-1.0 if (l & 1) else 1.0)
+            mant = np.where(sth > 0, mant, 0.0)
+            p_cur[l] = mant
+            scale[l] = e.astype(np.int64)
+        lam = np.ldexp(p_cur[: l + 1], np.clip(scale[: l + 1], -100000, 100000).astype(np.int32))
+        prev = np.zeros_like(lam)
+        prev[: lam_last.shape[0]] = lam_last
+        yield l, lam, prev
+        lam_last = lam
+
+
+def _ring_values(Fm, geom, ring_sel):
+    """Phase synthesis of selected rings -> list of arrays (nchan, nph_ring)."""
+    mmax = Fm.shape[0] - 1
+    m = np.arange(mmax + 1)
+    w = np.where(m == 0, 1.0, 2.0)
+    vals = []
+    for a, r in enumerate(ring_sel):
+        nph = int(geom["nph"][r])
+        ph = w * np.exp(1j * m * geom["phi0"][r])
+        G = np.zeros((nph, Fm.shape[2]), dtype=np.complex128)
+        np.add.at(G, m % nph, Fm[:, a, :] * ph[:, None])
+        vals.append((np.fft.ifft(G, axis=0).real * nph).T)
+    return vals
+
+
+def alm2map_rings(alm, nside, lmax, ring_sel):
+    """Scalar synthesis (same definition as ``alm2map``) evaluated only on the rings ``ring_sel`` (0-based
+    ring numbers, north to south).  Returns ``(vals, start)``: ``vals[k]`` is ``(nchan, nph)`` for ring
+    ``ring_sel[k]``, ``start[k]`` its first RING pixel."""
+    alm = np.atleast_2d(np.asarray(alm, dtype=np.complex128))
+    nchan = alm.shape[0]
+    g = ring_geometry(nside)
+    rs = np.asarray(ring_sel, dtype=np.int64)
+    Fm = np.zeros((lmax + 1, len(rs), nchan), dtype=np.complex128)
+    mall = np.arange(lmax + 1)
+    for l, lam, _ in lambda_sweep(lmax, g["cth"][rs], g["sth"][rs]):
+        a = alm[:, alm_index(lmax, l, mall[: l + 1])].T.copy()     # (l+1, nchan)
+        a[0] = a[0].real
+        Fm[: l + 1] += lam[:, :, None] * a[:, None, :]
+    return _ring_values(Fm, g, rs), g["start"][rs]
+
+
+def alm2map_spin2_rings(almE, almB, nside, lmax, ring_sel):
+    """(E, B) -> (Q, U) (same definition as ``alm2map_spin2``) on the rings ``ring_sel``."""
+    almE = np.atleast_2d(np.asarray(almE, dtype=np.complex128))
+    almB = np.atleast_2d(np.asarray(almB, dtype=np.complex128))
+    nchan = almE.shape[0]
+    g = ring_geometry(nside)
+    rs = np.asarray(ring_sel, dtype=np.int64)
+    c, s = g["cth"][rs], g["sth"][rs]
+    s2 = s * s
+    FQ = np.zeros((lmax + 1, len(rs), nchan), dtype=np.complex128)
+    FU = np.zeros_like(FQ)
+    mall = np.arange(lmax + 1)
+    for l, lam, lam_prev in lambda_sweep(lmax, c, s):
+        if l < 2:
+            continue
+        m = mall[: l + 1].astype(np.float64)
+        nl = 1.0 / np.sqrt((l + 2.0) * (l + 1.0) * l * (l - 1.0))
+        glm = np.sqrt((2.0 * l + 1) / (2.0 * l - 1) * (l * l - m * m))
+        X1 = (2 * nl) * (-((l - m * m)[:, None] / s2[None, :] + (l * (l - 1) / 2.0)) * lam
+                         + (c / s2)[None, :] * glm[:, None] * lam_prev)
+        X2 = (2 * nl) * (m[:, None] / s2[None, :]) * (-(l - 1.0) * c[None, :] * lam + glm[:, None] * lam_prev)
+        idx = alm_index(lmax, l, mall[: l + 1])
+        aE, aB = almE[:, idx].T.copy(), almB[:, idx].T.copy()
+        aE[0], aB[0] = aE[0].real, aB[0].real
+        FQ[: l + 1] += -(X1[:, :, None] * aE[:, None, :] + 1j * (X2[:, :, None] * aB[:, None, :]))
+        FU[: l + 1] += -(X1[:, :, None] * aB[:, None, :] - 1j * (X2[:, :, None] * aE[:, None, :]))
+    return _ring_values(FQ, g, rs), _ring_values(FU, g, rs), g["start"][rs]
+
+
+def map2alm_adjoint_ms(maps, nside, lmax, ms, ring_weights=None):
+    """One quadrature pass (``map2alm_adjoint``) for the selected m only: dict m -> (nchan, lmax - m + 1)."""
+    maps = np.atleast_2d(np.asarray(maps, dtype=np.float64))
+    g = ring_geometry(nside)
+    nring = 4 * nside - 1
+    wgt = _full_ring_weights(nside, ring_weights)
+    ms = [int(m) for m in ms]
+    F = {m: np.zeros((nring, maps.shape[0]), dtype=np.complex128) for m in ms}
+    for r in range(nring):
+        nph, start = int(g["nph"][r]), int(g["start"][r])
+        G = np.fft.fft(maps[:, start : start + nph], axis=1)
+        for m in ms:
+            F[m][r] = G[:, m % nph] * (wgt[r] * np.exp(-1j * m * g["phi0"][r]))
+    return {m: (lambda_lm(lmax, m, g["cth"], g["sth"]) @ F[m]).T for m in ms}
+
+
+def parity_rings(nside, n_extra=12, seed=0):
+    """Ring subset for production-size parity checks: both poles, the cap/belt boundaries, the equator
+    and a few random rings (0-based ring numbers)."""
+    n = int(nside)
+    base = [0, 1, 2, 3, n // 2, n - 3, n - 2, n - 1, n, n + 1, 2 * n - 3, 2 * n - 2, 2 * n - 1, 2 * n, 2 * n + 1,
+            3 * n - 3, 3 * n - 2, 3 * n - 1, 3 * n, 3 * n + 1, 4 * n - 5, 4 * n - 4, 4 * n - 3, 4 * n - 2]
+    rng = np.random.default_rng(seed)
+    extra = rng.integers(0, 4 * n - 1, size=n_extra).tolist()
+    return np.array(sorted({r for r in base + extra if 0 <= r < 4 * n - 1}), dtype=np.int64)

@@ -230,5 +230,36 @@ def main():
             print("  %-24s %8d B" % (f, os.path.getsize(os.path.join(HERE, f))))
 
 
+def extra_c2rows():
+    """Config 2's channel axis (256 channels, lmax 767) at 8 l rows through the reference's own ``clarray`` and
+    ``Corr21cm.angular_powerspectrum``: the spectrum is wrapped so that l index i evaluates l = rows[i] (clarray's
+    per-l results do not depend on its l-sectioning).  Stored: every 16th channel row (+ the last)."""
+    build_reference()
+    install_shims()
+    from cora.core import skysim
+    from cora.signal import corr21cm
+
+    rows = np.array([0, 1, 2, 5, 100, 383, 766, 767])
+    cr = corr21cm.Corr21cm()
+    freq = np.linspace(800.0, 400.0, 256, endpoint=False)
+
+    def aps(l, z1, z2):
+        return cr.angular_powerspectrum(rows[np.asarray(l)].astype(np.float64), z1, z2)
+
+    cl = skysim.clarray(aps, len(rows) - 1, freq)
+    chan_rows = np.unique(np.append(np.arange(0, 256, 16), 255))
+    np.savez(os.path.join(HERE, "cl_21cm_c2rows.npz"), rows=rows, freq=freq, chan_rows=chan_rows,
+             cl_rows=cl[:, chan_rows, :])
+    print("cl_21cm_c2rows.npz written")
+
+
 if __name__ == "__main__":
-    main()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "all":
+        main()
+    elif what == "c2rows":
+        extra_c2rows()
+    elif what == "root_large":
+        extra_root_large()
+    else:
+        raise SystemExit("usage: make_golden.py [all|c2rows|root_large]")

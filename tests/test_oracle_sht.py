@@ -7,6 +7,7 @@ import pytest
 from scipy.special import sph_harm_y
 
 from oracle import sht
+from oracle import sht as osht
 
 
 def test_ring_geometry_basic():
@@ -267,3 +268,38 @@ def test_ang_positions_and_nside_for_lmax_host_helpers():
         np.testing.assert_allclose(ang[:, 0], theta, atol=1e-14)
         np.testing.assert_allclose(ang[:, 1], phi, atol=1e-14)
     assert bh.nside_for_lmax(767) == 512 and bh.nside_for_lmax(95, accuracy_boost=0) == 32
+
+
+# ---------------------------------------------------------------- ring-subset routines (production-size parity helpers)
+def test_lambda_sweep_matches_lambda_lm():
+    nside, lmax = 16, 47
+    g = osht.ring_geometry(nside)
+    rs = osht.parity_rings(nside)
+    ref = {m: osht.lambda_lm(lmax, m, g["cth"][rs], g["sth"][rs]) for m in range(lmax + 1)}
+    for l, lam, prev in osht.lambda_sweep(lmax, g["cth"][rs], g["sth"][rs]):
+        want = np.array([ref[m][l - m] for m in range(l + 1)])
+        np.testing.assert_allclose(lam, want, rtol=1e-13, atol=1e-14)   # lambda = O(1); near its zeros only the absolute error is meaningful
+        if l:
+            wprev = np.array([ref[m][l - 1 - m] if m < l else np.zeros(len(rs)) for m in range(l + 1)])
+            np.testing.assert_allclose(prev, wprev, rtol=1e-13, atol=1e-14)
+
+
+def test_ring_subset_transforms_match_full():
+    nside, lmax = 16, 47
+    rng = np.random.default_rng(1)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    aE = rng.standard_normal((3, nalm)) + 1j * rng.standard_normal((3, nalm))
+    aB = rng.standard_normal((3, nalm)) + 1j * rng.standard_normal((3, nalm))
+    rs = osht.parity_rings(nside)
+    full = osht.alm2map(aE, nside, lmax)
+    vals, start = osht.alm2map_rings(aE, nside, lmax, rs)
+    for v, s in zip(vals, start):
+        np.testing.assert_allclose(v, full[:, s : s + v.shape[1]], atol=1e-12 * np.abs(full).max())
+    Q, U = osht.alm2map_spin2(aE, aB, nside, lmax)
+    vq, vu, start = osht.alm2map_spin2_rings(aE, aB, nside, lmax, rs)
+    for q, u, s in zip(vq, vu, start):
+        np.testing.assert_allclose(q, Q[:, s : s + q.shape[1]], atol=1e-12 * np.abs(Q).max())
+        np.testing.assert_allclose(u, U[:, s : s + u.shape[1]], atol=1e-12 * np.abs(U).max())
+    ad = osht.map2alm_adjoint(full, nside, lmax)
+    for m, v in osht.map2alm_adjoint_ms(full, nside, lmax, [0, 5, 47]).items():
+        np.testing.assert_array_equal(v, ad[:, osht.alm_index(lmax, m, m) : osht.alm_index(lmax, lmax, m) + 1])

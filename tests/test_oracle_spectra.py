@@ -118,3 +118,21 @@ def test_logspline_random_knots_kat():
     p = _log_spline(x, y)
     for i, x_ in enumerate(x):
         assert p(x_) == pytest.approx(y[i], rel=1e-13)
+
+
+def test_oracle_21cm_clarray_config2_rows_vs_reference(oracle_corr21cm):
+    """The oracle against the real reference at config 2's channel axis (256 channels, 8 l rows;
+    tests/golden/make_golden.py c2rows)."""
+    from conftest import golden
+    from oracle import skysim as osk
+
+    g = golden("cl_21cm_c2rows.npz")
+    rows = g["rows"]
+
+    def aps(l, z1, z2):
+        return oracle_corr21cm.angular_powerspectrum(rows[np.asarray(l)].astype(np.float64), z1, z2)
+
+    cl = osk.clarray(aps, len(rows) - 1, g["freq"])
+    d = np.sqrt(np.abs(np.einsum("lii->li", cl)))
+    scale = d[:, g["chan_rows"], None] * d[:, None, :] + 1e-300
+    assert np.max(np.abs(cl[:, g["chan_rows"], :] - g["cl_rows"]) / scale) < 1e-12
