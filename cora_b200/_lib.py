@@ -59,13 +59,14 @@ SIGNATURES = {
     "cora_b200_peer_free": (_i, [_vp]),
     "cora_b200_peer_open": (_i, [_c.c_char_p, _c.POINTER(_vp)]),
     "cora_b200_peer_close": (_i, [_vp]),
-    "cora_b200_peer_barrier": (_i, [_vp, _i, _i, _ull, _d, _vp, _vp]),
+    "cora_b200_peer_barrier": (_i, [_vp, _i, _i, _ull, _d, _vp, _i, _vp]),
     "cora_b200_cl_fill_21cm_pairs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _vp, _vp, _vp, _vp]),
     "cora_b200_draw_apply_peers": (_i, [_vp, _vp, _vp, _i, _i, _i, _ull, _i, _vp, _ll, _vp, _vp, _vp, _ll, _vp]),
     "cora_b200_alm2map_strided": (_i, [_vp, _vp, _i, _ll, _i, _vp, _ll, _vp, _ll, _vp]),
     "cora_b200_alm2map_spin2_strided": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
     "cora_b200_diag_max": (_i, [_vp, _i, _i, _vp, _i, _vp]),
-    "cora_b200_root_batched_block": (_i, [_vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "cora_b200_root_multi_workspace_bytes": (_ll, [_i, _i, _i]),
+    "cora_b200_root_batched_multi": (_i, [_vp, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
 }
 
 _lib = None

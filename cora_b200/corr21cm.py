@@ -181,6 +181,10 @@ class Corr21cm(maps.Sky3d):
         vec = _dev.to_device(self._sample_vectors(z), t.float64)  # [5, nz*zint]
         return self.table(), vec, _dev.to_device(w, t.float64)
 
+    # skysim.clarray takes the fused kernel only while these methods are the ones defined here (T_b, bias_z,
+    # growth_* and the cosmology enter through _sample_vectors and may be overridden freely, e.g. EoR21cm)
+    _b200_fill_methods = ("angular_powerspectrum", "_b200_fill", "_b200_fill_inputs", "_sample_vectors")
+
     def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None):
         tab, vec, wd = inputs
         _lib.call("cora_b200_cl_fill_21cm", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
@@ -194,6 +198,9 @@ class Corr21cm(maps.Sky3d):
         _lib.call("cora_b200_cl_fill_21cm_pairs", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
                   _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(nl), int(nz), int(zint), int(pair0), int(npairs),
                   _lib.ptr(out_ptrs), _lib.ptr(l_owner), _lib.ptr(l_row), _lib.stream_ptr(stream))
+
+
+Corr21cm._b200_fill_origin = Corr21cm
 
 
 class EoR21cm(Corr21cm):

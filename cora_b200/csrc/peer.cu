@@ -13,8 +13,12 @@ namespace cb {
 //   epoch     : strictly increasing barrier number (1, 2, ...)
 // All stores of earlier kernels on this stream are complete at kernel entry (stream order); the
 // system fence + release store publishes them to the peer before it observes the flag.
+// A peer that does not arrive within timeout_s: *status = 1 + its rank (sticky), and -- unless fatal == 0 --
+// the kernel traps: the kernels queued behind the barrier would otherwise read buffers the slow peer
+// has not finished writing and hand back wrong maps without any error.  After the trap every later CUDA
+// call of the process fails loudly.
 __global__ void peer_barrier_kernel(unsigned long long* const* __restrict__ flags, int rank, int size,
-                                    unsigned long long epoch, double timeout_s, int* __restrict__ status) {
+                                    unsigned long long epoch, double timeout_s, int* __restrict__ status, int fatal) {
     const int i = threadIdx.x;
     if (i >= size) return;
     __threadfence_system();
@@ -28,7 +32,12 @@ __global__ void peer_barrier_kernel(unsigned long long* const* __restrict__ flag
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(mine) : "memory");
         if (v >= epoch) break;
         asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
-        if (t1 - t0 > limit) { atomicExch(status, 1 + i); break; }   // a peer never arrived: report, do not hang
+        if (t1 - t0 > limit) {                                        // a peer never arrived: report, do not hang
+            atomicExch(status, 1 + i);
+            __threadfence_system();
+            if (fatal) __trap();
+            break;
+        }
         __nanosleep(200);
     }
     __threadfence_system();
@@ -77,11 +86,11 @@ extern "C" int cora_b200_peer_close(void* ptr) {
 }
 
 extern "C" int cora_b200_peer_barrier(const void* flags_ptrs, int rank, int size, unsigned long long epoch,
-                                      double timeout_s, int* status, void* stream) {
+                                      double timeout_s, int* status, int fatal, void* stream) {
     CB_REQUIRE(flags_ptrs && status && size >= 1 && size <= 1024 && rank >= 0 && rank < size && epoch > 0, 1,
                "peer_barrier: bad arguments");
     peer_barrier_kernel<<<1, ((size + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(
-        (unsigned long long* const*)flags_ptrs, rank, size, epoch, timeout_s > 0 ? timeout_s : 20.0, status);
+        (unsigned long long* const*)flags_ptrs, rank, size, epoch, timeout_s > 0 ? timeout_s : 60.0, status, fatal);
     count_launch();
     CB_LAUNCH_CHECK();
     return 0;

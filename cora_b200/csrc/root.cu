@@ -217,24 +217,59 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restr
     if (tid == 0) fail[blockIdx.x] = s_fail;
 }
 
-// ----------------------------------------------------------------- Jacobi fallback
-// G (rows) starts as the symmetrised jittered matrix; V starts as identity.  Rotating rows
-// p,q of both by the same plane rotation until all rows of G are mutually orthogonal gives
-// G = diag(lambda) V, rows of V the eigenvectors.  Round-robin ordering, one warp per pair.
-__global__ void jacobi_init_kernel(const double* __restrict__ cl, const int* __restrict__ fail_list, int nz,
-                                   double jitter_rel, const double* __restrict__ dmax, double* __restrict__ G,
-                                   double* __restrict__ V, const int* __restrict__ nfail_ptr) {
-    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;   // device-side count: no host round trip
-    const int l = fail_list[blockIdx.x];
-    const long long src = (long long)l * nz * nz, dst = (long long)blockIdx.x * nz * nz;
-    const double cmax = dmax[l] * jitter_rel;
-    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
-        const int r = (int)(e / nz), c = (int)(e % nz);
-        // LAPACK eigh(lower=True) reads the lower triangle only
-        const double v = (c <= r) ? cl[src + e] : cl[src + (long long)c * nz + r];
-        G[dst + e] = v + (r == c ? cmax : 0.0);
-        V[dst + e] = (r == c) ? 1.0 : 0.0;
-    }
+// ================================================================= eigen fallback
+// Reference semantics (cora/util/nputil.py:86-96): eigh of the jittered matrix, eigenvalues below
+// clip_rel * (largest eigenvalue) set to zero, root = evecs sqrt(evals), every column kept, ascending
+// eigenvalue order (so the zeroed columns come first).  For the block-diagonal polarised covariance of
+// cora/scripts/makesky.py:368-382 the jitter, the Cholesky-or-eigh decision and the clip threshold are
+// those of the WHOLE matrix: blocks of one l share a slot group, `eig_max[l]` is the maximum over blocks.
+//
+// Two implementations of the same definition:
+//  * exact: one-sided (Hestenes) Jacobi on the full nz x nz matrix (below) -- always for nz <= g_jacobi_max_nz,
+//    and for any matrix the low-rank route cannot certify;
+//  * low-rank (nz > g_jacobi_max_nz): the matrices that fail Cholesky are numerically rank-deficient covariances
+//    (the smooth foreground spectra keep ~10-60 of 1024 modes above the clip).  A = L L^T by diagonally pivoted
+//    Cholesky of the UN-jittered matrix down to the jitter level, the residual A - L L^T is verified to be at
+//    that level element by element, the r columns of L are orthogonalised by one-sided Jacobi (L W = U,
+//    eigenvalues lambda_k = |u_k|^2 of A to high relative accuracy), and the eigenpairs of the jittered matrix
+//    are (lambda_k + c, u_k / |u_k|); the remaining nz - r eigenvalues equal c (+ the certified residual) and
+//    are clipped because the route is only taken when c < clip threshold.  O(nz^2 r) instead of O(nz^3 sweeps).
+constexpr int MAXB = 8;
+struct RootBlocks {
+    const double* cl[MAXB];
+    double* root[MAXB];
+    int nb;
+};
+
+struct WaveCtx {
+    const int* fail_list;    // already offset by f0
+    const int* nfail_ptr;    // device count of failed l (NULL: every slot group of the wave is live)
+    int f0;
+    int nl;                  // per-block stride of used / num_pos
+    int nz;
+    double jitter_rel, clip_rel;
+    const double* dmax;      // [nl] global diagonal maximum
+    double* eig_max;         // [nl] global maximum eigenvalue of the jittered matrix (atomic max)
+    double* slots;           // per slot: G / L^T (nz^2 doubles) then V (nz^2 doubles)
+    double* evals;           // [slot][nz]
+    int* rank;               // [slot][nz]
+    int* lr_rank;            // [slot]
+    int* status;             // [slot] 0 = low-rank route holds the decomposition, 1 = exact Jacobi
+    int* sweeps;             // [slot]
+};
+
+// slot -> (l, block); false if the slot is beyond the device-side failure count
+__device__ __forceinline__ bool wave_slot(const WaveCtx& w, int nb, int slot, int& l, int& b) {
+    const int wi = slot / nb;
+    b = slot - wi * nb;
+    if (w.nfail_ptr && w.f0 + wi >= *w.nfail_ptr) return false;
+    l = w.fail_list[wi];
+    return true;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    // for non-negative doubles the IEEE bit pattern orders like the unsigned integer
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(fmax(v, 0.0)));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -243,27 +278,37 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall, double* __restrict__ Vall, int nz,
-                                                      int max_sweeps, int* __restrict__ sweeps_out,
-                                                      const int* __restrict__ nfail_ptr) {
-    __shared__ int s_rot;
-    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
-    double* G = Gall + (long long)blockIdx.x * nz * nz;
-    double* V = Vall + (long long)blockIdx.x * nz * nz;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int npl = nz + (nz & 1);          // players in the round-robin (pad to even)
-    const int nsteps = npl - 1, npairs = npl / 2;
-    {   // an all-zero matrix (C_0 of the l^-beta foreground spectra) is already diagonal: skip the sweep
-        int nonzero = 0;
-        for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) nonzero |= (G[e] != 0.0);
-        if (!__syncthreads_or(nonzero)) {
-            if (threadIdx.x == 0) sweeps_out[blockIdx.x] = 0;
-            return;
-        }
+// ----------------------------------------------------------------- exact: full Jacobi
+// G (rows) starts as the symmetrised jittered matrix; V starts as identity.  Rotating rows
+// p,q of both by the same plane rotation until all rows of G are mutually orthogonal gives
+// G = diag(lambda) V, rows of V the eigenvectors.  Round-robin ordering, one warp per pair.
+__global__ void jacobi_init_kernel(RootBlocks B, WaveCtx w) {
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b) || w.status[blockIdx.x] != 1) return;
+    const int nz = w.nz;
+    const double* cl = B.cl[b];
+    const long long src = (long long)l * nz * nz;
+    double* G = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    double* V = G + (long long)nz * nz;
+    const double cmax = w.dmax[l] * w.jitter_rel;
+    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
+        const int r = (int)(e / nz), c = (int)(e % nz);
+        // LAPACK eigh(lower=True) reads the lower triangle only
+        const double v = (c <= r) ? cl[src + e] : cl[src + (long long)c * nz + r];
+        G[e] = v + (r == c ? cmax : 0.0);
+        V[e] = (r == c) ? 1.0 : 0.0;
     }
+}
+
+// One-sided Jacobi on `nrow` rows of length `len` (G), optionally carrying V (same shape) along.
+// Returns the number of sweeps.  All threads of the CTA call it.
+__device__ int hestenes_sweeps(double* __restrict__ G, double* __restrict__ V, int nrow, int len, int max_sweeps, int* s_rot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int npl = nrow + (nrow & 1);          // players in the round-robin (pad to even)
+    const int nsteps = npl - 1, npairs = npl / 2;
     int sweep = 0;
     for (; sweep < max_sweeps; sweep++) {
-        if (threadIdx.x == 0) s_rot = 0;
+        if (threadIdx.x == 0) *s_rot = 0;
         __syncthreads();
         for (int step = 0; step < nsteps; step++) {
             for (int pi = warp; pi < npairs; pi += nwarp) {
@@ -271,11 +316,11 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall,
                 int a = (pi == 0) ? npl - 1 : (step + pi) % (npl - 1);
                 int b = (step + npl - 1 - pi) % (npl - 1);
                 int p = min(a, b), q = max(a, b);
-                if (q >= nz) continue;   // bye
-                double* gp = G + (long long)p * nz;
-                double* gq = G + (long long)q * nz;
+                if (q >= nrow) continue;   // bye
+                double* gp = G + (long long)p * len;
+                double* gq = G + (long long)q * len;
                 double app = 0, aqq = 0, apq = 0;
-                for (int c = lane; c < nz; c += 32) {
+                for (int c = lane; c < len; c += 32) {
                     const double x = gp[c], y = gq[c];
                     app = fma(x, x, app); aqq = fma(y, y, aqq); apq = fma(x, y, apq);
                 }
@@ -284,63 +329,95 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(double* __restrict__ Gall,
                 const double zeta = (aqq - app) / (2.0 * apq);
                 const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                 const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                for (int c = lane; c < nz; c += 32) {
+                for (int c = lane; c < len; c += 32) {
                     const double x = gp[c], y = gq[c];
                     gp[c] = cs * x - sn * y;
                     gq[c] = sn * x + cs * y;
                 }
-                double* vp = V + (long long)p * nz;
-                double* vq = V + (long long)q * nz;
-                for (int c = lane; c < nz; c += 32) {
-                    const double x = vp[c], y = vq[c];
-                    vp[c] = cs * x - sn * y;
-                    vq[c] = sn * x + cs * y;
+                if (V) {
+                    double* vp = V + (long long)p * len;
+                    double* vq = V + (long long)q * len;
+                    for (int c = lane; c < len; c += 32) {
+                        const double x = vp[c], y = vq[c];
+                        vp[c] = cs * x - sn * y;
+                        vq[c] = sn * x + cs * y;
+                    }
                 }
-                if (lane == 0) s_rot = 1;
+                if (lane == 0) *s_rot = 1;
             }
             __syncthreads();
         }
-        const int any = s_rot;
+        const int any = *s_rot;
         __syncthreads();
         if (!any) break;
     }
-    if (threadIdx.x == 0) sweeps_out[blockIdx.x] = sweep;
+    return sweep;
 }
 
-// eigenvalues lambda_i = v_i . g_i, clip, sort ascending, write root[:, rank] = v_i sqrt(lambda_i)
-__global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __restrict__ Gall, const double* __restrict__ Vall,
-                                                            const int* __restrict__ fail_list, int nz, double clip_rel,
-                                                            double* __restrict__ root, int* __restrict__ num_pos,
-                                                            double* __restrict__ evals_ws, int* __restrict__ rank_ws,
-                                                            const int* __restrict__ nfail_ptr,
-                                                            double* __restrict__ evals_sorted = nullptr,
-                                                            int* __restrict__ used = nullptr) {
-    // evals_sorted != nullptr: plain eigen-decomposition (scipy.linalg.eigh layout): column k of `root` is the
-    // unit eigenvector of the k-th smallest eigenvalue, evals_sorted[l][k] that eigenvalue; no clipping
-    __shared__ double s_max;
-    __shared__ int s_npos;
-    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
-    const int l = fail_list[blockIdx.x];
-    const double* G = Gall + (long long)blockIdx.x * nz * nz;
-    const double* V = Vall + (long long)blockIdx.x * nz * nz;
-    double* ev = evals_ws + (long long)blockIdx.x * nz;
-    int* rank = rank_ws + (long long)blockIdx.x * nz;
+__global__ void __launch_bounds__(1024) jacobi_kernel(RootBlocks B, WaveCtx w, int max_sweeps) {
+    __shared__ int s_rot;
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b) || w.status[blockIdx.x] != 1) return;
+    const int nz = w.nz;
+    double* G = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    double* V = G + (long long)nz * nz;
+    {   // a diagonal matrix (all-zero C_0 of the l^-beta foreground spectra, jitter only) needs no sweep
+        int offdiag = 0;
+        for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x)
+            offdiag |= (G[e] != 0.0) && (e / nz != e % nz);
+        if (!__syncthreads_or(offdiag)) {
+            if (threadIdx.x == 0) w.sweeps[blockIdx.x] = 0;
+            return;
+        }
+    }
+    const int sweep = hestenes_sweeps(G, V, nz, nz, max_sweeps, &s_rot);
+    if (threadIdx.x == 0) w.sweeps[blockIdx.x] = sweep;
+}
+
+// eigenvalues lambda_i = v_i . g_i of an exact-route slot; the largest goes into eig_max[l]
+__global__ void __launch_bounds__(256) jacobi_evals_kernel(RootBlocks B, WaveCtx w) {
+    __shared__ double s_red[8];
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b) || w.status[blockIdx.x] != 1) return;
+    const int nz = w.nz;
+    const double* G = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    const double* V = G + (long long)nz * nz;
+    double* ev = w.evals + (long long)blockIdx.x * nz;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double mx = 0.0;
     for (int i = warp; i < nz; i += nwarp) {
         double s = 0.0;
         for (int c = lane; c < nz; c += 32) s = fma(V[(long long)i * nz + c], G[(long long)i * nz + c], s);
         s = warp_sum(s);
         if (lane == 0) ev[i] = s;
+        mx = fmax(mx, s);
     }
+    if (lane == 0) s_red[warp] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double mx = -1.0e308;
-        for (int i = 0; i < nz; i++) mx = fmax(mx, ev[i]);
-        s_max = mx;
-        s_npos = 0;
+        for (int k = 1; k < nwarp; k++) mx = fmax(mx, s_red[k]);
+        atomic_max_nonneg(w.eig_max + l, mx);
     }
+}
+
+// clip against the global maximum, sort ascending, write root[:, rank] = v_i sqrt(lambda_i)
+__global__ void __launch_bounds__(256) jacobi_finish_kernel(RootBlocks B, WaveCtx w, int* __restrict__ num_pos,
+                                                            int* __restrict__ used,
+                                                            double* __restrict__ evals_sorted = nullptr) {
+    // evals_sorted != nullptr: plain eigen-decomposition (scipy.linalg.eigh layout): column k of `root` is the
+    // unit eigenvector of the k-th smallest eigenvalue, evals_sorted[l][k] that eigenvalue; no clipping
+    __shared__ int s_npos;
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b) || w.status[blockIdx.x] != 1) return;
+    const int nz = w.nz;
+    const double* G = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    const double* V = G + (long long)nz * nz;
+    (void)G;
+    const double* ev = w.evals + (long long)blockIdx.x * nz;
+    int* rank = w.rank + (long long)blockIdx.x * nz;
+    if (threadIdx.x == 0) s_npos = 0;
     __syncthreads();
-    const double thr = s_max * clip_rel;
+    const double thr = w.eig_max[l] * w.clip_rel;
     // rank of each eigenvalue in ascending order (ties broken by index)
     for (int i = threadIdx.x; i < nz; i += blockDim.x) {
         const double vi = ev[i];
@@ -353,7 +430,7 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
         if (!(vi < thr) && vi != 0.0) atomicAdd(&s_npos, 1);
     }
     __syncthreads();
-    double* R = root + (long long)l * nz * nz;
+    double* R = B.root[b] + (long long)l * nz * nz;
     for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
         const int i = (int)(e / nz), r = (int)(e % nz);     // eigenpair i, row r of the root
         const double lam = ev[i];
@@ -362,54 +439,49 @@ __global__ void __launch_bounds__(256) jacobi_finish_kernel(const double* __rest
     }
     if (evals_sorted)
         for (int i = threadIdx.x; i < nz; i += blockDim.x) evals_sorted[(long long)l * nz + rank[i]] = ev[i];
-    if (threadIdx.x == 0 && num_pos) num_pos[l] = s_npos;
-    if (threadIdx.x == 0 && used) used[l] = 1 + (nz - s_npos);     // 1 + number of leading zero columns
+    if (threadIdx.x == 0 && num_pos) num_pos[(long long)b * w.nl + l] = s_npos;
+    if (threadIdx.x == 0 && used) used[(long long)b * w.nl + l] = 1 + (nz - s_npos);     // 1 + number of leading zero columns
 }
 
-
-// ----------------------------------------------------------------- pivoted-Cholesky fallback
-// For large matrices the Jacobi eigen fallback is hopeless (11 s for one 1024^2 matrix: every
-// rotation streams whole rows through L2), while the matrices that need a fallback are the
-// numerically rank-deficient foreground covariances (rank ~50 of 1024).  A diagonally pivoted
-// Cholesky with the reference's relative clip gives a root with the same defining property,
-// M M^T = C + jitter to within clip_rel * trace element-wise, in O(nz^2 rank):
-//   p = argmax d;  stop when d[p] <= clip_rel * trace;  L[:,k] = (A[:,p] - L[:, :k] L[p, :k]^T) / sqrt(d[p]);
-//   d -= L[:,k]^2.
-// Columns are stored like the eigen branch stores its own: discarded (zero) columns first, the
-// retained ones last with the strongest in the last column; num_pos = rank.  One CTA per matrix.
-// Lws: [slot][k][i] (column k of L contiguous in i).
-__global__ void __launch_bounds__(1024) pchol_kernel(const double* __restrict__ cl, const int* __restrict__ fail_list, int nz,
-                                                     double jitter_rel, const double* __restrict__ dmax, double clip_rel,
-                                                     double* __restrict__ Lws_all, double* __restrict__ root,
-                                                     int* __restrict__ num_pos, const int* __restrict__ nfail_ptr,
-                                                     int* __restrict__ used) {
+// ----------------------------------------------------------------- low-rank route, step 1: pivoted Cholesky
+//   p = argmax d;  stop when d[p] <= tau;  L[:,k] = (A[:,p] - L[:, :k] L[p, :k]^T) / sqrt(d[p]);  d -= L[:,k]^2
+// tau = max(jitter / 4, 32 eps max(diag)): the jitter level when there is one (everything below it is clipped
+// together with the jitter itself), else the round-off level of the matrix entries.  Then the certificate:
+// max |A - L L^T| over the lower triangle (what LAPACK reads) must be <= 4 tau + 64 eps max(diag) -- true for
+// a positive semi-definite residual with diagonal <= tau; a matrix with a significant negative eigenvalue
+// fails it and is handed to the exact route (status 1).
+// L^T is stored in the slot's first nz^2 doubles as [k][i] (column k of L contiguous in i).
+__global__ void __launch_bounds__(1024) lr_pchol_kernel(RootBlocks B, WaveCtx w) {
     extern __shared__ __align__(16) double pc_smem[];
+    const int nz = w.nz;
     double* d = pc_smem;              // [nz] residual diagonal (-1 once a row has been a pivot)
     double* Lp = d + nz;              // [nz] row p of L
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
-    __shared__ double s_piv, s_tau;
+    __shared__ double s_piv, s_tau, s_dmax;
     __shared__ int s_p;
-    if (nfail_ptr && (int)blockIdx.x >= *nfail_ptr) return;
-    const int l = fail_list[blockIdx.x];
-    const double* A = cl + (long long)l * nz * nz;
-    double* Lws = Lws_all + (long long)blockIdx.x * nz * nz;
-    const double cmax = dmax[l] * jitter_rel;
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b)) return;
+    const double* A = B.cl[b] + (long long)l * nz * nz;
+    double* Lws = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    const double cmax = w.dmax[l] * w.jitter_rel;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
 
-    double tr = 0.0;
+    double mx = 0.0;
     for (int i = tid; i < nz; i += blockDim.x) {
-        const double v = A[(long long)i * nz + i] + cmax;
+        const double v = A[(long long)i * nz + i];
         d[i] = v;
-        tr += v;
+        mx = fmax(mx, v);
     }
-    tr = warp_sum(tr);
-    if (lane == 0) s_val[warp] = tr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_val[warp] = mx;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int w = 0; w < nwarp; w++) t += s_val[w];
-        s_tau = clip_rel * fmax(t, 0.0);
+        for (int k = 0; k < nwarp; k++) t = fmax(t, s_val[k]);
+        s_dmax = t;
+        s_tau = fmax(0.25 * cmax, 32.0 * 2.220446049250313e-16 * t);
     }
     __syncthreads();
     int k = 0;
@@ -432,8 +504,8 @@ __global__ void __launch_bounds__(1024) pchol_kernel(const double* __restrict__ 
         if (tid == 0) {
             double v = s_val[0];
             int ix = s_idx[0];
-            for (int w = 1; w < nwarp; w++)
-                if (s_val[w] > v || (s_val[w] == v && s_idx[w] < ix)) { v = s_val[w]; ix = s_idx[w]; }
+            for (int q = 1; q < nwarp; q++)
+                if (s_val[q] > v || (s_val[q] == v && s_idx[q] < ix)) { v = s_val[q]; ix = s_idx[q]; }
             s_p = ix;
             s_piv = v;
         }
@@ -460,50 +532,172 @@ __global__ void __launch_bounds__(1024) pchol_kernel(const double* __restrict__ 
         }
         __syncthreads();
     }
-    // ---- root[i][nz - 1 - kk] = L[i][kk]; zero columns first
-    double* R = root + (long long)l * nz * nz;
-    for (long long e = tid; e < (long long)nz * nz; e += blockDim.x) {
-        const int i = (int)(e / nz), c = (int)(e % nz);
-        const int kk = nz - 1 - c;
-        R[e] = (kk < k) ? Lws[(long long)kk * nz + i] : 0.0;
+    // ---- certificate: |A - L L^T| over the lower triangle; thread = column j, walks the rows i >= j
+    const double bound = 4.0 * s_tau + 64.0 * 2.220446049250313e-16 * s_dmax;
+    int bad = 0;
+    for (int j = tid; j < nz; j += blockDim.x) {
+        for (int i = j; i < nz; i++) {
+            double v = A[(long long)i * nz + j];
+            for (int kk = 0; kk < k; kk++) v = fma(-Lws[(long long)kk * nz + i], Lws[(long long)kk * nz + j], v);
+            bad |= !(fabs(v) <= bound);
+        }
     }
+    bad = __syncthreads_or(bad);
     if (tid == 0) {
-        num_pos[l] = k;
-        if (used) used[l] = 1 + (nz - k);                          // 1 + number of leading zero columns
+        w.lr_rank[blockIdx.x] = k;
+        w.status[blockIdx.x] = bad ? 1 : 0;
     }
 }
 
-__global__ void root_flags_kernel(const int* __restrict__ fail, int nl, int nz, int* __restrict__ used_eigh,
-                                  int* __restrict__ num_pos, int* __restrict__ fail_list, int* __restrict__ nfail) {
-    // single thread block: compact the failed indices (order preserved)
+// step 2: orthogonalise the r columns of L (rows of L^T) -> u_k, lambda_k = |u_k|^2; largest + jitter -> eig_max
+__global__ void __launch_bounds__(1024) lr_jacobi_kernel(RootBlocks B, WaveCtx w, int max_sweeps) {
+    __shared__ int s_rot;
+    __shared__ double s_red[32];
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b) || w.status[blockIdx.x] != 0) return;
+    const int nz = w.nz;
+    const int r = w.lr_rank[blockIdx.x];
+    double* Lt = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    double* lam = w.evals + (long long)blockIdx.x * nz;
+    const double cmax = w.dmax[l] * w.jitter_rel;
+    int sweep = 0;
+    if (r > 1) sweep = hestenes_sweeps(Lt, nullptr, r, nz, max_sweeps, &s_rot);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double mx = 0.0;
+    for (int k = warp; k < r; k += nwarp) {
+        double s = 0.0;
+        for (int c = lane; c < nz; c += 32) { const double x = Lt[(long long)k * nz + c]; s = fma(x, x, s); }
+        s = warp_sum(s);
+        if (lane == 0) lam[k] = s;
+        mx = fmax(mx, s);
+    }
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < nwarp; k++) mx = fmax(mx, s_red[k]);
+        atomic_max_nonneg(w.eig_max + l, mx + cmax);
+        w.sweeps[blockIdx.x] = sweep;
+    }
+}
+
+// step 3: the low-rank route is only valid if the nz - r eigenvalues it does not hold (all equal to the jitter c)
+// are clipped, i.e. c < clip_rel * eig_max; otherwise the reference keeps the null space (scaled sqrt(c)) and the
+// exact route has to produce it.  One thread per slot.
+__global__ void lr_decide_kernel(RootBlocks B, WaveCtx w, int nslots) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    int l, b;
+    if (!wave_slot(w, B.nb, slot, l, b) || w.status[slot] != 0) return;
+    const double c = w.dmax[l] * w.jitter_rel;
+    if (w.lr_rank[slot] < w.nz && c > 0.0 && !(c < w.clip_rel * w.eig_max[l])) w.status[slot] = 1;
+}
+
+// step 4: root[:, nz - r + rank_k] = u_k sqrt((lambda_k + c) / lambda_k), zero where lambda_k + c is clipped
+__global__ void __launch_bounds__(256) lr_finish_kernel(RootBlocks B, WaveCtx w, int* __restrict__ num_pos,
+                                                        int* __restrict__ used) {
+    extern __shared__ __align__(16) double lf_smem[];
+    __shared__ int s_npos;
+    int l, b;
+    if (!wave_slot(w, B.nb, blockIdx.x, l, b) || w.status[blockIdx.x] != 0) return;
+    const int nz = w.nz;
+    const int r = w.lr_rank[blockIdx.x];
+    double* scale = lf_smem;                 // [nz] by column position
+    int* src = (int*)(lf_smem + nz);         // [nz] column position -> k
+    const double* Lt = w.slots + (long long)blockIdx.x * 2 * nz * nz;
+    const double* lam = w.evals + (long long)blockIdx.x * nz;
+    const double c = w.dmax[l] * w.jitter_rel;
+    const double thr = w.clip_rel * w.eig_max[l];
+    if (threadIdx.x == 0) s_npos = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < r; k += blockDim.x) {
+        const double vk = lam[k];
+        int rk = 0;
+        for (int q = 0; q < r; q++) {
+            const double vq = lam[q];
+            rk += (vq < vk) || (vq == vk && q < k);
+        }
+        const double mu = vk + c;
+        const bool keep = !(mu < thr) && vk > 0.0;
+        src[rk] = k;
+        scale[rk] = keep ? sqrt(mu / vk) : 0.0;
+        if (keep) atomicAdd(&s_npos, 1);
+    }
+    __syncthreads();
+    double* R = B.root[b] + (long long)l * nz * nz;
+    const int c0 = nz - r;
+    for (long long e = threadIdx.x; e < (long long)nz * nz; e += blockDim.x) {
+        const int i = (int)(e / nz), col = (int)(e % nz);
+        double v = 0.0;
+        if (col >= c0) {
+            const double sc = scale[col - c0];
+            if (sc != 0.0) v = Lt[(long long)src[col - c0] * nz + i] * sc;
+        }
+        R[e] = v;
+    }
+    if (threadIdx.x == 0) {
+        num_pos[(long long)b * w.nl + l] = s_npos;
+        used[(long long)b * w.nl + l] = 1 + (nz - s_npos);
+    }
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// fail_any[l] = OR over blocks; used / num_pos defaults; failed l compacted (order preserved);
+// zero_scale[l] = sqrt(jitter): root of an implicit all-zero block on the Cholesky branch
+__global__ void root_flags_kernel(const int* __restrict__ fail, int nb, int nl, int nz, double jitter_rel,
+                                  const double* __restrict__ dmax, int* __restrict__ used_eigh, int* __restrict__ num_pos,
+                                  int* __restrict__ fail_list, int* __restrict__ nfail, double* __restrict__ zero_scale) {
     if (threadIdx.x == 0) {
         int n = 0;
         for (int l = 0; l < nl; l++) {
-            used_eigh[l] = fail[l];
-            num_pos[l] = nz;
-            if (fail[l]) fail_list[n++] = l;
+            int any = 0;
+            for (int b = 0; b < nb; b++) any |= fail[b * nl + l];
+            for (int b = 0; b < nb; b++) {
+                used_eigh[b * nl + l] = any;
+                num_pos[b * nl + l] = nz;
+            }
+            if (any) fail_list[n++] = l;
+            if (zero_scale) zero_scale[l] = sqrt(fmax(jitter_rel * dmax[l], 0.0));
         }
         *nfail = n;
     }
+}
+
+// implicit all-zero blocks (Stokes V) on the eigen branch: every eigenvalue equals the jitter c, kept iff c >= thr
+__global__ void zero_scale_kernel(WaveCtx w, int nwave, double* __restrict__ zero_scale) {
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwave) return;
+    if (w.nfail_ptr && w.f0 + wi >= *w.nfail_ptr) return;
+    const int l = w.fail_list[wi];
+    const double c = w.dmax[l] * w.jitter_rel;
+    zero_scale[l] = (c > 0.0 && !(c < w.clip_rel * fmax(w.eig_max[l], c))) ? sqrt(c) : 0.0;
 }
 
 }  // namespace cb
 
 using namespace cb;
 
-// workspace: dmax[nl] | fail[nl] | fail_list[nl] | nfail | evals[nl*nz] | rank[nl*nz] | sweeps[nl] | G | V (eigh slots)
-static long long root_fixed_bytes(int nl, int nz) {
-    return 8LL * nl + 4LL * nl * 3 + 64 + 12LL * nl * nz + 10 * 256;
+// workspace (nb blocks): dmax[nl] dmax2[nl] eig_max[nl] | fail[nb nl] fail_list[nl] nfail | per slot (nb nl):
+// sweeps, lr_rank, status, evals[nz], rank[nz] | slots: 2 nz^2 doubles each
+static long long root_fixed_bytes(int nb, int nl, int nz) {
+    return 24LL * nl + 4LL * nb * nl + 4LL * nl + 64 + 12LL * nb * nl + 12LL * nb * nl * nz + 12 * 256;
 }
 
-// Matrices up to this size take the Jacobi eigen fallback (the reference's exact eigen semantics);
-// larger ones the pivoted Cholesky.  CORA_B200_JACOBI_MAX_NZ overrides (e.g. a huge value forces Jacobi).
+// Matrices up to this size always take the exact Jacobi eigen fallback; larger ones the low-rank route first.
+// CORA_B200_JACOBI_MAX_NZ overrides (e.g. a huge value forces the exact route everywhere).
 static int g_jacobi_max_nz = [] { const char* e = getenv("CORA_B200_JACOBI_MAX_NZ"); return e ? atoi(e) : 128; }();
 
 extern "C" long long cora_b200_root_workspace_bytes(int nl, int nz) {
-    // room for every matrix to take the eigh path (2 nz^2 doubles each); a smaller workspace is
+    // room for every matrix to take the eigen path (2 nz^2 doubles each); a smaller workspace is
     // accepted and processed in waves
-    return root_fixed_bytes(nl, nz) + 16LL * nz * nz * (long long)nl;
+    return root_fixed_bytes(1, nl, nz) + 16LL * nz * nz * (long long)nl;
+}
+
+extern "C" long long cora_b200_root_multi_workspace_bytes(int nblocks, int nl, int nz) {
+    return root_fixed_bytes(nblocks, nl, nz) + 16LL * nz * nz * (long long)nl * nblocks;
 }
 
 // max(diag) per matrix, optionally merged with the maxima already in dmax (merge != 0)
@@ -531,76 +725,127 @@ extern "C" int cora_b200_diag_max(const double* cl, int nl, int nz, double* dmax
 
 extern "C" int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, double clip_rel, double* root,
                                       int* used_eigh, int* num_pos, void* workspace, long long ws_bytes, void* stream) {
-    return cora_b200_root_batched_block(cl, nl, nz, jitter_rel, clip_rel, nullptr, root, used_eigh, num_pos, workspace, ws_bytes, stream);
+    CB_REQUIRE(cl && root, 1, "root_batched: null argument");
+    const double* cls[1] = {cl};
+    double* roots[1] = {root};
+    return cora_b200_root_batched_multi(cls, 1, nl, nz, jitter_rel, clip_rel, roots, used_eigh, num_pos, nullptr, workspace,
+                                        ws_bytes, stream);
 }
 
-extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, double jitter_rel, double clip_rel,
-                                            const double* diag_max, double* root, int* used_eigh, int* num_pos,
-                                            void* workspace, long long ws_bytes, void* stream) {
-    CB_REQUIRE(cl && root && used_eigh && num_pos && workspace, 1, "root_batched: null argument");
-    CB_REQUIRE(nl >= 1 && nz >= 1, 1, "root_batched: bad sizes nl=%d nz=%d", nl, nz);
-    CB_REQUIRE(ws_bytes >= root_fixed_bytes(nl, nz) + 16LL * nz * nz, 4,
-               "root_batched: workspace too small (%lld B, need >= %lld B)", ws_bytes, root_fixed_bytes(nl, nz) + 16LL * nz * nz);
+extern "C" int cora_b200_root_batched_multi(const double* const* cl_blocks, int nblocks, int nl, int nz, double jitter_rel,
+                                            double clip_rel, double* const* root_blocks, int* used_eigh, int* num_pos,
+                                            double* zero_block_scale, void* workspace, long long ws_bytes, void* stream) {
+    CB_REQUIRE(cl_blocks && root_blocks && used_eigh && num_pos && workspace, 1, "root_batched: null argument");
+    CB_REQUIRE(nl >= 1 && nz >= 1 && nblocks >= 1 && nblocks <= MAXB, 1, "root_batched: bad sizes nl=%d nz=%d nblocks=%d", nl, nz,
+               nblocks);
+    const int nb = nblocks;
+    const long long slot_bytes = 16LL * nz * nz;
+    CB_REQUIRE(ws_bytes >= root_fixed_bytes(nb, nl, nz) + slot_bytes * nb, 4,
+               "root_batched: workspace too small (%lld B, need >= %lld B)", ws_bytes, root_fixed_bytes(nb, nl, nz) + slot_bytes * nb);
+    RootBlocks B;
+    B.nb = nb;
+    for (int b = 0; b < nb; b++) {
+        CB_REQUIRE(cl_blocks[b] && root_blocks[b], 1, "root_batched: null block pointer");
+        B.cl[b] = cl_blocks[b];
+        B.root[b] = root_blocks[b];
+    }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     auto take = [&](long long bytes) { char* p = ws; ws = (char*)(((uintptr_t)(ws + bytes) + 255) & ~(uintptr_t)255); return p; };
     double* dmax = (double*)take(8LL * nl);
-    int* fail = (int*)take(4LL * nl);
+    double* dmax2 = (double*)take(8LL * nl);
+    double* eig_max = (double*)take(8LL * nl);
+    int* fail = (int*)take(4LL * nb * nl);
     int* fail_list = (int*)take(4LL * nl);
-    int* sweeps = (int*)take(4LL * nl);
     int* nfail_d = (int*)take(64);
-    double* evals = (double*)take(8LL * nl * nz);
-    int* rank = (int*)take(4LL * nl * nz);
-    double* GV = (double*)ws;
-    long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
+    int* sweeps = (int*)take(4LL * nb * nl);
+    int* lr_rank = (int*)take(4LL * nb * nl);
+    int* status = (int*)take(4LL * nb * nl);
+    double* evals = (double*)take(8LL * nb * nl * nz);
+    int* rank = (int*)take(4LL * nb * nl * nz);
+    double* slot_mem = (double*)ws;
+    const long long groups = ((char*)workspace + ws_bytes - ws) / (slot_bytes * nb);   // l's whose blocks fit at once
 
-    { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<dim3(nl, nl >= 1024 ? 2 : 8), 256, 0, st>>>(cl, nz, jitter_rel, root, dmax, diag_max); }
-    count_launch();
+    for (int b = 0; b < nb; b++) {
+        diag_max_kernel<<<nl, 256, 0, st>>>(B.cl[b], nz, dmax, b > 0);
+        count_launch();
+    }
     CB_LAUNCH_CHECK();
-    {
+    for (int b = 0; b < nb; b++) {
+        { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<dim3(nl, nl >= 1024 ? 2 : 8), 256, 0, st>>>(B.cl[b], nz, jitter_rel, B.root[b], dmax2, dmax); }
+        count_launch();
+        CB_LAUNCH_CHECK();
         KTimer kt(K_CHOLESKY, st);
         const size_t smem = sizeof(double) * (2 * CH_STAGE + CH_NB * (CH_NB + 1));
         if (nz % 2 == 0) {
             CB_CUDA(cudaFuncSetAttribute(cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cholesky_kernel<true><<<nl, CH_THREADS, smem, st>>>(root, nz, fail);
+            cholesky_kernel<true><<<nl, CH_THREADS, smem, st>>>(B.root[b], nz, fail + (long long)b * nl);
         } else {
             CB_CUDA(cudaFuncSetAttribute(cholesky_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cholesky_kernel<false><<<nl, CH_THREADS, smem, st>>>(root, nz, fail);
+            cholesky_kernel<false><<<nl, CH_THREADS, smem, st>>>(B.root[b], nz, fail + (long long)b * nl);
         }
+        count_launch();
+        CB_LAUNCH_CHECK();
     }
+    root_flags_kernel<<<1, 32, 0, st>>>(fail, nb, nl, nz, jitter_rel, dmax, used_eigh, num_pos, fail_list, nfail_d, zero_block_scale);
     count_launch();
     CB_LAUNCH_CHECK();
-    root_flags_kernel<<<1, 32, 0, st>>>(fail, nl, nz, used_eigh, num_pos, fail_list, nfail_d);
-    count_launch();
-    CB_LAUNCH_CHECK();
-    const int threads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
-    auto wave = [&](int f0, int nb, const int* guard) -> int {
-        double* G = GV;
-        double* V = GV + (long long)nb * nz * nz;
+    CB_CUDA(cudaMemsetAsync(eig_max, 0, 8LL * nl, st));
+    const int jthreads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
+    const bool lowrank = nz > g_jacobi_max_nz;
+    auto wave = [&](int f0, int nw, const int* guard) -> int {
+        WaveCtx w;
+        w.fail_list = fail_list + f0;
+        w.nfail_ptr = guard;
+        w.f0 = f0;
+        w.nl = nl;
+        w.nz = nz;
+        w.jitter_rel = jitter_rel;
+        w.clip_rel = clip_rel;
+        w.dmax = dmax;
+        w.eig_max = eig_max;
+        w.slots = slot_mem;
+        w.evals = evals;
+        w.rank = rank;
+        w.lr_rank = lr_rank;
+        w.status = status;
+        w.sweeps = sweeps;
+        const int nslots = nw * nb;
         KTimer kt(K_EIGH, st);
-        if (nz > g_jacobi_max_nz) {
+        if (lowrank) {
             const size_t smem = sizeof(double) * 2 * (size_t)nz;
-            CB_CUDA(cudaFuncSetAttribute(pchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-            pchol_kernel<<<nb, nz >= 512 ? 1024 : 512, smem, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, clip_rel, G, root,
-                                                                   num_pos, guard, used_eigh);
+            CB_CUDA(cudaFuncSetAttribute(lr_pchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            lr_pchol_kernel<<<nslots, nz >= 512 ? 1024 : 512, smem, st>>>(B, w);
+            lr_jacobi_kernel<<<nslots, 1024, 0, st>>>(B, w, 60);
+            lr_decide_kernel<<<ceil_div(nslots, 128), 128, 0, st>>>(B, w, nslots);
+            count_launch(3);
+        } else {
+            fill_int_kernel<<<ceil_div(nslots, 256), 256, 0, st>>>(status, nslots, 1);
             count_launch();
-            CB_LAUNCH_CHECK();
-            return 0;
         }
-        jacobi_init_kernel<<<nb, 256, 0, st>>>(cl, fail_list + f0, nz, jitter_rel, dmax, G, V, guard);
-        count_launch();
         CB_LAUNCH_CHECK();
-        jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0, guard);
-        count_launch();
+        jacobi_init_kernel<<<nslots, 256, 0, st>>>(B, w);
+        jacobi_kernel<<<nslots, jthreads, 0, st>>>(B, w, 60);
+        jacobi_evals_kernel<<<nslots, 256, 0, st>>>(B, w);
+        count_launch(3);
         CB_LAUNCH_CHECK();
-        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, fail_list + f0, nz, clip_rel, root, num_pos, evals, rank, guard, nullptr,
-                                                 used_eigh);
+        if (lowrank) {
+            const size_t smem = 12 * (size_t)nz + 16;
+            CB_CUDA(cudaFuncSetAttribute(lr_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            lr_finish_kernel<<<nslots, 256, smem, st>>>(B, w, num_pos, used_eigh);
+            count_launch();
+        }
+        jacobi_finish_kernel<<<nslots, 256, 0, st>>>(B, w, num_pos, used_eigh, nullptr);
         count_launch();
+        if (zero_block_scale) {
+            zero_scale_kernel<<<ceil_div(nw, 128), 128, 0, st>>>(w, nw, zero_block_scale);
+            count_launch();
+        }
         CB_LAUNCH_CHECK();
         return 0;
     };
-    if (slots >= nl) {
-        // room for every matrix: launch the eigen fallback for all nl slots, CTAs beyond the
+    if (groups >= nl) {
+        // room for every matrix: launch the eigen fallback for all nl slot groups, CTAs beyond the
         // device-side failure count exit at once -- the host never waits for the count
         return wave(0, nl, nfail_d);
     }
@@ -608,10 +853,10 @@ extern "C" int cora_b200_root_batched_block(const double* cl, int nl, int nz, do
     CB_CUDA(cudaMemcpyAsync(&nfail, nfail_d, sizeof(int), cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaStreamSynchronize(st));
     if (nfail == 0) return 0;
-    CB_REQUIRE(slots >= 1, 4, "root_batched: no workspace for the eigen fallback");
-    for (int f0 = 0; f0 < nfail; f0 += (int)slots) {
-        const int nb = (int)std::min<long long>(slots, nfail - f0);
-        if (int rc = wave(f0, nb, nullptr)) return rc;
+    CB_REQUIRE(groups >= 1, 4, "root_batched: no workspace for the eigen fallback");
+    for (int f0 = 0; f0 < nfail; f0 += (int)groups) {
+        const int nw = (int)std::min<long long>(groups, nfail - f0);
+        if (int rc = wave(f0, nw, nullptr)) return rc;
     }
     return 0;
 }
@@ -623,7 +868,7 @@ __global__ void iota_kernel(int* p, int n, int base) {
 }
 
 extern "C" long long cora_b200_eigh_workspace_bytes(int nl, int nz) {
-    return 4LL * nl + 8LL * nl + 12LL * nl * nz + 4LL * nl + 8 * 256 + 16LL * nz * nz * (long long)nl;
+    return 4LL * nl + 16LL * nl + 12LL * nl * nz + 8LL * nl + 10 * 256 + 16LL * nz * nz * (long long)nl;
 }
 
 extern "C" int cora_b200_eigh_batched(const double* a, int nl, int nz, double* evecs, double* evals, void* workspace,
@@ -634,26 +879,49 @@ extern "C" int cora_b200_eigh_batched(const double* a, int nl, int nz, double* e
     auto take = [&](long long bytes) { char* p = ws; ws = (char*)(((uintptr_t)(ws + bytes) + 255) & ~(uintptr_t)255); return p; };
     int* list = (int*)take(4LL * nl);
     double* dzero = (double*)take(8LL * nl);
+    double* eig_max = (double*)take(8LL * nl);
     double* ev_ws = (double*)take(8LL * nl * nz);
     int* rank = (int*)take(4LL * nl * nz);
     int* sweeps = (int*)take(4LL * nl);
+    int* status = (int*)take(4LL * nl);
     double* GV = (double*)ws;
     const long long slots = ((char*)workspace + ws_bytes - ws) / (16LL * nz * nz);
     CB_REQUIRE(slots >= 1, 4, "eigh_batched: workspace too small (%lld B)", ws_bytes);
     iota_kernel<<<ceil_div(nl, 256), 256, 0, st>>>(list, nl, 0);
+    fill_int_kernel<<<ceil_div(nl, 256), 256, 0, st>>>(status, nl, 1);
     CB_CUDA(cudaMemsetAsync(dzero, 0, 8LL * nl, st));
-    count_launch();
+    CB_CUDA(cudaMemsetAsync(eig_max, 0, 8LL * nl, st));
+    count_launch(2);
     CB_LAUNCH_CHECK();
     const int threads = nz >= 512 ? 1024 : (nz >= 128 ? 512 : 256);
+    RootBlocks B;
+    B.nb = 1;
+    B.cl[0] = a;
+    B.root[0] = evecs;
     KTimer kt(K_EIGH, st);
     for (int f0 = 0; f0 < nl; f0 += (int)slots) {
-        const int nb = (int)std::min<long long>(slots, nl - f0);
-        double* G = GV;
-        double* V = GV + (long long)nb * nz * nz;
-        jacobi_init_kernel<<<nb, 256, 0, st>>>(a, list + f0, nz, 0.0, dzero, G, V, nullptr);
-        jacobi_kernel<<<nb, threads, 0, st>>>(G, V, nz, 60, sweeps + f0, nullptr);
-        jacobi_finish_kernel<<<nb, 256, 0, st>>>(G, V, list + f0, nz, 0.0, evecs, nullptr, ev_ws, rank, nullptr, evals);
-        count_launch(3);
+        const int nw = (int)std::min<long long>(slots, nl - f0);
+        WaveCtx w;
+        w.fail_list = list + f0;
+        w.nfail_ptr = nullptr;
+        w.f0 = f0;
+        w.nl = nl;
+        w.nz = nz;
+        w.jitter_rel = 0.0;
+        w.clip_rel = 0.0;
+        w.dmax = dzero;
+        w.eig_max = eig_max;
+        w.slots = GV;
+        w.evals = ev_ws;
+        w.rank = rank;
+        w.lr_rank = nullptr;
+        w.status = status;
+        w.sweeps = sweeps;
+        jacobi_init_kernel<<<nw, 256, 0, st>>>(B, w);
+        jacobi_kernel<<<nw, threads, 0, st>>>(B, w, 60);
+        jacobi_evals_kernel<<<nw, 256, 0, st>>>(B, w);
+        jacobi_finish_kernel<<<nw, 256, 0, st>>>(B, w, nullptr, nullptr, evals);
+        count_launch(4);
         CB_LAUNCH_CHECK();
     }
     return 0;

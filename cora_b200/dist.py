@@ -163,25 +163,17 @@ class ShardedSky(object):
         self._p2p = None
         self._k = 0
         if self.exchange == "p2p" and self.peers is None:
-            # set the peer group up now and make the ranks agree: if any of them cannot map its peers'
-            # memory (no peer access between some pair of GPUs), everybody takes the collective path
-            import torch
-
+            # set the peer group up now.  PeerGroup agrees on failure inside its own collectives and raises
+            # PeerSetupError on EVERY rank together (no peer access between some pair of GPUs, ...): then
+            # everybody takes the collective path, or everybody raises if p2p was asked for explicitly.
             from . import peer as _peer
 
-            ok = 1
             try:
                 self.peers = _peer.PeerGroup(self.rank, self.size, self.group)
-            except Exception as exc:  # noqa: BLE001 -- any failure means "no p2p here"
-                ok, self._p2p_error = 0, exc
-            flag = torch.tensor([ok], dtype=torch.int32, device=_dev.device())
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 0:
-                if self.peers is not None and requested != "p2p":
-                    self.peers = None
+            except _peer.PeerSetupError as exc:
                 if requested == "p2p":
-                    raise _lib.CoraB200Error("exchange='p2p' requested but peer memory could not be set up on every rank: %r"
-                                             % (getattr(self, "_p2p_error", None),))
+                    raise _lib.CoraB200Error("exchange='p2p' requested but peer memory could not be set up on every rank: %s" % exc)
+                self._p2p_error = exc
                 self.exchange = "collective"
 
     def _persistent(self, name, make):
@@ -457,13 +449,15 @@ class ShardedPolSky(object):
     ``(4 nfreq)^2`` per l (``cora/scripts/makesky.py:368-382``; 206 GB at nside 512 x 1024
     channels) and roots it whole.  Here the blocks are kept apart: T = ``FullSkySynchrotron``,
     E = B = ``FullSkyPolarisedSynchrotron`` (one root, applied to two independent draw streams),
-    V = 0.  What is preserved: the jitter ``1e-14 max(diag)`` is taken over the whole matrix'
-    diagonal (``cora_b200_root_batched_block``), the Philox counters of block b are offset by
-    ``b nfreq`` -- the same draws the dense formulation consumes -- and the output layout
-    ``float64[freq, 4, pix]``.  What differs, at the level of the regulariser only: the Cholesky
-    / eigen decision and the eigenvalue clip act per block (the reference's act on the whole
-    matrix), and Stokes V is exactly 0 (the reference's V is ``sqrt(cmax) g`` on the Cholesky
-    branch, <= 1e-7 of T, and 0 on the eigen branch).
+    V = 0.  The regulariser keeps the reference's whole-matrix semantics (``cora_b200_root_batched_multi``):
+    the jitter ``1e-14 max(diag)`` is taken over the whole matrix' diagonal, a Cholesky failure of any block
+    sends every block of that l to the eigen branch, and the eigenvalue clip is ``1e-16`` times the largest
+    eigenvalue over all blocks -- at 1024 channels this is what leaves 8 + 52 + 52 of 4096 modes (SURVEY
+    App. C.6).  The Philox counters of block b are offset by ``b nfreq`` -- the same draws the dense
+    formulation consumes -- and the output layout is ``float64[freq, 4, pix]``.  Stokes V: the reference's V
+    block is ``sqrt(cmax) I`` on the Cholesky branch (a map ``<= 1e-7`` of T) and 0 on the eigen branch;
+    ``self.vscale`` holds that factor per l, the V map itself is written as 0 (documented deviation at the
+    level of the regulariser on the few-channel Cholesky branch only).
 
     Exchange: apply stores straight into the PANEL buffers (T, E, B) of the GPU owning each
     channel (``cora_b200.peer``); one flag barrier per step.  With one rank the same code runs on
@@ -545,18 +539,16 @@ class ShardedPolSky(object):
         l0 = int(self.l_list[0])
         step = self.size if self.plan.partition == "interleaved" else 1
         cl = self._persistent("cl", lambda: [_dev.empty((nl, nz, nz), t.float64) for _ in range(2)])
-        roots = self._persistent("root", lambda: [(_dev.empty((nl, nz, nz), t.float64), _dev.empty((nl,), t.int32),
-                                                   _dev.empty((nl,), t.int32)) for _ in range(2)])
-        dmax = self._persistent("dmax", lambda: _dev.empty((nl,), t.float64))
+        roots = self._persistent("root", lambda: ([_dev.empty((nl, nz, nz), t.float64) for _ in range(2)],
+                                                  _dev.empty((2, nl), t.int32), _dev.empty((2, nl), t.int32)))
+        self.vscale = self._persistent("vscale", lambda: _dev.empty((nl,), t.float64))
         for b in range(2):
             self.models[b]._b200_fill(self.fill_inputs[b], l0, step, nl, nz, self.zint, cl[b])
-            _lib.call("cora_b200_diag_max", _lib.ptr(cl[b]), nl, nz, _lib.ptr(dmax), int(b > 0), _lib.stream_ptr())
-        rws = self._persistent("root_ws", lambda: nputil.root_workspace(nl, nz, max_eigh=nl if 16 * nz * nz * nl <= _dev.free_bytes() // 8
-                                                                        else max(4, nl // 8)))
-        for b in range(2):
-            root, used, npos = roots[b]
-            _lib.call("cora_b200_root_batched_block", _lib.ptr(cl[b]), nl, nz, 1e-14, 1e-16, _lib.ptr(dmax), _lib.ptr(root),
-                      _lib.ptr(used), _lib.ptr(npos), _lib.ptr(rws), int(rws.numel()), _lib.stream_ptr())
+        rws = self._persistent("root_ws", lambda: nputil.root_multi_workspace(
+            2, nl, nz, max_eigh=nl if 32 * nz * nz * nl <= _dev.free_bytes() // 8 else max(4, nl // 8)))
+        # one jitter, one Cholesky-or-eigh decision and one clip threshold per l over blockdiag(T, E, B, V)
+        nputil.root_batched_multi_device(cl, 1e-14, 1e-16, out=roots, ws=rws, zero_scale=self.vscale)
+        rlist, used_all, _ = roots
         lmax_loc = int(self.l_list.max())
 
         def mk():
@@ -567,7 +559,7 @@ class ShardedPolSky(object):
         ws = self._persistent("draw_ws", mk)
         tabs = self._nu_ptr(k)
         for f, b in ((0, 0), (1, 1), (2, 1)):      # field -> block: T <- T root, E and B <- the polarised root
-            root, used, _ = roots[b]
+            root, used = rlist[b], used_all[b]
             _lib.call("cora_b200_draw_apply_peers", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), nl, nz, self.lmax,
                       ctypes.c_ulonglong(int(seed)), f * nz, None, 0, _lib.ptr(tabs[f]), _lib.ptr(self.nu_width),
                       _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr())

@@ -63,10 +63,16 @@ class ForegroundSCK(ForegroundMap):
         t = _dev.torch()
         return _dev.to_device(nu_samples, t.float64), _dev.to_device(w, t.float64)
 
+    # skysim.clarray takes the fused kernel only while these methods are the ones defined here
+    _b200_fill_methods = ("angular_powerspectrum", "angular_ps", "frequency_covariance", "_b200_fill", "_params")
+
     def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None):
         ns, wd = inputs
         _lib.call("cora_b200_cl_fill_sck", *self._params(), _lib.ptr(ns), _lib.ptr(wd), int(l0), int(l_step), int(nl),
                   int(nz), int(zint), _lib.ptr(out), _lib.stream_ptr(stream))
+
+
+ForegroundSCK._b200_fill_origin = ForegroundSCK
 
 
 class Synchrotron(ForegroundSCK):

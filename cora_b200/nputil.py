@@ -26,6 +26,39 @@ def root_batched_device(cl_dev, jitter_rel=0.0, clip_rel=1e-16, stream=None, out
     return root, used, npos
 
 
+def root_multi_workspace(nblocks, nl, nz, max_eigh=None):
+    """Workspace for ``root_batched_multi_device`` (room for ``max_eigh`` l's on the eigen branch at once)."""
+    lib = _lib.load()
+    full = lib.cora_b200_root_multi_workspace_bytes(nblocks, nl, nz)
+    per_l = 16 * nz * nz * nblocks
+    one = full - per_l * (nl - 1)
+    want = full if max_eigh is None else one + per_l * (max(1, min(nl, max_eigh)) - 1)
+    return _dev.workspace(min(want, max(one, _dev.free_bytes() - (2 << 30))))
+
+
+def root_batched_multi_device(cl_blocks, jitter_rel=1e-14, clip_rel=1e-16, stream=None, out=None, ws=None, zero_scale=None):
+    """Root of ``blockdiag(cl_blocks[0][l], cl_blocks[1][l], ..., 0)`` kept as separate blocks, with the
+    reference's whole-matrix semantics (``cora/scripts/makesky.py:368-382`` + ``skysim.py:116-119`` +
+    ``nputil.py:81-96``): one jitter, one Cholesky-or-eigh decision and one eigenvalue clip threshold per l
+    (``cora_b200_root_batched_multi``).  ``cl_blocks``: list of CUDA float64 ``[nl, nz, nz]``.
+    Returns ``(roots list, used int32[nblocks, nl], num_pos int32[nblocks, nl])``; ``zero_scale`` (CUDA
+    float64[nl], optional) receives the root scale of an implicit all-zero block (Stokes V)."""
+    t = _dev.torch()
+    nb = len(cl_blocks)
+    nl, nz = int(cl_blocks[0].shape[0]), int(cl_blocks[0].shape[1])
+    if out is None:
+        out = ([_dev.empty((nl, nz, nz), t.float64) for _ in range(nb)], _dev.empty((nb, nl), t.int32),
+               _dev.empty((nb, nl), t.int32))
+    roots, used, npos = out
+    if ws is None:
+        ws = root_multi_workspace(nb, nl, nz)
+    cls = (ctypes.c_void_p * nb)(*[c.data_ptr() for c in cl_blocks])
+    rts = (ctypes.c_void_p * nb)(*[r.data_ptr() for r in roots])
+    _lib.call("cora_b200_root_batched_multi", cls, nb, nl, nz, float(jitter_rel), float(clip_rel), rts, _lib.ptr(used),
+              _lib.ptr(npos), _lib.ptr(zero_scale), _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr(stream))
+    return roots, used, npos
+
+
 def eigh_batched_device(a_dev):
     """Batched ``scipy.linalg.eigh`` on device: CUDA float64 ``[nl, nz, nz]`` -> ``(evals[nl, nz]``
     ascending, ``evecs[nl, nz, nz]`` with eigenvectors in columns``)`` (``cora_b200_eigh_batched``)."""
@@ -60,11 +93,13 @@ def matrix_root_manynull(mat, threshold=1e-16, truncate=True):
     last ``num_pos`` columns are kept and -- reference quirk preserved -- the array then has
     shape ``(1, N, num_pos)`` (``nputil.py:92-96``).
 
-    For matrices larger than 128 x 128 the fallback is a diagonally pivoted Cholesky with the same
-    relative clip instead of an eigen-decomposition (``csrc/root.cu: pchol_kernel``): the result has
-    the same defining property (``root @ root.T == mat`` to the clip, zero columns first, ``num_pos``
-    = numerical rank) but its columns are not eigenvectors.  ``CORA_B200_JACOBI_MAX_NZ`` (environment,
-    read when the library loads) moves the switch, e.g. to force the eigen path everywhere.
+    The eigen branch has the reference's semantics at every size: eigenvalues below ``threshold`` times the
+    largest are dropped, the columns are ``evecs * sqrt(evals)`` in ascending order.  Matrices larger than
+    128 x 128 get there through a low-rank factorisation when they are numerically rank-deficient positive
+    semi-definite (``csrc/root.cu``: pivoted Cholesky + one-sided Jacobi on the factor: the same eigenpairs, to
+    high relative accuracy), otherwise through the full Jacobi sweep.  Eigenvalues within a few ulp of
+    ``threshold * max`` are round-off in any implementation (LAPACK's included): ``num_pos`` can differ from
+    scipy's by the number of eigenvalues sitting in that band.
     """
     t = _dev.torch()
     mat = np.asarray(mat, dtype=np.float64)

@@ -48,58 +48,116 @@ class RawBuf(object):
         return out
 
 
+class PeerSetupError(_lib.CoraB200Error):
+    """Peer memory could not be set up on every rank (raised on ALL ranks of the group together)."""
+
+
+def _env_float(name, default):
+    import os
+
+    try:
+        return float(os.environ.get(name, default))
+    except ValueError:
+        return float(default)
+
+
 class PeerGroup(object):
     """Real multi-process group.  Every method that allocates is collective: all ranks call it
-    in the same order."""
+    in the same order.  A failure on any rank (no peer access between some pair of GPUs, out of
+    memory) is agreed on inside the call: every rank takes part in the same collectives, releases
+    what it had allocated or mapped for the failed request, and raises ``PeerSetupError``.
 
-    def __init__(self, rank, size, group=None):
+    ``timeout_s`` (default: ``CORA_B200_PEER_TIMEOUT_S`` or 60 s): how long a barrier waits for a
+    peer.  ``fatal`` (default on; ``CORA_B200_PEER_FATAL=0`` turns it off): a timed-out barrier traps
+    the kernel, so that nothing queued behind it runs on half-written buffers -- every later CUDA
+    call of the process raises.  With ``fatal`` off the caller must call ``check()`` before trusting
+    results produced after a barrier."""
+
+    def __init__(self, rank, size, group=None, timeout_s=None, fatal=None):
         import torch.distributed as dist
 
         self.rank, self.size, self.group, self._dist = int(rank), int(size), group, dist
         self._own, self._opened = [], []
         self._epoch = 0
+        self.timeout_s = _env_float("CORA_B200_PEER_TIMEOUT_S", 60.0) if timeout_s is None else float(timeout_s)
+        self.fatal = bool(int(_env_float("CORA_B200_PEER_FATAL", 1))) if fatal is None else bool(fatal)
         t = _dev.torch()
         self.status = _dev.zeros((1,), t.int32)
-        self._flags, flag_ptrs = self.alloc(8 * self.size)
+        try:
+            self._flags, flag_ptrs = self.alloc(8 * self.size)
+        except PeerSetupError:
+            self._release()
+            raise
         self._flag_ptrs = _dev.to_device(np.array(flag_ptrs, dtype=np.uint64).view(np.int64), t.int64)
         t.cuda.synchronize()
         dist.barrier(group=group)   # every rank's zeroed flags exist before anybody signals
 
     def alloc(self, nbytes):
         """-> (own RawBuf, [pointer of every rank's buffer as mapped in this process])."""
-        lib = _lib.load()
         nbytes = max(256, int(nbytes))
         p = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
-        _lib.call("cora_b200_peer_alloc", nbytes, ctypes.byref(p), handle)
-        own = RawBuf(p.value, nbytes, keep=self)
-        self._own.append(p.value)
+        err = None
+        try:
+            _lib.call("cora_b200_peer_alloc", nbytes, ctypes.byref(p), handle)
+        except _lib.CoraB200Error as exc:
+            err, p = "rank %d: %s" % (self.rank, exc), ctypes.c_void_p()
         handles = [None] * self.size
-        self._dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
-        ptrs = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                ptrs.append(p.value)
-                continue
-            q = ctypes.c_void_p()
-            _lib.call("cora_b200_peer_open", ctypes.create_string_buffer(h, 64), ctypes.byref(q))
-            self._opened.append(q.value)
-            ptrs.append(q.value)
-        del lib
-        return own, ptrs
+        self._dist.all_gather_object(handles, None if err else bytes(handle.raw), group=self.group)
+        ptrs, opened = [], []
+        if err is None and all(h is not None for h in handles):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(p.value)
+                    continue
+                q = ctypes.c_void_p()
+                try:
+                    _lib.call("cora_b200_peer_open", ctypes.create_string_buffer(h, 64), ctypes.byref(q))
+                except _lib.CoraB200Error as exc:
+                    err = "rank %d mapping rank %d: %s" % (self.rank, r, exc)
+                    break
+                opened.append(q.value)
+                ptrs.append(q.value)
+        elif err is None:
+            err = "rank %d: a peer could not allocate" % self.rank
+        # agree on the outcome: every rank has run the same collectives up to here whatever happened locally
+        errs = [None] * self.size
+        self._dist.all_gather_object(errs, err, group=self.group)
+        if any(e is not None for e in errs):
+            lib = _lib.load()
+            for q in opened:
+                lib.cora_b200_peer_close(ctypes.c_void_p(q))
+            self._dist.barrier(group=self.group)        # nobody still maps a buffer about to be freed
+            if p.value:
+                lib.cora_b200_peer_free(p)
+            raise PeerSetupError("peer memory setup failed: " + "; ".join(e for e in errs if e))
+        self._own.append(p.value)
+        self._opened.extend(opened)
+        return RawBuf(p.value, nbytes, keep=self), ptrs
 
     def barrier(self, stream=None):
         """Stream-ordered flag barrier over peer memory (all earlier stores of every rank are
         visible to every rank's later kernels)."""
         self._epoch += 1
         _lib.call("cora_b200_peer_barrier", _lib.ptr(self._flag_ptrs), self.rank, self.size,
-                  ctypes.c_ulonglong(self._epoch), 20.0, _lib.ptr(self.status), _lib.stream_ptr(stream))
+                  ctypes.c_ulonglong(self._epoch), self.timeout_s, _lib.ptr(self.status), int(self.fatal),
+                  _lib.stream_ptr(stream))
 
     def check(self):
         """Raise if a barrier timed out (synchronises)."""
         s = int(self.status.item())
         if s:
             raise _lib.CoraB200Error("peer barrier timed out waiting for rank %d" % (s - 1))
+
+    def _release(self):
+        """Unmap and free everything (local; the caller orders it against the other ranks)."""
+        lib = _lib.load()
+        for q in self._opened:
+            lib.cora_b200_peer_close(ctypes.c_void_p(q))
+        self._opened = []
+        for p in self._own:
+            lib.cora_b200_peer_free(ctypes.c_void_p(p))
+        self._own = []
 
     def close(self):
         t = _dev.torch()

@@ -43,6 +43,23 @@ def _sample_frequencies(zarray, zromb, zwidth):
     return za, zint
 
 
+def _fused_fill(aps, owner):
+    """The owner's fused fill kernel, but only if ``aps`` is this package's own implementation: a subclass
+    that overrides ``angular_powerspectrum`` (or, for the separable foregrounds, ``angular_ps`` /
+    ``frequency_covariance``; for 21cm any method the spectrum is built from) must be evaluated through the
+    callable, as the reference always does (``cora/core/skysim.py:57``)."""
+    if owner is None or getattr(aps, "__name__", "") != "angular_powerspectrum":
+        return None
+    fill = getattr(owner, "_b200_fill", None)
+    origin = getattr(type(owner), "_b200_fill_origin", None)
+    if fill is None or origin is None:
+        return None
+    for name in origin._b200_fill_methods:
+        if getattr(type(owner), name, None) is not getattr(origin, name, None) or name in getattr(owner, "__dict__", {}):
+            return None
+    return fill
+
+
 def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
     """Calculate an array of C_l(z, z') averaged over each frequency channel.
 
@@ -59,7 +76,7 @@ def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
     zarray = np.asarray(zarray, dtype=np.float64)
     nz = zarray.size
     owner = getattr(aps, "__self__", None)
-    fused = getattr(owner, "_b200_fill", None) if getattr(aps, "__name__", "") == "angular_powerspectrum" else None
+    fused = _fused_fill(aps, owner)
 
     if zromb != 0 and lmax < 5:
         # the reference dies in np.array_split(..., 0) (skysim.py:51); keep the error type

@@ -156,16 +156,28 @@ int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, 
                            double* root, int* used_eigh, int* num_pos, void* workspace,
                            long long ws_bytes, void* stream);
 
-/* Root of one diagonal block of a block-diagonal covariance (makesky gaussianfg --pol full builds
- * blockdiag(T, E, B, V), cora/scripts/makesky.py:368-382): the jitter is jitter_rel * diag_max[l]
- * with diag_max the maximum over the WHOLE matrix' diagonal (cora/core/skysim.py:116-117), given
- * per l in `diag_max` (device float64[nl]; NULL = this block's own maximum).  The Cholesky /
- * eigen decision and the eigenvalue clip act per block.  cora_b200_diag_max computes
- * dmax[l] = max_i cl[l][i][i], merged (max) with the values already in dmax when merge != 0.   */
+/* Root of a block-diagonal covariance blockdiag(cl_blocks[0][l], ..., cl_blocks[nblocks-1][l], 0, ...) kept as
+ * separate blocks (makesky gaussianfg --pol full builds blockdiag(T, E, B, V) densely, (4 nfreq)^2 per l:
+ * cora/scripts/makesky.py:368-382) with the semantics the reference applies to the WHOLE matrix:
+ *   - jitter = jitter_rel * max over every block's diagonal                    (cora/core/skysim.py:116-117)
+ *   - Cholesky of every block; if ANY block of an l fails, every block of that l takes the eigen branch
+ *     (scipy's cholesky of the whole matrix would have failed)                 (cora/util/nputil.py:81-86)
+ *   - eigenvalues below clip_rel * (largest eigenvalue over ALL blocks) are zeroed  (nputil.py:89-90)
+ * cl_blocks / root_blocks: HOST arrays of nblocks device pointers, each [nl][nz][nz]; the same pointer may
+ * not appear twice in root_blocks.  used_eigh / num_pos: device int[nblocks][nl] (meaning as above, per block).
+ * zero_block_scale (device float64[nl] or NULL): s with root = s I for an implicit all-zero block (Stokes V):
+ * sqrt(jitter) on the Cholesky branch and where the jitter survives the clip, else 0.
+ * Fallback implementation: nz <= 128 one-sided Jacobi on the full matrix; larger matrices first try the
+ * low-rank route (pivoted Cholesky down to the jitter level, certified residual, one-sided Jacobi on the
+ * factor's columns: the same eigenpairs in O(nz^2 rank)) and fall back to the full Jacobi when the matrix
+ * is not numerically low-rank positive semi-definite or when the jitter itself would survive the clip.
+ * workspace: cora_b200_root_multi_workspace_bytes(nblocks, nl, nz) (smaller: processed in waves, one host
+ * synchronisation).  cora_b200_diag_max: dmax[l] = max_i cl[l][i][i], merged (max) into dmax when merge != 0. */
 int cora_b200_diag_max(const double* cl, int nl, int nz, double* dmax, int merge, void* stream);
-int cora_b200_root_batched_block(const double* cl, int nl, int nz, double jitter_rel, double clip_rel,
-                                 const double* diag_max, double* root, int* used_eigh, int* num_pos,
-                                 void* workspace, long long ws_bytes, void* stream);
+long long cora_b200_root_multi_workspace_bytes(int nblocks, int nl, int nz);
+int cora_b200_root_batched_multi(const double* const* cl_blocks, int nblocks, int nl, int nz, double jitter_rel,
+                                 double clip_rel, double* const* root_blocks, int* used_eigh, int* num_pos,
+                                 double* zero_block_scale, void* workspace, long long ws_bytes, void* stream);
 
 /* Batched symmetric eigen-decomposition in scipy.linalg.eigh's layout (lower triangle read):
  * evals[l][k] ascending, column k of evecs[l] the unit eigenvector of evals[l][k].
@@ -252,15 +264,18 @@ int cora_b200_map_sub(const double* a, const double* b, long long n, double* out
  *     owns channel nu for the SHT stage.
  * Buffers come from cora_b200_peer_alloc (cudaMalloc + CUDA IPC handle, zero-filled); every
  * other process maps them with cora_b200_peer_open.  cora_b200_peer_barrier is a flag barrier
- * over the same memory (stream-ordered; `epoch` strictly increasing; a peer that does not
- * arrive within timeout_s sets *status != 0 instead of hanging the GPU).                     */
+ * over the same memory (stream-ordered; `epoch` strictly increasing).  A peer that does not arrive
+ * within timeout_s (<= 0: 60 s) sets *status = 1 + its rank instead of hanging the GPU and, with
+ * fatal != 0, traps: the kernels queued behind the barrier must not run on half-written buffers, so
+ * every later CUDA call of the process fails.  With fatal == 0 the caller must read *status before
+ * trusting anything computed after the barrier.                                                 */
 int cora_b200_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out);
 int cora_b200_peer_free(void* ptr);
 int cora_b200_peer_open(const unsigned char* handle64, void** ptr_out);
 int cora_b200_peer_close(void* ptr);
 /* flags_ptrs: device array [size] of pointers, entry r = rank r's flag array (u64[size]) as mapped here */
 int cora_b200_peer_barrier(const void* flags_ptrs, int rank, int size, unsigned long long epoch,
-                           double timeout_s, int* status, void* stream);
+                           double timeout_s, int* status, int fatal, void* stream);
 
 /* 21cm fill for channel pairs [pair0, pair0 + npairs) of the diagonal-major enumeration
  * (pair index p <-> (i, j), i >= j, ordered by d = i - j then j), all l = 0..nl-1.

@@ -253,6 +253,66 @@ def extra_c2rows():
     print("cl_21cm_c2rows.npz written")
 
 
+def extra_root_large():
+    """The eigen branch where it is live: the 1024-channel foreground covariance.
+    Through the reference's own ``clarray`` (l rows by the wrapper trick), ``mkfullsky``'s jitter and
+    ``nputil.matrix_root_manynull``: the unpolarised T matrix at four l, and the polarised
+    blockdiag(T, E, B, V) matrix ((4 x 1024)^2) at l = 5.  Stored: num_pos, the retained eigenvalues
+    (squared column norms of the root), the retained root columns (T) and M M^T on a sampled index set."""
+    build_reference()
+    install_shims()
+    from cora.core import skysim
+    from cora.foreground import galaxy
+    from cora.util import nputil
+
+    rows = np.array([1, 5, 100, 700, 1535, 1536])
+    nz = 1024
+    freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+
+    def rows_cl(model):
+        def aps(l, z1, z2):
+            return model.angular_powerspectrum(rows[np.asarray(l)].astype(np.float64), z1, z2)
+        return skysim.clarray(aps, len(rows) - 1, freq)
+
+    clT = rows_cl(galaxy.FullSkySynchrotron())
+    clP = rows_cl(galaxy.FullSkyPolarisedSynchrotron())
+    out = {"rows": rows, "freq": freq}
+    sel = np.unique(np.linspace(0, nz - 1, 96).astype(int))
+    out["sel"] = sel
+    for i in (1, 2, 4):           # l = 5, 100, 1535
+        cm = clT[i] + np.identity(nz) * np.max(np.diag(clT[i])) * 1.0e-14          # skysim.py:116-117
+        root = nputil.matrix_root_manynull(cm.copy(), truncate=False)
+        _, npos = nputil.matrix_root_manynull(cm.copy(), truncate=True)
+        lam = (root**2).sum(axis=0)
+        tag = "T%d_" % rows[i]
+        out[tag + "num_pos"] = npos
+        out[tag + "evals"] = lam[lam > 0]
+        out[tag + "cols"] = root[:, lam > 0]
+        out[tag + "mmt_sel"] = (root @ root.T)[np.ix_(sel, sel)]
+        out[tag + "cl_sel"] = clT[i][np.ix_(sel, sel)]
+    # polarised block matrix at l = 5 (makesky.py:368-382)
+    i = 1
+    cv = np.zeros((4, nz, 4, nz))
+    cv[0, :, 0, :] = clT[i]
+    cv[1, :, 1, :] = clP[i]
+    cv[2, :, 2, :] = clP[i]
+    cv = cv.reshape(4 * nz, 4 * nz)
+    cm = cv + np.identity(4 * nz) * np.max(np.diag(cv)) * 1.0e-14
+    root = nputil.matrix_root_manynull(cm, truncate=False)
+    lam = (root**2).sum(axis=0)
+    keep = lam > 0
+    out["pol5_num_pos"] = int(keep.sum())
+    out["pol5_evals"] = lam[keep]
+    blk = np.array([[np.abs(root[b * nz:(b + 1) * nz, c]).max() > 0 for b in range(4)] for c in np.where(keep)[0]])
+    out["pol5_cols_per_block"] = blk.sum(axis=0)
+    psel = np.concatenate([b * nz + sel[::3] for b in range(4)])
+    out["pol5_sel"] = psel
+    out["pol5_mmt_sel"] = (root[psel] @ root[psel].T)
+    out["pol5_v_rows_max"] = np.abs(root[3 * nz:]).max()
+    np.savez(os.path.join(HERE, "root_large.npz"), **out)
+    print("root_large.npz written:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "all":

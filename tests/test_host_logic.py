@@ -125,3 +125,37 @@ def test_makesky_cli_parses(tmp_path, monkeypatch):
     assert seen["nside"] == 4 and seen["pol"] == "none" and seen["oversample"] == 2 and not seen["eor"]
     np.testing.assert_allclose(seen["freq"], [800.0, 700.0])
     assert np.load(out).shape == (2, 192)
+
+
+
+def test_fused_fill_only_for_the_package_own_spectrum():
+    """clarray's fused-kernel dispatch: a subclass overriding the spectrum (or a piece of it) must be
+    evaluated through the callable, like the reference's clarray always does."""
+    from cora_b200 import corr21cm, galaxy, skysim
+
+    fs = galaxy.FullSkySynchrotron.__new__(galaxy.FullSkySynchrotron)
+    assert skysim._fused_fill(fs.angular_powerspectrum, fs) is not None
+
+    class Tilted(galaxy.FullSkySynchrotron):
+        def angular_ps(self, l):
+            return 2.0 * super().angular_ps(l)
+
+    t = Tilted.__new__(Tilted)
+    assert skysim._fused_fill(t.angular_powerspectrum, t) is None
+
+    class Other(galaxy.FullSkySynchrotron):
+        def angular_powerspectrum(self, l, nu1, nu2):
+            return 0.0 * l
+
+    o = Other.__new__(Other)
+    assert skysim._fused_fill(o.angular_powerspectrum, o) is None
+    c = corr21cm.EoR21cm.__new__(corr21cm.EoR21cm)          # overrides T_b / bias only: still the fused kernel
+    assert skysim._fused_fill(c.angular_powerspectrum, c) is not None
+
+    class My21(corr21cm.Corr21cm):
+        def angular_powerspectrum(self, l, nu1, nu2, redshift=False):
+            return 1.0
+
+    m = My21.__new__(My21)
+    assert skysim._fused_fill(m.angular_powerspectrum, m) is None
+    assert skysim._fused_fill(lambda l, a, b: 1.0, None) is None
