@@ -47,6 +47,11 @@ WORKLOAD_TEXT = {
     "c4": "cora-makesky gaussianfg --pol full (T/E/B, spin-2 SHT) nside=512, 1024 channels 400-800 MHz",
     "c5": "cora-makesky 21cm nside=1024, 2048 channels 400-800 MHz",
 }
+# The default is the largest configuration that fits one GPU (config 3's 21cm half, nside 512 x 1024
+# channels, ~0.45 s/step on one B200), so that the driver's 1/2/4/8-GPU runs measure the regime the north star is
+# about; `--workload c2` is BASELINE.json's single-GPU config (16 ms/step) and is also measured in every default
+# run (the "secondary" block of the line).
+DEFAULT_WORKLOAD = "c3"
 METRIC = "full-sky map voxels/sec (pixels x channels)"
 UNIT = "voxels/s"
 
@@ -65,20 +70,21 @@ def sht_flops(nside, lmax, nchan):
 
 
 # =============================================================================== CPU arm
-def _cpu_fill_one(args):
-    """worker: C_l for one l (aps evaluation at all (9 nz)^2 sample pairs + both Romberg passes)."""
+def _cpu_fill_rows(args):
+    """worker: channel-averaged C_l of a block of channel rows (all columns) for one l: aps evaluation at the
+    (9 nrow) x (9 nz) sample pairs + both Romberg passes (what clarray does for these entries)."""
     import scipy.integrate as si
 
-    l, za, nz, zint, dx, h = args
-    clt = _CPU["aps"](np.array([l])[:, None, None], za[None, :, None], za[None, None, :])
-    clt = np.broadcast_to(clt, (1, nz * zint, nz * zint)).reshape(1, nz, zint, nz, zint)
+    l, za_rows, za, nrow, nz, zint, dx, h = args
+    clt = _CPU["aps"](np.array([l])[:, None, None], za_rows[None, :, None], za[None, None, :])
+    clt = np.broadcast_to(clt, (1, nrow * zint, nz * zint)).reshape(1, nrow, zint, nz, zint)
     clt = si.romb(clt, dx=dx, axis=4)
     clt = si.romb(clt, dx=dx, axis=2)
-    return clt[0] / (2 * h) ** 2
+    return float(clt.sum()) / (2 * h) ** 2
 
 
 def _cpu_leg_one(args):
-    """worker: Legendre stage of one m for all channels (lambda recursion + contraction)."""
+    """worker: Legendre stage of one m for a block of channels (lambda recursion + contraction)."""
     from oracle import sht as osht
 
     m, lmax, nchan, seed = args
@@ -108,8 +114,10 @@ def cpu_reference_setup(wp):
     return time.time() - t0
 
 
-def cpu_reference_step(wp, pool, ncores, scale=4):
-    """Time a bounded sample of the path on the host and extrapolate to the whole workload.
+def cpu_reference_step(wp, pool, ncores, budget=1.0):
+    """Time a BOUNDED sample of every stage of the path on the host and extrapolate linearly by work to the whole
+    workload (the C3 workload would take hours on the host: SURVEY 8d prescribes the sampling).  ``budget`` scales
+    the sample (1.0: about 20-60 s of wall time on 8-32 cores at any workload).
 
     Returns (extrapolated seconds for the whole workload, per-stage dict, sample description)."""
     import scipy.linalg as la
@@ -126,20 +134,41 @@ def cpu_reference_step(wp, pool, ncores, scale=4):
     dx = 2.0 * h / 2 ** wp["zromb"]
     za = (freq[:, None] + np.linspace(-h, h, zint)[None, :]).flatten()
 
-    # --- stage 1: C_l fill, one l per worker, ls spread over the range
-    n_l = max(1, ncores * scale)
+    # --- stage 1: C_l fill.  Work = evaluations of the spectrum; sample: n_l values of l x a subset of channel
+    # rows (all columns), dealt to the pool in blocks of rows.
+    evals_budget = 2.0e7 * ncores * budget
+    n_l = 8 if nz >= 1024 else 24
     ls = np.unique(np.linspace(1, lmax, n_l).astype(int))
+    rows_per_task = max(1, min(nz, int(2.0e6 // (zint * zint * nz)) or 1))
+    ntask = max(ncores, int(evals_budget / (len(ls) * rows_per_task * zint * zint * nz)))
+    ntask = min(ntask, max(1, nz // rows_per_task))
+    starts = np.unique(np.linspace(0, nz - rows_per_task, ntask).astype(int))
+    tasks = []
+    for l in ls:
+        for r0 in starts:
+            zr = (freq[r0:r0 + rows_per_task, None] + np.linspace(-h, h, zint)[None, :]).flatten()
+            tasks.append((int(l), zr, za, rows_per_task, nz, zint, dx, h))
     t0 = time.time()
-    cls = pool.map(_cpu_fill_one, [(int(l), za, nz, zint, dx, h) for l in ls])
+    pool.map(_cpu_fill_rows, tasks)
     t_fill_s = time.time() - t0
-    t_fill = t_fill_s * L / len(ls)
+    evals_done = len(tasks) * rows_per_task * zint * zint * nz
+    t_fill = t_fill_s * (float(L) * (zint * nz) ** 2) / evals_done
 
-    # --- stages 2-4: root, draws, apply for the same l's (BLAS threads)
+    # --- stages 2-4: root, draws, apply (BLAS/LAPACK threads) for sampled l on matrices of the workload's size.
+    # LAPACK/BLAS time does not depend on the matrix values: a synthetic covariance of the same conditioning
+    # class (21cm: positive definite -> Cholesky branch; foregrounds: the SCK closed form -> eigh branch at >= 1024 ch).
     rng = np.random.default_rng(0)
+    if wp["model"] == "21cm":
+        x = np.arange(nz, dtype=np.float64)
+        cm0 = np.exp(-np.abs(x[:, None] - x[None, :]) / 3.0)
+    else:
+        cm0 = _CPU["aps"](np.array([100.0]), freq[:, None], freq[None, :])
+    n_r = 3 if nz >= 1024 else 8
+    lr = np.unique(np.linspace(1, lmax, n_r).astype(int))
     t_root_s = t_draw_s = t_apply_s = 0.0
-    for l, c in zip(ls, cls):
+    for l in lr:
         t0 = time.time()
-        cm = c + np.identity(nz) * c.diagonal().max() * 1e-14
+        cm = cm0 + np.identity(nz) * cm0.diagonal().max() * 1e-14
         tr = onp.matrix_root_manynull(cm, truncate=False)
         t1 = time.time()
         g = onp.complex_std_normal((nz, l + 1), rng=rng)
@@ -149,36 +178,42 @@ def cpu_reference_step(wp, pool, ncores, scale=4):
         t_root_s += t1 - t0
         t_draw_s += t2 - t1
         t_apply_s += t3 - t2
-    wsum = float(np.sum(ls + 1))
+    wsum = float(np.sum(lr + 1))
     wall = L * (L + 1) / 2.0
-    t_root = t_root_s * L / len(ls)
+    t_root = t_root_s * L / len(lr)
     t_draw = t_draw_s * wall / wsum
     t_apply = t_apply_s * wall / wsum
 
-    # --- stage 5: inverse SHT (restatement of healpy.alm2map): Legendre over sampled m, phase over sampled rings
-    n_m = max(2, 2 * ncores * scale)
+    # --- stage 5: inverse SHT (restatement of healpy.alm2map): Legendre over sampled m for a block of channels,
+    # phase synthesis over sampled rings
+    ch_leg = min(nz, 64)
+    n_m = max(8, int(2 * ncores * budget))
     ms = np.unique(np.linspace(0, lmax, n_m).astype(int))
     t0 = time.time()
-    pool.map(_cpu_leg_one, [(int(m), lmax, nz, 7 + int(m)) for m in ms])
+    pool.map(_cpu_leg_one, [(int(m), lmax, ch_leg, 7 + int(m)) for m in ms])
     t_leg_s = time.time() - t0
-    t_leg = t_leg_s * wall / float(np.sum(lmax - ms + 1))
+    t_leg = t_leg_s * (wall / float(np.sum(lmax - ms + 1))) * (nz / float(ch_leg))
     nring = 4 * nside - 1
-    rs = np.unique(np.linspace(0, nring - 1, max(2, 2 * ncores * scale)).astype(int))
-    Fm = (rng.standard_normal((L, len(rs), nz)) + 1j * rng.standard_normal((L, len(rs), nz)))
-    out = np.empty((nz, npix))
+    ch_ph = min(nz, 32)
+    rs = np.unique(np.linspace(0, nring - 1, 16).astype(int))
+    Fm = (rng.standard_normal((L, len(rs), ch_ph)) + 1j * rng.standard_normal((L, len(rs), ch_ph)))
+    out = np.empty((ch_ph, npix))
     t0 = time.time()
     osht._rings_from_phase(Fm, _CPU["geom"], rs, out)
     t_ph_s = time.time() - t0
-    t_phase = t_ph_s * nring / len(rs)
+    pix_done = float(np.sum(_CPU["geom"]["nph"][rs]))
+    t_phase = t_ph_s * (npix / pix_done) * (nz / float(ch_ph))
 
     stages = {"cl_fill_s": t_fill, "root_s": t_root, "draws_s": t_draw, "apply_s": t_apply, "sht_legendre_s": t_leg,
               "sht_phase_s": t_phase}
     total = sum(stages.values())
-    sample = ("oracle port (numpy/scipy), %d-process fork pool + BLAS threads; per step: C_l fill + root/draw/apply for "
-              "%d of %d l (extrapolated x l-count / x sum(l+1)), SHT Legendre for %d of %d m and phase synthesis for "
-              "%d of %d rings, all %d channels (extrapolated by work); SHT leg is the restatement, not healpy; "
-              "sample wall %.1f s" % (ncores, len(ls), L, len(ms), L, len(rs), nring, nz,
-                                      t_fill_s + t_root_s + t_draw_s + t_apply_s + t_leg_s + t_ph_s))
+    sample = ("oracle port (numpy/scipy), %d-process fork pool + BLAS threads; per step: C_l fill of %d l x %d channel rows x "
+              "all %d columns (%.3g of %.3g evaluations, extrapolated by evaluations); root/draw/apply for %d l on a synthetic "
+              "covariance of the workload's size (extrapolated x l-count / x sum(l+1)); SHT Legendre for %d of %d m x %d of %d "
+              "channels and phase synthesis for %d of %d rings x %d channels (extrapolated by work); the SHT leg is the "
+              "restatement, not healpy; sample wall %.1f s"
+              % (ncores, len(ls), len(starts) * rows_per_task, nz, evals_done, float(L) * (zint * nz) ** 2, len(lr), len(ms), L,
+                 ch_leg, nz, len(rs), nring, ch_ph, t_fill_s + t_root_s + t_draw_s + t_apply_s + t_leg_s + t_ph_s))
     return total, stages, sample
 
 
@@ -320,6 +355,59 @@ class ClockSampler(object):
 
 
 # =============================================================================== GPU arm
+def _make_model(wp, torch):
+    """(model, one-off table build seconds)."""
+    if wp["model"] == "21cm":
+        from cora_b200 import corr21cm
+
+        model = corr21cm.Corr21cm()
+        t0 = time.time()
+        model.table()
+        torch.cuda.synchronize()
+        table_s = time.time() - t0
+    else:
+        from cora_b200 import galaxy
+
+        model = galaxy.FullSkySynchrotron()
+        table_s = 0.0
+    model.nside = wp["nside"]
+    model.frequencies = wp["freq"]
+    model.oversample = wp["zromb"]
+    return model, table_s
+
+
+def _measure_resident(sh, out, steps, warmup, barrier, lib, sampler=None):
+    """W warm-up steps, then K steps between barrier + synchronize, CUDA events on the launching stream.
+    Returns (ms for K steps, launches, {kernel kind: (ms, count)}, (t0, t1) perf_counter of the timed region)."""
+    import torch
+
+    for i in range(warmup):
+        sh.step(seed=1000 + i, out=out)
+    barrier()
+    lib.cora_b200_timing_enable(1)
+    n0 = lib.cora_b200_launch_count()
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    tc0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        sh.step(seed=i, out=out)
+    e1.record()
+    barrier()
+    tc1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = lib.cora_b200_launch_count() - n0
+    nk = lib.cora_b200_timing_kinds()
+    kms = (ctypes_double * nk)()
+    kcnt = (ctypes_ll * nk)()
+    lib.cora_b200_timing_read(kms, kcnt, nk)
+    lib.cora_b200_timing_enable(0)
+    kernels = {lib.cora_b200_timing_name(i).decode(): (kms[i], kcnt[i]) for i in range(nk)}
+    return ms, launches, kernels, (tc0, tc1)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -345,22 +433,7 @@ def run_ours(args):
 
     wp = workload_params(args.workload)
     nside, nchan, lmax, npix = wp["nside"], wp["nchan"], wp["lmax"], wp["npix"]
-    if wp["model"] == "21cm":
-        from cora_b200 import corr21cm
-
-        model = corr21cm.Corr21cm()
-        t0 = time.time()
-        model.table()
-        torch.cuda.synchronize()
-        table_s = time.time() - t0
-    else:
-        from cora_b200 import galaxy
-
-        model = galaxy.FullSkySynchrotron()
-        table_s = 0.0
-    model.nside = nside
-    model.frequencies = wp["freq"]
-    model.oversample = wp["zromb"]
+    model, table_s = _make_model(wp, torch)
     pol = wp["model"] == "gaussianfg_pol"
     npol = 4 if pol else 1
     sht_equiv = 5.0 if pol else 1.0    # T scalar + the (E,B)->(Q,U) pair = 4 scalar-equivalents; V is identically 0
@@ -378,50 +451,68 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value")
-    for i in range(args.warmup):
-        sh.step(seed=1000 + i, out=out)
-    barrier()
-    lib.cora_b200_timing_enable(1)
-    n0 = lib.cora_b200_launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    tc0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        sh.step(seed=i, out=out)
-    e1.record()
-    barrier()
-    tc1 = time.perf_counter()
-    clocks = sampler.stop(tc0, tc1) if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    launches = lib.cora_b200_launch_count() - n0
-    nk = lib.cora_b200_timing_kinds()
-    kms = (ctypes_double * nk)()
-    kcnt = (ctypes_ll * nk)()
-    lib.cora_b200_timing_read(kms, kcnt, nk)
-    lib.cora_b200_timing_enable(0)
-    kernels = {lib.cora_b200_timing_name(i).decode(): (kms[i], kcnt[i]) for i in range(nk)}
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        tt = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+        return float(tt.item())
+
+    # ---- N > 1: the sharded run must reproduce the single-GPU path (same seed) for this rank's channel block
+    parity = None
+    parity_note = None
+    if world > 1:
+        if pol:
+            parity_note = "not run: the single-GPU polarised path does not fit beside the sharded buffers"
+        else:
+            need = 8.0 * (lmax + 1) * nchan * nchan * 2 + 16.0 * (lmax + 1) * (lmax + 2) / 2 * nchan * 2.2 + 8.0 * sh.cb * npix
+            free = torch.cuda.mem_get_info()[0]
+            if need > 0.8 * free:
+                parity_note = "not run: the single-GPU path needs %.0f GB, %.0f GB free" % (need / 1e9, free / 1e9)
+            else:
+                sky = sh.step(seed=4242, out=out)
+                lo = int(sh.plan.chan_lo[rank])
+                ref = cdist.single_gpu_block(model, nside, wp["freq"], lmax, wp["zromb"], 4242, lo, lo + sh.cb)
+                err = float((sky - ref).abs().max() / ref.abs().max())
+                del ref
+                torch.cuda.empty_cache()
+                parity = allmax(err)
+                if not parity <= 1e-12:
+                    raise SystemExit("bench.py: sharded maps differ from the single-GPU path: max rel diff %.3e > 1e-12" % parity)
+        barrier()
+
+    # ---- device-resident throughput ("value")
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, kernels, (tc0, tc1) = _measure_resident(sh, out, args.steps, args.warmup, barrier, lib, sampler)
+    clocks = sampler.stop(tc0, tc1) if rank == 0 else None
+    ms = allmax(ms)
+    if world > 1:
         lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
     voxels = float(npix) * nchan * npol
     value = voxels * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the public API, host buffers in / host maps out ("e2e")
+    # columns the apply kernel really multiplies per l (it skips the zero triangle of Cholesky roots and the
+    # leading all-zero columns of eigen-branch roots): read back from the root stage's flags
     nl_local, cb_local = sh.nl, sh.cb
+    l_local = np.asarray(sh.l_list, dtype=np.float64)
+    try:
+        used = sh._buf["root"][1].cpu().numpy().reshape(-1, nl_local)          # [blocks, nl]
+        cols = np.where(used == 0, (nchan + 1) / 2.0, nchan - (used - 1.0))
+        fields = np.array([1.0, 2.0])[:used.shape[0]] if pol else np.ones(used.shape[0])   # E and B share the polarised root
+        apply_flops = float(np.sum(fields[:, None] * 4.0 * nchan * cols * (l_local[None, :] + 1.0)))
+        n_eigh = int((used > 0).sum())
+    except Exception:
+        apply_flops, n_eigh = None, None
+
+    # ---- end to end through the public API, host buffers in / host maps out ("e2e")
     exchange_mode = sh.exchange
     if world > 1 and sh.exchange == "p2p":
-        sh.peers.check()             # a timed-out peer barrier would have produced garbage: fail loudly
+        sh.peers.check()             # (non-fatal mode) a timed-out peer barrier would have produced garbage
     if world == 1 and not pol:
         del sh                       # the resident-path buffers go back to the allocator first
+        sh = None
     del out
     torch.cuda.empty_cache()
     e2e_steps = max(1, min(args.steps, 5))
@@ -431,6 +522,8 @@ def run_ours(args):
         if world == 1 and not pol:
             np.random.seed(seed)
             return model.getsky()  # Sky3d.getsky(): clarray + mkfullsky -> numpy float64[nfreq, npix]
+        if not pol:
+            return sh.getsky(seed=seed)          # ShardedSky.getsky(): this rank's channels -> numpy (pinned, persistent)
         sky = sh.step(seed=seed)
         sky = sky.reshape(sky.shape[0], -1)
         if sky.numel() * 8 > (4 << 30):          # too large to hold pinned: stream it through a staging ring
@@ -438,12 +531,17 @@ def run_ours(args):
             return sky[:, :0].cpu().numpy().reshape(sky.shape[0], 0)
         return _dev.to_host(sky)   # this rank's channels -> pinned host array
 
+    if world == 1 and not pol:
+        e2e_api = "%s.getsky() -> numpy" % type(model).__name__
+    elif not pol:
+        e2e_api = "dist.ShardedSky.getsky() -> numpy (this rank's channels)"
+    else:
+        e2e_api = "dist.ShardedPolSky.step() -> host"
     e2e_error = None
     e2e_each = []
     try:
         e2e_once(99)  # warm the pinned-buffer cache (two passes: the first one allocates the host block,
-        if float(npix) * cb_local * 8 * npol < (4 << 30):
-            e2e_once(98)  # the second confirms torch's host allocator hands the same block back)
+        e2e_once(98)  # the second confirms the allocator hands the same block back)
         _dev.traffic["h2d"] = _dev.traffic["d2h"] = 0
         barrier()
         t0 = time.perf_counter()
@@ -456,7 +554,7 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
     except (torch.OutOfMemoryError, RuntimeError) as exc:   # only the oversized extra workloads get here
-        if args.workload == "c2":
+        if args.workload in ("c2", DEFAULT_WORKLOAD):
             raise
         e2e_error = "%s: %s" % (type(exc).__name__, str(exc)[:120])
         e2e_s = float("inf")
@@ -496,11 +594,11 @@ def run_ours(args):
     L = lmax + 1
     nalm = L * (L + 1) / 2.0
     nring = 4 * nside - 1
-    sum_l1 = float(np.sum(np.arange(L)[rank::world] + 1)) if world > 1 else nalm   # sum over local l of (l+1)
+    sum_l1 = float(np.sum(l_local + 1.0))   # sum over local l of (l+1)
 
     def _stage(name, work, unit_scale, peak, bound, what):
         t_ms = stage_share.get(name)
-        if not t_ms:
+        if not t_ms or work is None:
             return None
         ach = work / (t_ms * 1e-3) / unit_scale
         return {"ms": t_ms, "bound": bound, "achieved": round(ach, 3), "peak": round(peak, 1), "frac": round(ach / peak, 4),
@@ -514,8 +612,10 @@ def run_ours(args):
         "sht_phase": _stage("sht_phase", (3 if pol else 1) * cb_local * (16.0 * nring * L + 8.0 * npix), 1e9, hbm_peak,
                             "hbm floor (measured: FP64 issue-bound FFT butterflies)",
                             "16*nring*L + 8*npix bytes per channel (F read + map written)"),
-        "apply": _stage("apply", (3 if pol else 1) * 2.0 * nchan * nchan * sum_l1 * 2 / 2.0, 1e12, pk, "tensor(fp64 DMMA)",
-                        "2*nz^2*(l+1) real flop per l for complex draws, halved for the triangular (Cholesky) roots"),
+        "apply": _stage("apply", apply_flops, 1e12, pk, "tensor(fp64 DMMA)",
+                        "4*nz*cols(l)*(l+1) real flop per l (complex draws, real root); cols(l) = the columns the kernel "
+                        "multiplies: (nz+1)/2 for a triangular Cholesky root, the retained columns of an eigen-branch root "
+                        "(%s of %d local roots are eigen-branch)" % (n_eigh, nl_local * (2 if pol else 1))),
         "cholesky": _stage("cholesky", (2 if pol else 1) * nl_local * nchan ** 3 / 3.0, 1e12, pk, "tensor(fp64 DMMA) / latency",
                            "nz^3/3 flop per l"),
         "draw": _stage("draw", (3 if pol else 1) * 16.0 * nchan * sum_l1, 1e9, hbm_peak, "hbm (measured: FP64 ALU-bound Box-Muller)",
@@ -524,9 +624,28 @@ def run_ours(args):
                           "8*L*nz^2 output bytes; %.3g evaluations of the 2-D interpolant" % (L * (zi * nchan) ** 2 / 2.0 / world)),
     }
     stage_roofline = {k: v for k, v in stage_roofline.items() if v}
-    if (world > 1 or pol) and exchange_mode == "p2p":
+    if sh is not None and exchange_mode == "p2p" and (world > 1 or pol):
         sh.peers.check()
         sh.peers.close()
+    sh = None
+    torch.cuda.empty_cache()
+
+    # ---- secondary: BASELINE.json's single-GPU configuration (C2) measured in the same run, device-resident
+    secondary = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_secondary:
+        wp2 = workload_params("c2")
+        model2, _ = _make_model(wp2, torch)
+        sh2 = cdist.ShardedSky(model2, wp2["nside"], wp2["freq"], lmax=wp2["lmax"], zromb=wp2["zromb"], rank=rank, size=world)
+        out2 = torch.empty((sh2.cb, wp2["npix"]), dtype=torch.float64, device="cuda")
+        ms2, _, k2, _ = _measure_resident(sh2, out2, max(args.steps, 10), args.warmup, barrier, lib)
+        ms2 = allmax(ms2) / max(args.steps, 10)
+        if sh2.exchange == "p2p" and world > 1:
+            sh2.peers.check()
+            sh2.peers.close()
+        secondary = {"workload": WORKLOAD_TEXT["c2"], "ms_per_step": ms2,
+                     "value": float(wp2["npix"]) * wp2["nchan"] / (ms2 * 1e-3), "unit": UNIT, "steps": max(args.steps, 10),
+                     "stage_ms_per_step": {k: round(v[0] / max(args.steps, 10), 4) for k, v in k2.items() if v[1]}}
+        del sh2, out2
 
     if rank != 0:
         if world > 1:
@@ -544,6 +663,8 @@ def run_ours(args):
         except Exception as exc:  # the GPU numbers stand on their own
             cpu_baseline = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % (exc,)}
 
+    leg_kernel = ("sht_legendre_kernel<2> + sht_legendre_ws_kernel (FP64 DMMA)" if pol else
+                  "sht_legendre_ws_kernel (FP64 DMMA, warp-specialised, TMA-fed)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -559,18 +680,25 @@ def run_ours(args):
                    "stage_ms_per_step": stage_share,
                    "stage_roofline": stage_roofline, "hbm_peak_source": hbm_src},
         "e2e": {"value": None, "unit": UNIT, "error": e2e_error} if e2e_error else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-                "steps": e2e_steps, "ms_each": e2e_each, "host_bound_to_gpu_numa_node": numa_bound, "api": "Corr21cm.getsky() -> numpy" if (world == 1 and not pol) else "dist.Sharded%sSky.step() -> host" % ("Pol" if pol else "")},
+                "steps": e2e_steps, "ms_each": e2e_each, "host_bound_to_gpu_numa_node": numa_bound, "api": e2e_api},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "sht_legendre_kernel<0> (FP64 DMMA)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": leg_kernel, "achieved": achieved,
                      "peak": float(peak[0]), "unit": "TFLOP/s", "frac": achieved / float(peak[0]) if peak[0] else None,
                      "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, profiles/ncu_traffic.json)",
                      "algorithmic_bytes_per_launch": 16.0 * cb_local * ((lmax + 1) * (lmax + 2) / 2 + (4 * nside - 1) * (lmax + 1)),
                      "peak_source": "FP64 DMMA peak measured in this run by cora_b200_fp64_peak (MEASURED_PEAKS.json "
                                     "has no FP64 entry; 37.1 TFLOP/s recorded in profiles/microbench/)",
-                     "flops_per_launch": flops_per_launch, "launch_ms": leg_ms / max(1, leg_n)},
+                     "flops_per_launch": flops_per_launch, "launch_ms": leg_ms / max(1, leg_n),
+                     "note": "frac is algorithmic flop (incl. the polar (ring, m, l) octets the kernel skips) over the DMMA peak"},
         "cpu_baseline": cpu_baseline,
     }
+    if world > 1:
+        line["parity_vs_single_gpu"] = parity
+        if parity_note:
+            line["parity_vs_single_gpu_note"] = parity_note
+    if secondary:
+        line["secondary"] = secondary
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -588,8 +716,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 block measured next to the default workload")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU

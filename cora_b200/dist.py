@@ -147,6 +147,7 @@ class ShardedSky(object):
         self.nl = len(self.l_list)
         self.cb = int(self.plan.cb[rank])
         self.npix = 12 * self.nside**2
+        self.zromb = int(zromb)
         za, self.zint = skysim._sample_frequencies(self.freq, zromb, None)
         self.fill_inputs = model._b200_fill_inputs(za, skysim.romberg_weights(zromb))
         base, width = self.plan.nu_tables(rank)
@@ -381,6 +382,50 @@ class ShardedSky(object):
         self.peers.barrier()
         return self.p2p_sht(k, out=out)
 
+    def getsky(self, seed=None, nbatch=4):
+        """The public end-to-end call of the sharded generator -- ``Sky3d.getsky`` (``cora/core/maps.py:227-235``)
+        for one rank of a multi-GPU run: host frequency axis in, this rank's channels out as a numpy
+        ``float64[cb, npix]`` array.  Every call uploads the per-sample vectors again (what ``clarray`` does per call),
+        runs fill -> root -> draw/apply -> exchange, and transforms the channels in ``nbatch`` batches whose device ->
+        host copies overlap the next batch.  The result lives in a pinned buffer owned by this object and is
+        overwritten by the next call.  No ``torch.distributed`` collective is issued on the p2p path."""
+        from . import skysim
+
+        t = _dev.torch()
+        if seed is None:
+            seed = int(np.random.randint(0, 2**31 - 1))
+        za, _ = skysim._sample_frequencies(self.freq, self.zromb, None)
+        self.fill_inputs = self.model._b200_fill_inputs(za, skysim.romberg_weights(self.zromb))
+        L = self.lmax + 1
+        nalm = L * (L + 1) // 2
+        if self.exchange == "p2p":
+            k = self._k & 1
+            self._k += 1
+            if self.p2p_fill(k):
+                self.peers.barrier()
+            self.p2p_alm(k, seed=seed)
+            self.peers.barrier()
+            st = self._p2p_setup()
+            panel = self._persistent("panel_view%d" % k, lambda: st["panel"][k].tensor((nalm, self.cb), t.complex128))
+        else:
+            cla = self.fill()
+            send = self.alm_local(cla, seed=seed)
+            if self.size == 1:
+                panel = send
+            else:
+                rbuf = self._persistent("recv", lambda: _dev.empty((sum(self.plan.recv_splits(self.rank)),), t.complex128))
+                recv = exchange(send, self.plan, self.rank, self.group, out=rbuf)
+                panel = self._persistent("panel", lambda: _dev.empty((nalm, self.cb), t.complex128))
+                _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(recv), _lib.ptr(self.l_off), self.lmax, self.cb,
+                          _lib.ptr(panel), self.cb, 0, _lib.stream_ptr())
+        host = self._persistent("host_maps", lambda: t.empty((self.cb, self.npix), dtype=t.float64, pin_memory=True))
+        sky = hputil.alm2map_to_host(panel, self.nside, self.lmax, self.cb, nbatch=nbatch, host=host, cache=self._buf)
+        mean = np.asarray(self.model.mean_nu(self.freq), dtype=np.float64) if hasattr(self.model, "mean_nu") else None
+        if mean is not None and mean.any():
+            lo = int(self.plan.chan_lo[self.rank])
+            sky += mean[lo:lo + self.cb, None]          # the reference's host-side broadcast add (maps.py:235)
+        return sky
+
     def close(self):
         """Check the barrier status and release the peer buffers (collective when a real PeerGroup is used)."""
         if self.exchange == "p2p" and self.peers is not None:
@@ -401,6 +446,24 @@ class ShardedSky(object):
             rbuf = self._persistent("recv", lambda: _dev.empty((sum(self.plan.recv_splits(self.rank)),), _dev.torch().complex128))
         recv = exchange(send, self.plan, self.rank, self.group, out=rbuf)
         return self.synthesize(recv, out=out)
+
+
+def single_gpu_block(model, nside, frequencies, lmax, zromb, seed, chan_lo, chan_hi):
+    """The single-GPU path (all l, all channels for fill / root / apply on this device) with the inverse SHT of
+    channels [chan_lo, chan_hi) only: what a rank of a sharded run must reproduce for its channel block (Philox
+    counters are keyed by (l, m, nu), so the maps do not depend on the number of ranks).  CUDA ``float64[n, npix]``."""
+    t = _dev.torch()
+    one = ShardedSky(model, nside, frequencies, lmax=lmax, zromb=zromb, rank=0, size=1, exchange="collective")
+    cla = one.fill()
+    panel = one.alm_local(cla, seed=seed)          # PANEL [nalm, nz]
+    n = int(chan_hi) - int(chan_lo)
+    out = _dev.empty((n, one.npix), t.float64)
+    plan = _dev.sht_plan(one.nside, one.lmax)
+    ws, nbytes = _dev.sht_workspace(plan, _lib.ALM_PANEL, n)
+    _lib.call("cora_b200_alm2map", plan, _lib.ptr_off(panel, 16 * int(chan_lo)), _lib.ALM_PANEL, one.nz, n, _lib.ptr(out),
+              _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+    t.cuda.current_stream().synchronize()
+    return out
 
 
 def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, partition="interleaved", seed=0, gauss=None,

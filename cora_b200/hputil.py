@@ -75,20 +75,26 @@ def alm2map_device(alm_dev, nside, lmax, layout, alm_stride, nchan, out=None, st
     return out
 
 
-def alm2map_to_host(alm_panel, nside, lmax, nchan, nbatch=4):
+def alm2map_to_host(alm_panel, nside, lmax, nchan, nbatch=4, host=None, cache=None):
     """Scalar synthesis of a PANEL alm array straight into a pinned host array: the channels are
     transformed in ``nbatch`` batches and every finished batch is copied back on a second
     stream while the next one is computed (the PCIe copy of the float64 maps takes longer than
-    the transform itself)."""
+    the transform itself).  ``host``: a pinned ``float64[nchan, npix]`` tensor to fill (default: a new
+    one); ``cache``: a dict that keeps the device staging buffers and the workspace between calls."""
     t = _dev.torch()
     npix = 12 * nside * nside
     plan = _dev.sht_plan(nside, lmax)
-    host = t.empty((nchan, npix), dtype=t.float64, pin_memory=True)
+    if host is None:
+        host = t.empty((nchan, npix), dtype=t.float64, pin_memory=True)
     cb = max(16, -(-nchan // nbatch))
     cb += (-cb) % 16
     main, side = t.cuda.current_stream(), _dev.copy_stream()
-    bufs = [_dev.empty((min(cb, nchan), npix), t.float64) for _ in range(2)]
-    ws, nbytes = _dev.sht_workspace(plan, _lib.ALM_PANEL, min(cb, nchan))
+    cache = {} if cache is None else cache
+    key = ("a2m_host", nside, lmax, min(cb, nchan))
+    if key not in cache:
+        bufs = [_dev.empty((min(cb, nchan), npix), t.float64) for _ in range(2)]
+        cache[key] = (bufs,) + _dev.sht_workspace(plan, _lib.ALM_PANEL, min(cb, nchan))
+    bufs, ws, nbytes = cache[key]
     freed = [None, None]
     stride = int(alm_panel.shape[1])
     for i, c0 in enumerate(range(0, nchan, cb)):
@@ -205,9 +211,10 @@ def sphtrans_inv_sky(alm, nside, device_out=False):
 
 # ------------------------------------------------------------------ forward transform
 # cora calls healpy.map2alm with use_weights=True, iter=2 (``hputil.py:46-47``).  healpy's ring
-# weights are data files of the healpy distribution (not available here): pass them explicitly
-# as ``ring_weights`` (absolute weights of the 2*nside northern rings) to reproduce that mode.
-_weight = True
+# weights are data files of the healpy distribution (not available here), so every forward transform below
+# is UNWEIGHTED unless the caller passes ``ring_weights`` (absolute weights of the 2*nside northern rings
+# incl. the equator): results then differ from cora.util.hputil at the quadrature-error level that the
+# ``iter`` Jacobi refinements leave (``mkconstrained`` is unaffected: healpy's default there is unweighted).
 _iter = 2
 
 
@@ -297,7 +304,8 @@ def _nside_of(npix):
 
 
 def sphtrans_real(hpmap, lmax=None, lside=None, ring_weights=None):
-    """Spherical harmonic transform of a real map -> ``alm[l, m]``, m >= 0 (``hputil.py:195-234``)."""
+    """Spherical harmonic transform of a real map -> ``alm[l, m]``, m >= 0 (``hputil.py:195-234``).
+    Unweighted quadrature + 2 refinements unless ``ring_weights`` is given (see the note above ``_iter``)."""
     t = _dev.torch()
     hpmap = np.ascontiguousarray(hpmap, dtype=np.float64)
     nside = _nside_of(hpmap.size)

@@ -11,45 +11,57 @@ below return the ``(nfreq, npol, npix)`` arrays the commands would write.
 import numpy as np
 
 
+def _axis_centre(start, stop, num):
+    """``num`` channel centres from ``start`` towards ``stop``, the last one a channel short of ``stop``."""
+    return np.linspace(start, stop, num, endpoint=False), abs(stop - start) / num
+
+
+def _axis_centre_nyquist(start, stop, num):
+    """Centres including both ends (the Nyquist channel is kept)."""
+    return np.linspace(start, stop, num, endpoint=True), abs((stop - start) / (num - 1))
+
+
+def _axis_edge(start, stop, num):
+    """``start`` / ``stop`` are the band edges; the width keeps the sign of the axis direction."""
+    width = (stop - start) / num
+    return start + width * (np.arange(num) + 0.5), width
+
+
+_AXIS_MODES = {"centre": _axis_centre, "centre_nyquist": _axis_centre_nyquist}
+
+
 class FreqState(object):
-    """Process and store the frequency spec (``makesky.py:44-92``)."""
+    """The frequency specification of ``cora-makesky`` and the channel axis it stands for
+    (same attributes, defaults and results as ``cora/scripts/makesky.py:44-92``).
+
+    ``freq = (start, stop, number)`` in MHz with ``freq_mode`` one of ``centre`` (default; the CHIME band
+    800 -> 400 MHz in 1025 channels unless set), ``centre_nyquist`` or -- any other value -- ``edge``;
+    ``channel_bin`` averages groups of neighbouring channels, ``channel_list`` (which takes precedence) or
+    ``channel_range = (first, last + 1)`` select a subset afterwards."""
 
     def __init__(self):
         self.freq = (800.0, 400.0, 1025)
-        self.channel_range = None
-        self.channel_list = None
-        self.channel_bin = 1
         self.freq_mode = "centre"
-
-    @property
-    def frequencies(self):
-        """The frequency centres in MHz."""
-        return self._calculate()[0]
-
-    @property
-    def freq_width(self):
-        """The frequency width in MHz."""
-        return self._calculate()[1]
+        self.channel_bin = 1
+        self.channel_list = None
+        self.channel_range = None
 
     def _calculate(self):
-        sf, ef, nf = self.freq
-        if self.freq_mode == "centre":
-            df = abs(ef - sf) / nf
-            frequencies = np.linspace(sf, ef, nf, endpoint=False)
-        elif self.freq_mode == "centre_nyquist":
-            df = abs((ef - sf) / (nf - 1))
-            frequencies = np.linspace(sf, ef, nf, endpoint=True)
-        else:
-            df = (ef - sf) / nf
-            frequencies = sf + df * (np.arange(nf) + 0.5)
-        if self.channel_bin > 1:
-            frequencies = frequencies.reshape(-1, self.channel_bin).mean(axis=1)
-            df = df * self.channel_bin
+        """-> (channel centres, channel width) in MHz."""
+        centres, width = _AXIS_MODES.get(self.freq_mode, _axis_edge)(*self.freq)
+        nbin = self.channel_bin
+        if nbin > 1:
+            centres = centres.reshape(-1, nbin).mean(axis=1)
+            width = width * nbin
         if self.channel_list is not None:
-            frequencies = frequencies[self.channel_list]
+            centres = centres[self.channel_list]
         elif self.channel_range is not None:
-            frequencies = frequencies[self.channel_range[0] : self.channel_range[1]]
-        return frequencies, df
+            first, end = self.channel_range[0], self.channel_range[1]
+            centres = centres[first:end]
+        return centres, width
+
+    frequencies = property(lambda self: self._calculate()[0], doc="The frequency centres in MHz.")
+    freq_width = property(lambda self: self._calculate()[1], doc="The frequency width in MHz.")
 
 
 def make_21cm(fstate, nside, pol="full", eor=False, oversample=None):
