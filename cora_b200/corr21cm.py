@@ -178,25 +178,41 @@ class Corr21cm(maps.Sky3d):
         vectors chi, b, f, pf, D (host cosmology, ``corr.py:944-951``) and the Romberg weights."""
         t = _dev.torch()
         z = NU21 / np.asarray(nu_samples, dtype=np.float64) - 1.0
-        vec = _dev.to_device(self._sample_vectors(z), t.float64)  # [5, nz*zint]
-        return self.table(), vec, _dev.to_device(w, t.float64)
+        hv = self._sample_vectors(z)
+        vec = _dev.to_device(hv, t.float64)  # [5, nz*zint]
+        # kernel choice: the row-weight kernel reads every distinct table row of a channel pair's y window once; its
+        # window is ~2 x (comoving width of a channel) x 20/pi rows tall.  Tall windows (wide channels) favour the
+        # per-sample-pair kernel (measured: 256 channels over 400-800 MHz, ~100-140 rows: 4.3 vs 5.0 ms; 1024 channels,
+        # ~30 rows: 104 vs 44 ms).
+        zint = len(w)
+        chi = hv[0].reshape(-1, zint)
+        rows = 2.0 * float(np.max(np.abs(chi[:, -1] - chi[:, 0]))) * (20.0 / np.pi) if zint > 1 else 0.0
+        variant = 1 if rows > 80.0 else 0
+        forced = os.environ.get("CORA_B200_FILL_VARIANT")          # "0" / "1": A/B runs and tests
+        if forced in ("0", "1"):
+            variant = int(forced)
+        return self.table(), vec, _dev.to_device(w, t.float64), variant
 
     # skysim.clarray takes the fused kernel only while these methods are the ones defined here (T_b, bias_z,
     # growth_* and the cosmology enter through _sample_vectors and may be overridden freely, e.g. EoR21cm)
     _b200_fill_methods = ("angular_powerspectrum", "_b200_fill", "_b200_fill_inputs", "_sample_vectors")
+    _b200_fill_lower = True      # the fill kernel writes lower triangles; skysim.clarray mirrors them
 
-    def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None):
-        tab, vec, wd = inputs
+    def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None, lower_only=False):
+        """``lower_only``: write the entries ``(i, j <= i)`` only -- all the root stage reads; the upper triangle of
+        ``out`` is left as it was."""
+        tab, vec, wd, variant = inputs
         _lib.call("cora_b200_cl_fill_21cm", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
                   _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(l0), int(l_step), int(nl), int(nz), int(zint),
-                  _lib.ptr(out), _lib.stream_ptr(stream))
+                  _lib.ptr(out), int(bool(lower_only)), int(variant), _lib.stream_ptr(stream))
 
 
-    def _b200_fill_pairs(self, inputs, nl, nz, zint, pair0, npairs, out_ptrs, l_owner, l_row, stream=None):
-        """Pair-sharded fill with the rows scattered to the GPUs owning each l (multi-GPU path)."""
-        tab, vec, wd = inputs
-        _lib.call("cora_b200_cl_fill_21cm_pairs", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
-                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(nl), int(nz), int(zint), int(pair0), int(npairs),
+    def _b200_fill_tiles(self, inputs, nl, nz, zint, tile0, ntiles, out_ptrs, l_owner, l_row, stream=None):
+        """Fill sharded over channel-pair tiles with the rows scattered to the GPUs owning each l (multi-GPU path;
+        lower triangle only)."""
+        tab, vec, wd, variant = inputs
+        _lib.call("cora_b200_cl_fill_21cm_tiles", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
+                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(nl), int(nz), int(zint), int(tile0), int(ntiles), int(variant),
                   _lib.ptr(out_ptrs), _lib.ptr(l_owner), _lib.ptr(l_row), _lib.stream_ptr(stream))
 
 

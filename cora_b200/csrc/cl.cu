@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
                                                         const double* __restrict__ w, int l0, int l_step, int nl, int nz,
                                                         int zint, double* __restrict__ out, long long pair0,
                                                         double* const* __restrict__ out_ptrs,
-                                                        const int* __restrict__ l_owner, const int* __restrict__ l_row) {
+                                                        const int* __restrict__ l_owner, const int* __restrict__ l_row,
+                                                        const long long* __restrict__ tile_start, int lower_only) {
     extern __shared__ __align__(16) unsigned char smraw[];
     PairPre* pre = (PairPre*)smraw;                                     // [zint*zint]
     double* R = (double*)(smraw + sizeof(PairPre) * zint * zint);        // [FILL_EB][FILL_WMAX]
@@ -209,13 +210,27 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
     // decode the channel pair.  Pairs are enumerated diagonal by diagonal (d = i - j, then j): CTAs that
     // run together then share almost the same band of table rows (y ~ |chi_i - chi_j|), which keeps
     // the band in L2 instead of re-reading it from HBM.  first(d) = d nz - d (d - 1) / 2.
-    const long long pidx = pair0 + blockIdx.x;
-    int d = (int)(((2.0 * nz + 1.0) - sqrt((2.0 * nz + 1.0) * (2.0 * nz + 1.0) - 8.0 * (double)pidx)) * 0.5);
-    d = max(0, min(nz - 1, d));
-    while (d + 1 < nz && (long long)(d + 1) * nz - (long long)(d + 1) * d / 2 <= pidx) d++;
-    while (d > 0 && (long long)d * nz - (long long)d * (d - 1) / 2 > pidx) d--;
-    const int j = (int)(pidx - ((long long)d * nz - (long long)d * (d - 1) / 2));
-    const int i = j + d;
+    int i, j;
+    if (tile_start) {
+        // tile enumeration of the row-weight kernel (4 CTAs per tile (i; j0 .. j0+3), pair0 = first tile)
+        const long long tidx = pair0 + (blockIdx.x >> 2);
+        int lo = 0, hi = nz - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_start[mid] <= tidx) lo = mid; else hi = mid - 1;
+        }
+        j = 4 * (int)(tidx - tile_start[lo]) + (blockIdx.x & 3);
+        i = 4 * (int)(tidx - tile_start[lo]) + lo;
+        if (j > i) return;
+    } else {
+        const long long pidx = pair0 + blockIdx.x;
+        int d = (int)(((2.0 * nz + 1.0) - sqrt((2.0 * nz + 1.0) * (2.0 * nz + 1.0) - 8.0 * (double)pidx)) * 0.5);
+        d = max(0, min(nz - 1, d));
+        while (d + 1 < nz && (long long)(d + 1) * nz - (long long)(d + 1) * d / 2 <= pidx) d++;
+        while (d > 0 && (long long)d * nz - (long long)d * (d - 1) / 2 > pidx) d--;
+        j = (int)(pidx - ((long long)d * nz - (long long)d * (d - 1) / 2));
+        i = j + d;
+    }
     const int npair = zint * zint;
     const int tid = threadIdx.x;
     const double PI = 3.14159265358979323846;
@@ -360,8 +375,451 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
                 o = out_ptrs[l_owner[l]] + (long long)l_row[l] * nz2;
             }
             o[oij] = acc[q];
-            if (i != j) o[oji] = acc[q];
+            if (i != j && !lower_only) o[oji] = acc[q];
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------- 21cm fill, row-weight form
+// The sum over the zint^2 sample pairs e of a channel pair is linear in the table entries:
+//     R_e[x] = sum_t c_t(e) [ (1 - wy_e) T_t[y0_e][x] + wy_e T_t[y1_e][x] ]        (y-interpolated, combined row)
+//     Cbar_l = sum_e interp_x(R_e; x_e(l)),   x_e(l) = (log10 l - shift_e) xscale = X_g(l) - delta_e,
+// where the samples are split into G groups of neighbouring shift, X_g is taken at the mid shift of group g and
+// |delta_e| <= Delta_g/2 << 1 (Delta ~ 0.12 / G at 256 channels, 0.03 / G at 1024: the sample points of one channel
+// pair see almost the same k_perp).  Whenever every x_e(l) of a group lies in the cell k = floor(X_g) of X_g itself,
+//     sum_{e in g} = S_g[k] + (X_g - k)(S_g[k+1] - S_g[k]) - (V_g[k+1] - V_g[k]),
+//     S_g[x] = sum_{e in g} R_e[x],   V_g[x] = sum_{e in g} delta_e R_e[x],
+// and S_g, V_g are weighted sums over the DISTINCT table rows of the pair's y window,
+//     S_g[x] = sum_t sum_y A_gt[y] T_t[y][x],   A_gt[y] = sum_{e in g} c_t(e) [(1 - wy_e) 1(y = y0_e) + wy_e 1(y = y1_e)]
+// (B_gt, V_g likewise with delta_e): ~30 rows x 3 tables per x at 1024 channels instead of 81 x 6 table reads, and G
+// x-interpolations per l instead of 81.  The l whose X_g sits within Delta_g/2 of a cell boundary ("slow", a
+// fraction Delta_g of them) have some x_e in the neighbouring cell; for those e the piecewise-linear interpolant
+// differs from the linear extension of cell k by |x_e - b| D2_e[b] (b the boundary crossed, D2_e the second
+// difference of R_e at b), which a flat pass over the (slow l, sample) candidates adds exactly.  Everything is
+// summed in a fixed order: the table is deterministic.  It agrees with the per-sample-pair evaluation (the
+// reference's order, `cl21_fill_kernel` above) to a few ulp of the row's largest entry (tests/test_gpu_spectra.py).
+//
+// One CTA walks a 1 x 4 tile of channel pairs (i; j0 .. j0+3): its four 8-byte stores per l land in one 32-byte
+// sector within microseconds and merge in L2 (the per-pair kernel's lone 8-byte stores cost a DRAM
+// read-modify-write each: 100 GB of DRAM traffic for a 12.9 GB table at 1024 channels).  With lower_only the
+// mirror element (j, i) is not written: the root stage reads the lower triangle only (LAPACK-style).
+constexpr int F3_THREADS = 320;
+constexpr int F3_TILE = 4;        // j-adjacent channel pairs per CTA
+constexpr int F3_GMAX = 4;        // shift groups per channel pair: 4 for short y windows, 2 for tall ones
+constexpr int F3_YSPLIT = 64;     // y windows taller than this use 2 groups (the band pass costs 2 G FMAs per table entry)
+constexpr int F3_WMAX = 352;      // widest x band
+constexpr int F3_YWMAX = 192;     // tallest y window of one pair (256 channels over 400-800 MHz: up to ~140 rows)
+constexpr int F3_NPMAX = 81;      // largest zint^2 on the banded path (zromb <= 3; larger: direct evaluation)
+constexpr int F3_LISTMAX = 768;   // (slow l, group) entries listed per pair (more: evaluated directly)
+constexpr int F3_WDOUBLES = F3_GMAX * 3 * 96 * 2;   // doubles in the weight array (G x 3 x YW x (A, B); G YW <= 4 x 96 = 2 x 192)
+
+__device__ __forceinline__ double fill_direct_all(const double* __restrict__ tab, const PairPre* pre, int npair, double lx,
+                                                  double xscale) {
+    double a = 0.0;
+    for (int e = 0; e < npair; e++) a += fill_direct(tab, pre[e], lx, xscale);
+    return a;
+}
+
+__global__ void log10_table_kernel(int l0, int l_step, int nl, double* __restrict__ lx) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nl) return;
+    const int l = l0 + li * l_step;
+    lx[li] = log10(l <= 0 ? 1e-10 : (double)l);
+}
+
+struct F3Smem {
+    double W[F3_WDOUBLES];                  // (A, B) row weights [g][t][r]; after the band pass: the slow candidates' corrections
+    double2 SV[F3_GMAX][F3_WMAX + 2];       // (S, V) band sums
+    PairPre pre[F3_NPMAX];
+    double delta[F3_NPMAX];
+    double gsref[F3_GMAX], gdpos[F3_GMAX], gdneg[F3_GMAX];
+    int slow_li[F3_LISTMAX];
+    int queue[F3_WDOUBLES];                 // crossing candidates of the current chunk
+    int rank[F3_NPMAX];
+    short member[F3_GMAX][F3_NPMAX];        // sample index of the eg-th member (ascending shift) of group g (-1: none)
+    unsigned char grp[F3_NPMAX];
+    unsigned char slow_g[F3_LISTMAX], slow_n[F3_LISTMAX];   // group of the entry; number of entries of its l (first entry only, else 0)
+    double smin, smax;
+    int ymin, ymax, nslow, nqueue;
+};
+
+struct F3Ctx {
+    const double* tab;
+    const double* lxtab;
+    double* out;
+    double* const* out_ptrs;
+    const int* l_owner;
+    const int* l_row;
+    long long nz2, oij, oji;
+    double xscale;
+    int l0, l_step, nl, li_first, lfirst, llast, npair, mirror;
+    __device__ __forceinline__ void store(int li, double v) const {
+        double* o = out + (long long)li * nz2;
+        if (out_ptrs) {   // tile-sharded fill: row l lives on the GPU that owns l (peer store over NVLink)
+            const int l = l0 + li * l_step;
+            o = out_ptrs[l_owner[l]] + (long long)l_row[l] * nz2;
+        }
+        __stcs(o + oij, v);               // streaming store: the table is written once and read by a later kernel
+        if (mirror) __stcs(o + oji, v);
+    }
+};
+
+// The banded evaluation of one channel pair with G shift groups.  Returns false (uniformly) if the geometry does not
+// fit (x clipped inside the band, band or window too large, very wide channels): the caller evaluates directly.
+template <int G>
+__device__ bool fill3_banded(F3Smem& sm, const F3Ctx& c) {
+    const int tid = threadIdx.x;
+    const int npair = c.npair;
+    const double xscale = c.xscale;
+    const int egn = (npair + G - 1) / G;
+    // ---- groups of neighbouring shift: group = rank G / npair, members listed in ascending shift
+    for (int e = tid; e < G * F3_NPMAX; e += F3_THREADS) sm.member[e / F3_NPMAX][e % F3_NPMAX] = -1;
+    __syncthreads();
+    for (int e = tid; e < npair; e += F3_THREADS) {
+        const int rk = sm.rank[e];
+        const int g = rk * G / npair;
+        const int first = (g * npair + G - 1) / G;      // smallest rank with rank G / npair == g
+        sm.grp[e] = (unsigned char)g;
+        sm.member[g][rk - first] = (short)e;
+    }
+    __syncthreads();
+    if (tid < G) {
+        // the group's members are sorted: its extreme shifts are those of the first and the last member
+        const int first = (tid * npair + G - 1) / G, next = ((tid + 1) * npair + G - 1) / G;
+        double mn, mx;
+        if (next > first) { mn = sm.pre[sm.member[tid][0]].shift; mx = sm.pre[sm.member[tid][next - first - 1]].shift; }
+        else { mn = mx = sm.smin; }            // empty group (npair < G)
+        const double sref = 0.5 * (mn + mx);
+        sm.gsref[tid] = sref;
+        sm.gdpos[tid] = (mx - sref) * xscale;
+        sm.gdneg[tid] = (sref - mn) * xscale;
+    }
+    __syncthreads();
+    const int ymin = sm.ymin, YW = sm.ymax - sm.ymin + 1;
+    // x band reachable by the l >= 1 of this call (one cell of margin either side + the k + 1 entry); no clip of x
+    // anywhere in it (bilinearmap.pyx:44-45 is then the identity), band and window fit, and the cells of one group's
+    // samples differ by at most one
+    const double xa_raw = (log10((double)c.lfirst) - sm.smax) * xscale, xb_raw = (log10((double)c.llast) - sm.smin) * xscale;
+    const int xbase = (int)xa_raw - 1;
+    const int W = (int)xb_raw + 3 - xbase;
+    double dmaxg = 0.0;
+#pragma unroll
+    for (int g = 0; g < G; g++) dmaxg = fmax(dmaxg, sm.gdpos[g] + sm.gdneg[g]);
+    if (!((xa_raw >= 2.0) && (xb_raw < (double)(NKPERP - 3)) && (W <= F3_WMAX) && (YW * G * 6 <= F3_WDOUBLES) && (dmaxg < 0.45)))
+        return false;
+    for (int e = tid; e < npair; e += F3_THREADS) sm.delta[e] = (sm.pre[e].shift - sm.gsref[sm.grp[e]]) * xscale;
+    __syncthreads();
+    // ---- row weights of the y window per group (fixed summation order: the group's members in ascending shift)
+    double2* W2 = (double2*)sm.W;                  // [g][t][r], r < YW
+    for (int it = tid; it < YW * G; it += F3_THREADS) {
+        const int r = it / G, g = it - r * G;
+        const int y = ymin + r;
+        double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+        for (int eg = 0; eg < egn; eg++) {
+            const int e = sm.member[g][eg];
+            if (e < 0) break;
+            const int ey0 = sm.pre[e].y0, ey1 = sm.pre[e].y1;
+            if (ey0 != y && ey1 != y) continue;
+            const PairPre p = sm.pre[e];
+            double u = 0.0;
+            if (ey0 == y) u += 1.0 - p.wy;
+            if (ey1 == y) u += p.wy;
+            const double de = sm.delta[e];
+            const double cdd = p.cdd * u, cdv = p.cdv * u, cvv = p.cvv * u;
+            a0 += cdd; a1 += cdv; a2 += cvv;
+            b0 = fma(de, cdd, b0); b1 = fma(de, cdv, b1); b2 = fma(de, cvv, b2);
+        }
+        W2[(g * 3 + 0) * YW + r] = make_double2(a0, b0);
+        W2[(g * 3 + 1) * YW + r] = make_double2(a1, b1);
+        W2[(g * 3 + 2) * YW + r] = make_double2(a2, b2);
+    }
+    __syncthreads();
+    // ---- (S_g, V_g)[x] over the band: thread = x, coalesced row reads, 2 G FMAs per table entry
+    for (int xi = tid; xi < W; xi += F3_THREADS) {
+        double sv[G], vv[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) sv[g] = vv[g] = 0.0;
+        const double* col = c.tab + (long long)ymin * NKPERP + (xbase + xi);
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const double* ct = col + (long long)t * NKPAR * NKPERP;
+#pragma unroll 16
+            for (int r = 0; r < YW; r++) {
+                const double v = __ldg(ct + (long long)r * NKPERP);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const double2 wg = W2[(g * 3 + t) * YW + r];
+                    sv[g] = fma(wg.x, v, sv[g]);
+                    vv[g] = fma(wg.y, v, vv[g]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) sm.SV[g][xi] = make_double2(sv[g], vv[g]);
+    }
+    __syncthreads();
+    // ---- G interpolations per l; an l with a group near a cell boundary books one entry per such group
+    double rsref[G], rdpos[G], rdneg[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) { rsref[g] = sm.gsref[g]; rdpos[g] = sm.gdpos[g] + 1e-9; rdneg[g] = 1.0 - sm.gdneg[g] - 1e-9; }
+    auto fast_sum = [&](double lx) {
+        double acc = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const double X = (lx - rsref[g]) * xscale;
+            const int k = (int)X;
+            const double f = X - (double)k;
+            const double2 c0 = sm.SV[g][k - xbase], c1 = sm.SV[g][k - xbase + 1];
+            acc += (c0.x + f * (c1.x - c0.x)) - (c1.y - c0.y);
+        }
+        return acc;
+    };
+    for (int li = c.li_first + tid; li < c.nl; li += F3_THREADS) {
+        const double lx = c.lxtab[li];
+        int mask = 0, cnt = 0;
+        double acc = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const double X = (lx - rsref[g]) * xscale;
+            const int k = (int)X;
+            const double f = X - (double)k;
+            if (f < rdpos[g] || f > rdneg[g]) { mask |= 1 << g; cnt++; }
+            const double2 c0 = sm.SV[g][k - xbase], c1 = sm.SV[g][k - xbase + 1];
+            acc += (c0.x + f * (c1.x - c0.x)) - (c1.y - c0.y);
+        }
+        if (mask == 0) { c.store(li, acc); continue; }
+        const int slot = atomicAdd(&sm.nslow, cnt);
+        if (slot + cnt > F3_LISTMAX) {        // no room (pathological geometry): evaluate directly; void straddled slots
+            for (int q = slot; q < F3_LISTMAX; q++) { sm.slow_li[q] = li; sm.slow_g[q] = 0; sm.slow_n[q] = 0; }
+            c.store(li, fill_direct_all(c.tab, sm.pre, npair, lx, xscale));
+            continue;
+        }
+        int q = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            if (mask & (1 << g)) {
+                sm.slow_li[slot + q] = li;
+                sm.slow_g[slot + q] = (unsigned char)g;
+                sm.slow_n[slot + q] = (unsigned char)(q == 0 ? cnt : 0);
+                q++;
+            }
+    }
+    __syncthreads();
+    // ---- slow candidates (entry, member of its group): the exact correction of a sample in the neighbouring cell.
+    // Pass 1, one thread per candidate: is the sample in another cell than its group's X?  (no table access; its
+    // correction slot is zeroed, the crossing ones are queued.)  Pass 2, one thread per queued candidate: the second
+    // difference from 18 table reads.  Pass 3, one thread per l: its candidates summed in a fixed order.  In chunks
+    // whose corrections fit the weight array (idle now).
+    const int nslow = min(sm.nslow, F3_LISTMAX);
+    double* contrib = sm.W;
+    const int chunk = max(1, F3_WDOUBLES / egn);   // entries per chunk
+    for (int s0 = 0; s0 < nslow;) {
+        int s1 = min(s0 + chunk, nslow);
+        while (s1 < nslow && s1 > s0 + 1 && sm.slow_n[s1] == 0) s1--;       // do not split the entries of one l (uniform)
+        if (tid == 0) sm.nqueue = 0;
+        __syncthreads();
+        for (int cc = tid; cc < (s1 - s0) * egn; cc += F3_THREADS) {
+            const int sl = cc / egn, eg = cc - sl * egn;
+            const int slot = s0 + sl;
+            const int g = sm.slow_g[slot];
+            const int e = sm.member[g][eg];
+            contrib[cc] = 0.0;
+            if (e >= 0) {
+                const double lx = c.lxtab[sm.slow_li[slot]];
+                const int k = (int)((lx - sm.gsref[g]) * xscale);
+                const int ke = (int)((lx - sm.pre[e].shift) * xscale);
+                if (ke != k) sm.queue[atomicAdd(&sm.nqueue, 1)] = cc;
+            }
+        }
+        __syncthreads();
+        const int nq = sm.nqueue;
+        for (int qi = tid; qi < nq; qi += F3_THREADS) {
+            const int cc = sm.queue[qi];
+            const int sl = cc / egn, eg = cc - sl * egn;
+            const int slot = s0 + sl;
+            const int g = sm.slow_g[slot];
+            const PairPre p = sm.pre[sm.member[g][eg]];
+            const double lx = c.lxtab[sm.slow_li[slot]];
+            const int k = (int)((lx - sm.gsref[g]) * xscale);
+            const double xe = (lx - p.shift) * xscale;
+            const int b = ((int)xe < k) ? k : k + 1;            // the boundary between cell k and the sample's cell
+            const double* c0 = c.tab + (long long)p.y0 * NKPERP + b;
+            const double* c1 = c.tab + (long long)p.y1 * NKPERP + b;
+            double d2 = 0.0;
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const long long off = (long long)t * NKPAR * NKPERP;
+                const double r0 = __ldg(c0 + off + 1) - 2.0 * __ldg(c0 + off) + __ldg(c0 + off - 1);
+                const double r1 = __ldg(c1 + off + 1) - 2.0 * __ldg(c1 + off) + __ldg(c1 + off - 1);
+                const double ct = (t == 0) ? p.cdd : ((t == 1) ? p.cdv : p.cvv);
+                d2 = fma(ct, (1.0 - p.wy) * r0 + p.wy * r1, d2);
+            }
+            contrib[cc] = fabs(xe - (double)b) * d2;
+        }
+        __syncthreads();
+        for (int slot = s0 + tid; slot < s1; slot += F3_THREADS) {
+            const int n = sm.slow_n[slot];
+            if (n == 0) continue;                                // not the first entry of its l
+            double corr = 0.0;
+            const double* cp = contrib + (slot - s0) * egn;
+            const int nn = min(n, s1 - slot) * egn;
+            for (int q = 0; q < nn; q++) corr += cp[q];
+            const int li = sm.slow_li[slot];
+            c.store(li, fast_sum(c.lxtab[li]) + corr);
+        }
+        __syncthreads();
+        s0 = s1;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(F3_THREADS, 3) cl21_fill3_kernel(const double* __restrict__ tab, const double* __restrict__ chi,
+                                                                   const double* __restrict__ bb, const double* __restrict__ ff,
+                                                                   const double* __restrict__ pf, const double* __restrict__ DD,
+                                                                   const double* __restrict__ w, const double* __restrict__ lxtab,
+                                                                   const long long* __restrict__ tile_start,
+                                                                   int l0, int l_step, int nl, int nz, int zint,
+                                                                   double* __restrict__ out, long long tile0, int lower_only,
+                                                                   double* const* __restrict__ out_ptrs,
+                                                                   const int* __restrict__ l_owner, const int* __restrict__ l_row) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    F3Smem& sm = *(F3Smem*)smraw;
+    const int npair = zint * zint;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tile (i; j0 .. j0+3): tiles are enumerated by dt = i - j0 first (tiles that run together share the band of
+    // table rows, y ~ |chi_i - chi_j|), then by j0 / 4.  tile_start[dt] = index of the first tile of offset dt.
+    const long long tidx = tile0 + blockIdx.x;
+    int lo = 0, hi = nz - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_start[mid] <= tidx) lo = mid; else hi = mid - 1;
+    }
+    const int dt = lo;
+    const int j0 = F3_TILE * (int)(tidx - tile_start[dt]);
+    const int i = j0 + dt;
+    const double PI = 3.14159265358979323846;
+    F3Ctx c;
+    c.tab = tab; c.lxtab = lxtab; c.out = out; c.out_ptrs = out_ptrs; c.l_owner = l_owner; c.l_row = l_row;
+    c.nz2 = (long long)nz * nz;
+    c.xscale = (double)(NKPERP - 1) / log10(KPERP_MAX / KPERP_MIN);
+    c.l0 = l0; c.l_step = l_step; c.nl = nl; c.npair = npair;
+    c.li_first = (l0 >= 1) ? 0 : 1;   // first li with l = l0 + li l_step >= 1 (l0 >= 0, l_step >= 1)
+    c.lfirst = l0 + c.li_first * l_step;
+    c.llast = l0 + (nl - 1) * l_step;
+    const bool have_l = (c.llast >= 1) && (c.li_first < nl);
+    const double xscale = c.xscale;
+
+    // sample-pair constants of (i, j); all of them fit shared memory up to zint = 9, else they are recomputed on the fly
+    auto make_pre = [&](int j, int e) {
+        const int a = e / zint, b = e % zint;
+        const int s1 = i * zint + a, s2 = j * zint + b;
+        const double x1 = chi[s1], x2 = chi[s2];
+        const double xc = 0.5 * (x1 + x2);
+        const double rpar = fabs(x2 - x1);
+        double y = rpar / (PI / KPAR_MAX);
+        y = fmin(fmax(y, 0.0), (double)NKPAR - 1e-5);
+        const unsigned y0 = (unsigned)y;
+        PairPre p;
+        p.y0 = (int)y0;
+        p.y1 = (int)min(y0 + 1u, (unsigned)(NKPAR - 1));
+        p.wy = y - (double)y0;
+        p.shift = log10(xc * KPERP_MIN);
+        const double pref = w[a] * w[b] * (DD[s1] * DD[s2] * pf[s1] * pf[s2] / (xc * xc * PI));
+        p.cdd = pref * (bb[s1] * bb[s2]);
+        p.cdv = pref * (ff[s1] * bb[s2] + ff[s2] * bb[s1]);
+        p.cvv = pref * (ff[s1] * ff[s2]);
+        return p;
+    };
+
+    for (int pp = 0; pp < F3_TILE; pp++) {
+        const int j = j0 + pp;
+        if (j > i) break;                      // uniform: partial tile on the diagonal
+        c.oij = (long long)i * nz + j;
+        c.oji = (long long)j * nz + i;
+        c.mirror = (i != j && !lower_only) ? 1 : 0;
+        __syncthreads();                       // the previous pair's shared state is no longer read
+        const bool small = (npair <= F3_NPMAX);
+        if (small) {
+            for (int e = tid; e < npair; e += F3_THREADS) { sm.pre[e] = make_pre(j, e); sm.rank[e] = 0; }
+        }
+        if (tid == 0) sm.nslow = 0;
+        __syncthreads();
+        bool done = false;
+        if (small && have_l) {
+            // rank of every sample by shift (ties by index; three threads count a third of the samples each)
+            for (int it = tid; it < 3 * npair; it += F3_THREADS) {
+                const int e = it / 3, part = it - 3 * e;
+                const int q0 = part * npair / 3, q1 = (part + 1) * npair / 3;
+                const double se = sm.pre[e].shift;
+                int rk = 0;
+                for (int q = q0; q < q1; q++) {
+                    const double sq = sm.pre[q].shift;
+                    rk += (sq < se) || (sq == se && q < e);
+                }
+                atomicAdd(&sm.rank[e], rk);
+            }
+            if (warp == 9) {
+                double mn = 1.0e308, mx = -1.0e308;
+                int ymn = 0x7fffffff, ymx = -1;
+                for (int e = lane; e < npair; e += 32) {
+                    mn = fmin(mn, sm.pre[e].shift); mx = fmax(mx, sm.pre[e].shift);
+                    ymn = min(ymn, sm.pre[e].y0); ymx = max(ymx, sm.pre[e].y1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    ymn = min(ymn, __shfl_xor_sync(0xffffffffu, ymn, o)); ymx = max(ymx, __shfl_xor_sync(0xffffffffu, ymx, o));
+                }
+                if (lane == 0) { sm.smin = mn; sm.smax = mx; sm.ymin = ymn; sm.ymax = ymx; }
+            }
+            __syncthreads();
+            const int YW = sm.ymax - sm.ymin + 1;
+            done = (YW > F3_YSPLIT || npair < 4) ? fill3_banded<2>(sm, c) : fill3_banded<4>(sm, c);
+        }
+        if (!done && have_l) {
+            // exotic geometry: the plain per-sample-pair evaluation
+            if (small) {
+                for (int li = c.li_first + tid; li < nl; li += F3_THREADS) c.store(li, fill_direct_all(tab, sm.pre, npair, lxtab[li], xscale));
+            } else {
+                for (int li = c.li_first + tid; li < nl; li += F3_THREADS) {
+                    double a = 0.0;
+                    for (int e = 0; e < npair; e++) a += fill_direct(tab, make_pre(j, e), lxtab[li], xscale);
+                    c.store(li, a);
+                }
+            }
+        }
+        // l <= 0 (l = 0 replaced by 1e-10, corr.py:957): x clips to 0 -> direct, spread over the threads
+        if (c.li_first > 0) {
+            double v = 0.0;
+            for (int e = tid; e < npair; e += F3_THREADS) v += fill_direct(tab, small ? sm.pre[e] : make_pre(j, e), log10(1e-10), xscale);
+            __syncthreads();
+            sm.W[tid] = v;
+            __syncthreads();
+            if (tid == 0) {
+                double tsum = 0.0;
+                for (int k = 0; k < F3_THREADS; k++) tsum += sm.W[k];
+                for (int li = 0; li < min(c.li_first, nl); li++) c.store(li, tsum);
+            }
+        }
+    }
+}
+
+// upper triangle <- lower triangle (32 x 32 tiles through shared memory, full-sector writes)
+__global__ void cl_symmetrize_kernel(double* __restrict__ cl, int nz) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    double* M = cl + (long long)blockIdx.z * nz * nz;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 256 threads: 8 rows per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        tile[r][tx] = (i < nz && j < nz) ? M[(long long)i * nz + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = bj * 32 + r, i = bi * 32 + tx;           // write element (j, i) = tile[i - bi 32][j - bj 32]
+        if (i < nz && j < nz && j < i) M[(long long)j * nz + i] = tile[tx][r];
     }
 }
 
@@ -491,38 +949,98 @@ extern "C" int cora_b200_ps_table_21cm(const double* lnk_h, const double* lnp_h,
     return 0;
 }
 
-extern "C" int cora_b200_cl_fill_21cm(const double* tab, const double* chi, const double* b, const double* f, const double* pf,
-                                      const double* D, const double* w, int l0, int l_step, int nl, int nz, int zint,
-                                      double* out_cl, void* stream) {
-    CB_REQUIRE(tab && chi && b && f && pf && D && w && out_cl, 1, "cl_fill_21cm: null argument");
-    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_21cm: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
-    const long long npairs = (long long)nz * (nz + 1) / 2;
-    CB_REQUIRE(npairs < 2147483647LL, 3, "cl_fill_21cm: too many channel pairs");
-    size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
-    CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KTimer kt(K_CL_FILL, (cudaStream_t)stream);
-    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl,
-                                                                            0, nullptr, nullptr, nullptr);
-    count_launch();
-    CB_LAUNCH_CHECK();
+// CORA_B200_FILL_V1=1: the per-sample-pair kernel of round 1 (A/B reference for the row-weight kernel)
+static const bool g_fill_v1 = [] { const char* e = getenv("CORA_B200_FILL_V1"); return e && atoi(e) != 0; }();
+
+// tiles (i; j0 = 4 jt .. j0 + 3), j0 <= i, enumerated by dt = i - j0 then jt: tile_start[dt], dt = 0 .. nz
+static long long fill_ntiles(int nz) {
+    long long n = 0;
+    for (int dt = 0; dt < nz; dt++) n += (nz - 1 - dt) / F3_TILE + 1;
+    return n;
+}
+struct TileTab { int dev, nz; long long* d; };
+static std::vector<TileTab> g_tile_tabs;
+static int fill_tile_table(int nz, const long long** out) {
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    for (auto& t : g_tile_tabs)
+        if (t.dev == dev && t.nz == nz) { *out = t.d; return 0; }
+    std::vector<long long> h(nz + 1);
+    long long n = 0;
+    for (int dt = 0; dt <= nz; dt++) {
+        h[dt] = n;
+        if (dt < nz) n += (nz - 1 - dt) / F3_TILE + 1;
+    }
+    TileTab t;
+    t.dev = dev; t.nz = nz; t.d = nullptr;
+    CB_CUDA(cudaMalloc(&t.d, sizeof(long long) * (nz + 1)));
+    CB_CUDA(cudaMemcpy(t.d, h.data(), sizeof(long long) * (nz + 1), cudaMemcpyHostToDevice));
+    g_tile_tabs.push_back(t);
+    *out = t.d;
     return 0;
 }
 
-extern "C" int cora_b200_cl_fill_21cm_pairs(const double* tab, const double* chi, const double* b, const double* f,
+extern "C" long long cora_b200_cl_fill_21cm_ntiles(int nz) { return nz >= 1 ? fill_ntiles(nz) : 0; }
+
+static int fill21_launch(const double* tab, const double* chi, const double* b, const double* f, const double* pf,
+                         const double* D, const double* w, int l0, int l_step, int nl, int nz, int zint, double* out_cl,
+                         int lower_only, int variant, long long tile0, long long ntiles, double* const* out_ptrs,
+                         const int* l_owner, const int* l_row, cudaStream_t st) {
+    KTimer kt(K_CL_FILL, st);
+    const long long* tstart = nullptr;
+    if (int rc = fill_tile_table(nz, &tstart)) return rc;
+    if (g_fill_v1 || variant == 1) {
+        size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
+        CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cl21_fill_kernel<<<(unsigned)(ntiles * F3_TILE), 256, smem, st>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl, tile0,
+                                                                         out_ptrs, l_owner, l_row, tstart, lower_only);
+        count_launch();
+        CB_LAUNCH_CHECK();
+        return 0;
+    }
+    double* lx = nullptr;
+    CB_CUDA(cudaMallocAsync(&lx, sizeof(double) * (size_t)nl, st));
+    log10_table_kernel<<<ceil_div(nl, 256), 256, 0, st>>>(l0, l_step, nl, lx);
+    count_launch();
+    const size_t smem = sizeof(F3Smem);
+    CB_CUDA(cudaFuncSetAttribute(cl21_fill3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cl21_fill3_kernel<<<(unsigned)ntiles, F3_THREADS, smem, st>>>(tab, chi, b, f, pf, D, w, lx, tstart, l0, l_step, nl, nz, zint, out_cl,
+                                                                 tile0, lower_only, out_ptrs, l_owner, l_row);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    CB_CUDA(cudaFreeAsync(lx, st));
+    return 0;
+}
+
+extern "C" int cora_b200_cl_fill_21cm(const double* tab, const double* chi, const double* b, const double* f, const double* pf,
+                                      const double* D, const double* w, int l0, int l_step, int nl, int nz, int zint,
+                                      double* out_cl, int lower_only, int variant, void* stream) {
+    CB_REQUIRE(tab && chi && b && f && pf && D && w && out_cl, 1, "cl_fill_21cm: null argument");
+    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_21cm: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
+    const long long ntiles = fill_ntiles(nz);
+    CB_REQUIRE((long long)nz * (nz + 1) / 2 < 2147483647LL, 3, "cl_fill_21cm: too many channel pairs");
+    return fill21_launch(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl, lower_only, variant, 0, ntiles, nullptr, nullptr,
+                         nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cora_b200_cl_fill_21cm_tiles(const double* tab, const double* chi, const double* b, const double* f,
                                             const double* pf, const double* D, const double* w, int nl, int nz, int zint,
-                                            long long pair0, long long npairs, const void* out_ptrs, const int* l_owner,
-                                            const int* l_row, void* stream) {
-    CB_REQUIRE(tab && chi && b && f && pf && D && w && out_ptrs && l_owner && l_row, 1, "cl_fill_21cm_pairs: null argument");
-    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT, 1, "cl_fill_21cm_pairs: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
-    const long long all = (long long)nz * (nz + 1) / 2;
-    CB_REQUIRE(pair0 >= 0 && npairs >= 0 && pair0 + npairs <= all && npairs < 2147483647LL, 1,
-               "cl_fill_21cm_pairs: pair range [%lld, %lld) outside [0, %lld)", pair0, pair0 + npairs, all);
-    if (npairs == 0) return 0;
-    size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
-    CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KTimer kt(K_CL_FILL, (cudaStream_t)stream);
-    cl21_fill_kernel<<<(unsigned)npairs, 256, smem, (cudaStream_t)stream>>>(tab, chi, b, f, pf, D, w, 0, 1, nl, nz, zint, nullptr,
-                                                                            pair0, (double* const*)out_ptrs, l_owner, l_row);
+                                            long long tile0, long long ntiles, int variant, const void* out_ptrs,
+                                            const int* l_owner, const int* l_row, void* stream) {
+    CB_REQUIRE(tab && chi && b && f && pf && D && w && out_ptrs && l_owner && l_row, 1, "cl_fill_21cm_tiles: null argument");
+    CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT, 1, "cl_fill_21cm_tiles: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
+    const long long all = fill_ntiles(nz);
+    CB_REQUIRE(tile0 >= 0 && ntiles >= 0 && tile0 + ntiles <= all && ntiles < 2147483647LL, 1,
+               "cl_fill_21cm_tiles: tile range [%lld, %lld) outside [0, %lld)", tile0, tile0 + ntiles, all);
+    if (ntiles == 0) return 0;
+    return fill21_launch(tab, chi, b, f, pf, D, w, 0, 1, nl, nz, zint, nullptr, 1, variant, tile0, ntiles, (double* const*)out_ptrs,
+                         l_owner, l_row, (cudaStream_t)stream);
+}
+
+extern "C" int cora_b200_cl_symmetrize(double* cl, int nl, int nz, void* stream) {
+    CB_REQUIRE(cl && nl >= 1 && nz >= 1 && nl <= 65535, 1, "cl_symmetrize: bad arguments");
+    const int nb = ceil_div(nz, 32);
+    cl_symmetrize_kernel<<<dim3(nb, nb, nl), 256, 0, (cudaStream_t)stream>>>(cl, nz);
     count_launch();
     CB_LAUNCH_CHECK();
     return 0;

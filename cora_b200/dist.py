@@ -183,16 +183,15 @@ class ShardedSky(object):
             self._buf[name] = make()
         return self._buf[name]
 
-    def fill(self, out=None):
-        """This rank's C_l(nu, nu') rows, ``float64[nl, nz, nz]`` (``skysim.clarray`` for the local l's)."""
+    def fill(self, out=None, lower_only=True):
+        """This rank's C_l(nu, nu') rows, ``float64[nl, nz, nz]`` (``skysim.clarray`` for the local l's).  By default
+        only the lower triangles are filled (``lower_only``): that is all the root stage reads."""
         t = _dev.torch()
         if out is None:
-            out = self._persistent("cla", lambda: _dev.empty((self.nl, self.nz, self.nz), t.float64))
-        if self.plan.partition == "interleaved":
-            self.model._b200_fill(self.fill_inputs, int(self.l_list[0]) if self.nl else 0, self.size, self.nl, self.nz,
-                                  self.zint, out)
-        else:
-            self.model._b200_fill(self.fill_inputs, int(self.l_list[0]) if self.nl else 0, 1, self.nl, self.nz, self.zint, out)
+            out = self._persistent("cla", lambda: _dev.zeros((self.nl, self.nz, self.nz), t.float64))
+        step = self.size if self.plan.partition == "interleaved" else 1
+        self.model._b200_fill(self.fill_inputs, int(self.l_list[0]) if self.nl else 0, step, self.nl, self.nz, self.zint, out,
+                              lower_only=lower_only)
         return out
 
     def alm_local(self, cla, seed=0, gauss=None, roots=None):
@@ -262,7 +261,7 @@ class ShardedSky(object):
         pg = self.peers
         L = self.lmax + 1
         nalm = L * (L + 1) // 2
-        st = {"pairs": hasattr(self.model, "_b200_fill_pairs")}
+        st = {"pairs": hasattr(self.model, "_b200_fill_tiles")}
         st["cla"], st["cla_ptrs"], st["panel"], st["panel_ptrs"] = [], [], [], []
         for _ in range(2):
             if st["pairs"]:
@@ -281,9 +280,9 @@ class ShardedSky(object):
         for s_ in range(self.size):
             width[int(self.plan.chan_lo[s_]):int(self.plan.chan_hi[s_])] = int(self.plan.cb[s_])
         st["nu_width"] = _dev.to_device(width, t.int32)
-        npair = self.nz * (self.nz + 1) // 2
-        st["pair0"] = npair * self.rank // self.size
-        st["npairs"] = npair * (self.rank + 1) // self.size - st["pair0"]
+        ntile = int(_lib.load().cora_b200_cl_fill_21cm_ntiles(self.nz)) if st["pairs"] else 0
+        st["pair0"] = ntile * self.rank // self.size
+        st["npairs"] = ntile * (self.rank + 1) // self.size - st["pair0"]
         st["tables"] = [None, None]
         self._p2p = st
         return st
@@ -315,7 +314,7 @@ class ShardedSky(object):
         st = self._p2p_setup()
         if st["pairs"]:
             tab = self._p2p_tables(k)
-            self.model._b200_fill_pairs(self.fill_inputs, self.lmax + 1, self.nz, self.zint, st["pair0"], st["npairs"],
+            self.model._b200_fill_tiles(self.fill_inputs, self.lmax + 1, self.nz, self.zint, st["pair0"], st["npairs"],
                                         tab["cla_ptrs"], st["l_owner"], st["l_row"])
             return True     # remote stores in flight: barrier before the root reads cla[k]
         self.fill()

@@ -66,8 +66,8 @@ class ForegroundSCK(ForegroundMap):
     # skysim.clarray takes the fused kernel only while these methods are the ones defined here
     _b200_fill_methods = ("angular_powerspectrum", "angular_ps", "frequency_covariance", "_b200_fill", "_params")
 
-    def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None):
-        ns, wd = inputs
+    def _b200_fill(self, inputs, l0, l_step, nl, nz, zint, out, stream=None, lower_only=False):
+        ns, wd = inputs   # (lower_only is a 21cm-kernel option; the closed-form fill always writes full matrices)
         _lib.call("cora_b200_cl_fill_sck", *self._params(), _lib.ptr(ns), _lib.ptr(wd), int(l0), int(l_step), int(nl),
                   int(nz), int(zint), _lib.ptr(out), _lib.stream_ptr(stream))
 

@@ -61,7 +61,8 @@ class Sky3d(Map3d):
     def getsky(self):
         """Create a map of the unpolarised sky, ``float64[nfreq, npix]``."""
         lmax = 3 * self.nside - 1
-        cla = skysim.clarray(self.angular_powerspectrum, lmax, self.nu_pixels, zromb=self.oversample, device_out=True)
+        cla = skysim.clarray(self.angular_powerspectrum, lmax, self.nu_pixels, zromb=self.oversample, device_out=True,
+                             _lower_only=True)      # mkfullsky's root reads the lower triangle only (LAPACK-style)
         mean = np.asarray(self.mean_nu(np.asarray(self.nu_pixels, dtype=np.float64)), dtype=np.float64)
         if not mean.any():
             return skysim.mkfullsky(cla, self.nside)

@@ -60,7 +60,7 @@ def _fused_fill(aps, owner):
     return fill
 
 
-def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
+def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False, _lower_only=False):
     """Calculate an array of C_l(z, z') averaged over each frequency channel.
 
     Same contract as ``cora/core/skysim.py:10-69``: ``aps(l, z1, z2)`` is the angular power
@@ -87,7 +87,14 @@ def clarray(aps, lmax, zarray, zromb=3, zwidth=None, device_out=False):
 
     if fused is not None:
         out = _dev.empty((lmax + 1, nz, nz), t.float64)
-        fused(owner._b200_fill_inputs(za, w), 0, 1, lmax + 1, nz, zint, out)
+        # the 21cm kernel fills the lower triangles (full 32-byte sectors); the mirror pass makes the table symmetric
+        # as the reference's is, unless the caller only feeds mkfullsky (which reads the lower triangle, like LAPACK)
+        lower = getattr(owner, "_b200_fill_lower", False)
+        if lower and _lower_only:
+            out.zero_()
+        fused(owner._b200_fill_inputs(za, w), 0, 1, lmax + 1, nz, zint, out, lower_only=lower)
+        if lower and not _lower_only:
+            _lib.call("cora_b200_cl_symmetrize", _lib.ptr(out), lmax + 1, nz, _lib.stream_ptr())
         return out if device_out else _dev.to_host(out)
 
     if zromb == 0:

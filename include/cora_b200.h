@@ -121,7 +121,15 @@ long long cora_b200_ps_table_21cm_workspace_bytes(void);
  * chi (comoving distance), b, f, pf, D.                                                  */
 int cora_b200_cl_fill_21cm(const double* tab, const double* chi, const double* b, const double* f,
                            const double* pf, const double* D, const double* w, int l0, int l_step, int nl,
-                           int nz, int zint, double* out_cl, void* stream);
+                           int nz, int zint, double* out_cl, int lower_only, int variant, void* stream);
+/* variant: 0 = the row-weight kernel (band sums over the distinct table rows of a channel pair's y window + exact
+ * cell-boundary corrections; 2-3x faster for narrow channels, >= 512 channels over the band), 1 = the
+ * per-sample-pair kernel (faster when the y window is taller than ~64 rows, e.g. 256 channels over 400 MHz).
+ * The two agree to a few ulp of each row's scale.  The host picks from the comoving width of a channel.
+ * lower_only != 0: only the entries (i, j <= i) are written (what the root stage reads, LAPACK-style); the
+ * fill's 8-byte stores then merge into full 32-byte sectors.  cora_b200_cl_symmetrize mirrors the lower
+ * triangle of every matrix into its upper triangle (cl[nl][nz][nz], in place).                        */
+int cora_b200_cl_symmetrize(double* cl, int nl, int nz, void* stream);
 
 /* Romberg average of a block evaluated by a generic host callable:
  * in[nl][nz][zint][nz][zint] -> out[nl][nz][nz]  (the two scipy.integrate.romb calls and the
@@ -257,7 +265,7 @@ int cora_b200_map_sub(const double* a, const double* b, long long n, double* out
  * The reference moves data between ranks with caput's MPIArray.redistribute
  * (cora/core/skysim.py:128) after the compute.  Here the producing kernels store straight into
  * the consumer GPU's buffer, so the exchange happens in the kernel epilogue:
- *   - cora_b200_cl_fill_21cm_pairs: the 21cm C_l fill sharded over channel PAIRS (its cost per
+ *   - cora_b200_cl_fill_21cm_tiles: the 21cm C_l fill sharded over channel PAIRS (its cost per
  *     pair does not shrink with the l range, so l-sharding it would not scale); row l of the
  *     result is written to the GPU that owns l for the root/apply stage.
  *   - cora_b200_draw_apply_peers: apply writes a_lm(nu) into the PANEL buffer of the GPU that
@@ -277,14 +285,15 @@ int cora_b200_peer_close(void* ptr);
 int cora_b200_peer_barrier(const void* flags_ptrs, int rank, int size, unsigned long long epoch,
                            double timeout_s, int* status, int fatal, void* stream);
 
-/* 21cm fill for channel pairs [pair0, pair0 + npairs) of the diagonal-major enumeration
- * (pair index p <-> (i, j), i >= j, ordered by d = i - j then j), all l = 0..nl-1.
- * out_ptrs: device array of per-GPU C_l buffers; element (l, i, j) and its mirror (l, j, i) go
- * to out_ptrs[l_owner[l]][(l_row[l] * nz + i) * nz + j].  l_owner / l_row: device int[nl].     */
-int cora_b200_cl_fill_21cm_pairs(const double* tab, const double* chi, const double* b, const double* f,
+/* 21cm fill for the channel-pair tiles [tile0, tile0 + ntiles) of cora_b200_cl_fill_21cm_ntiles(nz) tiles
+ * (a tile = channel i against 4 consecutive channels j0 .. j0+3 <= i; tiles ordered by i - j0, then j0),
+ * all l = 0..nl-1, lower triangle only.  out_ptrs: device array of per-GPU C_l buffers; element (l, i, j) goes
+ * to out_ptrs[l_owner[l]][(l_row[l] * nz + i) * nz + j] (32-byte runs over NVLink).  l_owner / l_row: device int[nl]. */
+long long cora_b200_cl_fill_21cm_ntiles(int nz);
+int cora_b200_cl_fill_21cm_tiles(const double* tab, const double* chi, const double* b, const double* f,
                                  const double* pf, const double* D, const double* w, int nl, int nz, int zint,
-                                 long long pair0, long long npairs, const void* out_ptrs, const int* l_owner,
-                                 const int* l_row, void* stream);
+                                 long long tile0, long long ntiles, int variant, const void* out_ptrs,
+                                 const int* l_owner, const int* l_row, void* stream);
 
 /* draw + apply for the local l's with the exchange fused into the epilogue: element (l, m, nu)
  * is stored at nu_ptr[nu][idx(l, m) * nu_width[nu]] (complex elements), where nu_ptr[nu] (device

@@ -34,7 +34,7 @@ def lib():
 def test_header_declares_the_hot_path():
     d = _declared()
     for name in ("cora_b200_cl_fill_21cm", "cora_b200_cl_fill_sck", "cora_b200_root_batched", "cora_b200_draw_apply",
-                 "cora_b200_alm2map", "cora_b200_alm2map_spin2", "cora_b200_draw_apply_peers", "cora_b200_cl_fill_21cm_pairs",
+                 "cora_b200_alm2map", "cora_b200_alm2map_spin2", "cora_b200_draw_apply_peers", "cora_b200_cl_fill_21cm_tiles",
                  "cora_b200_peer_barrier"):
         assert name in d
     assert len(d) >= 35

@@ -144,7 +144,9 @@ def test_p2p_virtual_ranks_21cm_pair_sharded_fill(size, partition, gpu_corr21cm_
     for sh in shards:
         mine = sh._p2p["cla"][0].tensor((sh.nl, nz, nz), torch.float64).cpu().numpy()
         want = cla[torch.from_numpy(sh.l_list.astype(np.int64)).cuda()].cpu().numpy()
-        np.testing.assert_array_equal(mine, want)
+        # the sharded fill writes the lower triangles only (all the root stage reads); those are bit-identical
+        np.testing.assert_array_equal(np.tril(mine), np.tril(want))
+        assert np.all(np.triu(mine, 1) == 0)
     np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=1e-13 * np.abs(ref).max())
 
 

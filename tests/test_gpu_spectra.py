@@ -161,3 +161,39 @@ def test_21cm_clarray_config2_axis_vs_oracle_rows(gpu_corr21cm, oracle_corr21cm)
     d = np.sqrt(np.abs(np.einsum("lii->li", a)))
     scale = d[:, g["chan_rows"], None] * d[:, None, :] + 1e-300
     assert np.max(np.abs(a[:, g["chan_rows"], :] - g["cl_rows"]) / scale) < 1e-11
+
+
+def test_21cm_fill_row_weight_kernel_vs_per_sample_kernel(gpu_corr21cm):
+    """The row-weight fill kernel (one x-interpolation per l over row-weighted band sums + exact boundary
+    corrections) against the per-sample-pair kernel of round 1 (CORA_B200_FILL_V1=1 in a subprocess, same device
+    table): agreement to a few ulp of the row scale on config-2-like and narrow-channel axes, with interleaved l."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    from cora_b200 import skysim
+
+    cases = [(np.linspace(800.0, 400.0, 64, endpoint=False), 383), (np.linspace(650.0, 600.0, 48, endpoint=False), 1535),
+             (np.linspace(800.0, 400.0, 16, endpoint=False), 47)]
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+from cora_b200 import corr21cm, skysim
+c = corr21cm.Corr21cm()
+cases = [(np.linspace(800.0, 400.0, 64, endpoint=False), 383), (np.linspace(650.0, 600.0, 48, endpoint=False), 1535),
+         (np.linspace(800.0, 400.0, 16, endpoint=False), 47)]
+np.savez(sys.argv[1], *[skysim.clarray(c.angular_powerspectrum, lmax, f) for f, lmax in cases])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "v1.npz")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, CORA_B200_FILL_VARIANT="1"))
+        old = np.load(path)
+        os.environ["CORA_B200_FILL_VARIANT"] = "0"      # the host would pick per geometry: force the row-weight kernel
+        try:
+            for k, (freq, lmax) in enumerate(cases):
+                new = skysim.clarray(gpu_corr21cm.angular_powerspectrum, lmax, freq)
+                assert _normwise(new, old["arr_%d" % k]) < 2e-14
+                assert np.array_equal(new, np.transpose(new, (0, 2, 1)))
+        finally:
+            del os.environ["CORA_B200_FILL_VARIANT"]
