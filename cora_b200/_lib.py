@@ -49,6 +49,8 @@ SIGNATURES = {
     "cora_b200_eigh_workspace_bytes": (_ll, [_i, _i]),
     "cora_b200_eigh_batched": (_i, [_vp, _i, _i, _vp, _vp, _vp, _ll, _vp]),
     "cora_b200_draw_apply_workspace_bytes": (_ll, [_i, _i, _i]),
+    "cora_b200_draw_bytes": (_ll, [_vp, _i, _i]),
+    "cora_b200_draw": (_i, [_vp, _i, _i, _ull, _i, _vp, _ll, _vp]),
     "cora_b200_draw_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _ull, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _vp]),
     "cora_b200_draw_apply_slabs": (_i, [_vp, _vp, _vp, _i, _i, _i, _ull, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "cora_b200_alm_slabs_to_panel": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _vp]),

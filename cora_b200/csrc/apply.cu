@@ -273,7 +273,9 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
     long long avail = (char*)workspace + ws_bytes - ws;
     for (int i = 0; i < nl; i++)
         CB_REQUIRE(l_list_h[i] >= 0 && l_list_h[i] <= lmax, 1, "draw_apply: l_list[%d]=%d outside [0,%d]", i, l_list_h[i], lmax);
-    if (gauss) CB_REQUIRE(gauss_ld >= lmax + 1 || nl == 0, 1, "draw_apply: gauss_ld %lld < lmax+1", gauss_ld);
+    const bool packed = gauss && gauss_ld < 0;     // draws made by cora_b200_draw: block i holds [nz][l_i + 1], blocks back to back
+    if (gauss && !packed) CB_REQUIRE(gauss_ld >= lmax + 1 || nl == 0, 1, "draw_apply: gauss_ld %lld < lmax+1", gauss_ld);
+    long long packed_off = 0;
 
     int i0 = 0;
     while (i0 < nl) {
@@ -285,11 +287,12 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
             LDesc d;
             d.l = l_list_h[i1];
             d.orow = row0_h ? row0_h[i1] : 0;
-            if (gauss) { d.goff = (long long)i1 * nz * gauss_ld; d.ld = (int)gauss_ld; }
+            if (packed) { d.goff = packed_off; d.ld = d.l + 1; packed_off += (long long)nz * d.ld; }
+            else if (gauss) { d.goff = (long long)i1 * nz * gauss_ld; d.ld = (int)gauss_ld; }
             else { d.goff = gneed; d.ld = d.l + 1; }
             long long add = gauss ? 0 : (long long)nz * d.ld;
             long long bytes = ((long long)(hd.size() + 1) * sizeof(LDesc) + 255) / 256 * 256 + 16 * (gneed + add) + 512;
-            if (bytes > avail && i1 > i0) break;
+            if (bytes > avail && i1 > i0) { if (packed) packed_off -= (long long)nz * d.ld; break; }
             CB_REQUIRE(bytes <= avail, 4, "draw_apply: workspace too small (%lld B) for a single l (needs %lld B)", avail, bytes);
             gneed += add;
             hd.push_back(d);
@@ -332,6 +335,43 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
         CB_LAUNCH_CHECK();
         if (i1 < nl) CB_CUDA(cudaStreamSynchronize(st));   // workspace reuse
         i0 = i1;
+    }
+    return 0;
+}
+
+extern "C" long long cora_b200_draw_bytes(const int* l_list_h, int nl, int nz) {
+    if (!l_list_h || nl < 0 || nz < 1) return -1;
+    long long n = 0;
+    for (int i = 0; i < nl; i++) n += (long long)nz * (l_list_h[i] + 1);
+    return 16 * n;
+}
+
+extern "C" int cora_b200_draw(const int* l_list_h, int nl, int nz, unsigned long long seed, int draw_counter0, void* gauss_packed,
+                              long long bytes, void* stream) {
+    CB_REQUIRE(l_list_h && gauss_packed && nl >= 1 && nz >= 1 && draw_counter0 >= 0, 1, "draw: bad arguments");
+    CB_REQUIRE(bytes >= cora_b200_draw_bytes(l_list_h, nl, nz), 4, "draw: buffer too small (%lld B, need %lld B)", bytes,
+               cora_b200_draw_bytes(l_list_h, nl, nz));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < nl; i0 += 65535) {
+        const int nb = std::min(65535, nl - i0);
+        std::vector<LDesc> hd(nb);
+        long long off = 0;
+        for (int i = 0; i < i0; i++) off += (long long)nz * (l_list_h[i] + 1);
+        int lbig = 0;
+        for (int i = 0; i < nb; i++) {
+            CB_REQUIRE(l_list_h[i0 + i] >= 0, 1, "draw: negative l");
+            hd[i].l = l_list_h[i0 + i];
+            hd[i].ld = hd[i].l + 1;
+            hd[i].goff = off;
+            hd[i].orow = 0;
+            off += (long long)nz * hd[i].ld;
+            lbig = std::max(lbig, hd[i].l);
+        }
+        LDesc* dd = nullptr;
+        if (int rc = cached_descs(hd, &dd)) return rc;
+        { KTimer kt(K_DRAW, st); draw_kernel<<<dim3(ceil_div(lbig + 1, 128), nz, nb), 128, 0, st>>>(dd, nz, seed, (double2*)gauss_packed, (unsigned)draw_counter0); }
+        count_launch();
+        CB_LAUNCH_CHECK();
     }
     return 0;
 }

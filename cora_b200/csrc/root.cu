@@ -844,19 +844,13 @@ extern "C" int cora_b200_root_batched_multi(const double* const* cl_blocks, int 
         CB_LAUNCH_CHECK();
         return 0;
     };
-    if (groups >= nl) {
-        // room for every matrix: launch the eigen fallback for all nl slot groups, CTAs beyond the
-        // device-side failure count exit at once -- the host never waits for the count
-        return wave(0, nl, nfail_d);
-    }
-    int nfail = 0;
-    CB_CUDA(cudaMemcpyAsync(&nfail, nfail_d, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaStreamSynchronize(st));
-    if (nfail == 0) return 0;
+    // The eigen fallback is launched for every l in waves of `groups` slot groups; the CTAs of a wave beyond the
+    // device-side failure count exit at once, so the host never waits for the count (no synchronisation in a step),
+    // whatever the number of failures.  With room for every matrix (groups >= nl) that is a single wave.
     CB_REQUIRE(groups >= 1, 4, "root_batched: no workspace for the eigen fallback");
-    for (int f0 = 0; f0 < nfail; f0 += (int)groups) {
-        const int nw = (int)std::min<long long>(groups, nfail - f0);
-        if (int rc = wave(f0, nw, nullptr)) return rc;
+    for (int f0 = 0; f0 < nl; f0 += (int)std::min<long long>(groups, nl)) {
+        const int nw = (int)std::min<long long>(groups, nl - f0);
+        if (int rc = wave(f0, nw, nfail_d)) return rc;
     }
     return 0;
 }

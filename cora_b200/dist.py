@@ -20,6 +20,7 @@ Differences from the reference, by design:
 """
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -183,6 +184,42 @@ class ShardedSky(object):
             self._buf[name] = make()
         return self._buf[name]
 
+    def _draw_begin(self, seed, counter0=0):
+        """Start this step's Philox draws on a side stream: they do not depend on C_l, so they overlap the fill and
+        the root (the draw kernel is FP64-ALU bound, the fill L2-latency bound, the Cholesky latency bound).  Needs a
+        buffer for all local draws (``16 nz sum(l+1)`` bytes); if that does not fit, the apply call draws by itself."""
+        t = _dev.torch()
+        lib = _lib.load()
+        self._predrawn = None
+        if self.nl == 0 or os.environ.get("CORA_B200_DRAW_OVERLAP", "0") != "1":   # measured: no gain (the fill slows by what the draws take), off by default
+            return
+        need = int(lib.cora_b200_draw_bytes(_lib.ptr(self.l_list), self.nl, self.nz))
+        if "draw_buf" not in self._buf:
+            if need + (8 << 30) > _dev.free_bytes():
+                return
+            self._buf["draw_buf"] = _dev.workspace(need)
+            self._draw_stream = t.cuda.Stream()
+        buf = self._buf["draw_buf"]
+        main = t.cuda.current_stream()
+        ev = t.cuda.Event()
+        ev.record(main)                       # the previous step's apply has finished reading the buffer
+        self._draw_stream.wait_event(ev)
+        _lib.call("cora_b200_draw", _lib.ptr(self.l_list), self.nl, self.nz, ctypes.c_ulonglong(int(seed)), int(counter0),
+                  _lib.ptr(buf), int(buf.numel()), _lib.stream_ptr(self._draw_stream))
+        done = t.cuda.Event()
+        done.record(self._draw_stream)
+        self._predrawn = (buf, done, int(seed))
+
+    def _draw_take(self, seed):
+        """(gauss pointer, gauss_ld) of the draws started by ``_draw_begin`` for this seed (the main stream then waits
+        for them), or (None, 0)."""
+        pd = getattr(self, "_predrawn", None)
+        self._predrawn = None
+        if pd is None or pd[2] != int(seed):
+            return None, 0
+        _dev.torch().cuda.current_stream().wait_event(pd[1])
+        return _lib.ptr(pd[0]), -1
+
     def fill(self, out=None, lower_only=True):
         """This rank's C_l(nu, nu') rows, ``float64[nl, nz, nz]`` (``skysim.clarray`` for the local l's).  By default
         only the lower triangles are filled (``lower_only``): that is all the root stage reads."""
@@ -208,14 +245,16 @@ class ShardedSky(object):
         if self.size > 1:
             send = self._persistent("send", lambda: _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128))
         lmax_loc = int(self.l_list.max())
-        if gauss is None:
+        gptr, gld = self._draw_take(seed) if gauss is None else (None, 0)
+        if gauss is None and gptr is None:
             def mk():
                 full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
                 one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
                 return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
 
             ws = self._persistent("draw_ws", mk)
-            gptr, gld = None, 0
+        elif gauss is None:
+            ws = self._persistent("desc_ws", lambda: _dev.workspace(64 * self.nl + 4096))
         else:
             gauss = _dev.to_device(gauss, t.complex128)
             ws = _dev.workspace(64 * self.nl + 4096)
@@ -340,14 +379,16 @@ class ShardedSky(object):
         else:
             root, used = _dev.to_device(roots, t.float64), None
         lmax_loc = int(self.l_list.max())
-        if gauss is None:
+        gptr, gld = self._draw_take(seed) if gauss is None else (None, 0)
+        if gauss is None and gptr is None:
             def mk():
                 full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
                 one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
                 return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
 
             ws = self._persistent("draw_ws", mk)
-            gptr, gld = None, 0
+        elif gauss is None:
+            ws = self._persistent("desc_ws", lambda: _dev.workspace(64 * self.nl + 4096))
         else:
             gauss = _dev.to_device(gauss, t.complex128)
             ws = _dev.workspace(64 * self.nl + 4096)
@@ -375,6 +416,7 @@ class ShardedSky(object):
     def _step_p2p(self, seed=0, out=None):
         k = self._k & 1
         self._k += 1
+        self._draw_begin(seed)
         if self.p2p_fill(k):
             self.peers.barrier()
         self.p2p_alm(k, seed=seed)
@@ -397,6 +439,7 @@ class ShardedSky(object):
         self.fill_inputs = self.model._b200_fill_inputs(za, skysim.romberg_weights(self.zromb))
         L = self.lmax + 1
         nalm = L * (L + 1) // 2
+        self._draw_begin(seed)
         if self.exchange == "p2p":
             k = self._k & 1
             self._k += 1
@@ -437,6 +480,7 @@ class ShardedSky(object):
     def step(self, seed=0, out=None):
         if self.exchange == "p2p":
             return self._step_p2p(seed=seed, out=out)
+        self._draw_begin(seed)
         cla = self.fill()
         send = self.alm_local(cla, seed=seed)
         del cla

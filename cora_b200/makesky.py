@@ -1,11 +1,12 @@
 """Drivers of record for the path: ``cora-makesky 21cm`` and ``cora-makesky gaussianfg``.
 
 Mirrors ``cora/scripts/makesky.py``: ``FreqState`` (``:44-92``), the ``21cm`` command
-(``:313-344``) and the ``gaussianfg`` command (``:347-390``).  The click CLI and the HDF5 writer
-(``write_map``, ``:412-450``; h5py is not available here) are outside the hot path; the functions
-below return the ``(nfreq, npol, npix)`` arrays the commands would write.
+(``:313-344``) and the ``gaussianfg`` command (``:347-390``).  The functions below return the
+``(nfreq, npol, npix)`` arrays the commands write; ``write_map`` (``:412-450``) is ``cora_b200.mapio``
+(frequency-sharded ``.npy`` + JSON index maps; ``tools/map_to_hdf5.py`` converts to the reference's HDF5 layout).
 
     python -m cora_b200.makesky 21cm --nside 64 --freq 800 400 32 --pol none out.npy
+    torchrun --nproc-per-node 8 -m cora_b200.makesky 21cm --nside 1024 --freq 800 400 2048 --pol none outdir
 """
 
 import numpy as np
@@ -124,8 +125,32 @@ def make_gaussianfg(fstate, nside, pol="full", rng=None, seed=None, blocked=None
     return hputil.sphtrans_inv_sky(alms, nside)
 
 
+def make_sharded(command, fstate, nside, pol="full", eor=False, oversample=None, seed=0):
+    """The same generators, one rank of a multi-GPU run (``torchrun``; also works with one rank): returns
+    ``(this rank's channels as a CUDA tensor [freq_local, npix] or [freq_local, 4, npix], first global channel)``.
+    The l-sharded root / apply and the channel-sharded SHT of ``dist.ShardedSky`` / ``ShardedPolSky``."""
+    from . import corr21cm, galaxy
+    from . import dist as cdist
+
+    if command == "21cm":
+        model = corr21cm.EoR21cm() if eor else corr21cm.Corr21cm()
+        zromb = oversample if oversample is not None else 3
+        sh = cdist.ShardedSky(model, nside, fstate.frequencies, lmax=3 * nside - 1, zromb=zromb)
+    elif pol == "full":
+        sh = cdist.ShardedPolSky(nside, fstate.frequencies)
+        sh.exchange = "p2p"
+    else:
+        sh = cdist.ShardedSky(galaxy.FullSkySynchrotron(), nside, fstate.frequencies, lmax=3 * nside)
+    sky = sh.step(seed=seed).clone()
+    if getattr(sh, "exchange", None) == "p2p" and sh.size > 1:
+        sh.peers.check()
+    first = int(sh.plan.chan_lo[sh.rank])
+    return sky, first, sh
+
+
 def main(argv=None):
     import argparse
+    import os
 
     ap = argparse.ArgumentParser(prog="cora_b200.makesky", description=__doc__.split("\n")[0])
     ap.add_argument("command", choices=["21cm", "gaussianfg"])
@@ -136,18 +161,49 @@ def main(argv=None):
     ap.add_argument("--eor", action="store_true")
     ap.add_argument("--oversample", type=int, default=None)
     ap.add_argument("--seed", type=int, default=None)
-    ap.add_argument("filename")
+    ap.add_argument("--sharded", action="store_true",
+                    help="generate with the l-/channel-sharded engine and write the frequency-sharded map directory "
+                         "(implied under torchrun with more than one rank)")
+    ap.add_argument("filename", help="X.npy: one array (single GPU); anything else: a map directory (cora_b200.mapio)")
     a = ap.parse_args(argv)
     fs = FreqState()
     fs.freq = (a.freq[0], a.freq[1], int(a.freq[2]))
     fs.freq_mode = a.freq_mode
     if a.seed is not None:
         np.random.seed(a.seed)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or a.sharded:
+        import torch
+
+        from . import mapio
+
+        rank = int(os.environ.get("RANK", "0"))
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+        sky, first, sh = make_sharded(a.command, fs, a.nside, a.pol, a.eor, a.oversample, seed=a.seed or 0)
+        if a.command == "21cm" and a.pol == "zero":
+            sky = sky[:, None, :]          # cora-makesky --pol zero: intensity only is generated, write_map pads (makesky.py:422-426)
+        mapio.write_map(a.filename, sky, fs.frequencies, fs.freq_width, include_pol=(a.pol != "none"), freq_start=first,
+                        rank=rank, size=world)
+        if world > 1:
+            dist.barrier()
+            if getattr(sh, "exchange", None) == "p2p":
+                sh.peers.close()
+            dist.destroy_process_group()
+        return
     if a.command == "21cm":
         m = make_21cm(fs, a.nside, a.pol, a.eor, a.oversample)
     else:
         m = make_gaussianfg(fs, a.nside, a.pol, seed=a.seed)
-    np.save(a.filename, m)
+    if a.filename.endswith(".npy"):
+        np.save(a.filename, m)
+    else:
+        from . import mapio
+
+        mapio.write_map(a.filename, m, fs.frequencies, fs.freq_width, include_pol=(a.pol != "none"))
 
 
 if __name__ == "__main__":

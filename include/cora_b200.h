@@ -179,8 +179,8 @@ int cora_b200_root_batched(const double* cl, int nl, int nz, double jitter_rel, 
  * low-rank route (pivoted Cholesky down to the jitter level, certified residual, one-sided Jacobi on the
  * factor's columns: the same eigenpairs in O(nz^2 rank)) and fall back to the full Jacobi when the matrix
  * is not numerically low-rank positive semi-definite or when the jitter itself would survive the clip.
- * workspace: cora_b200_root_multi_workspace_bytes(nblocks, nl, nz) (smaller: processed in waves, one host
- * synchronisation).  cora_b200_diag_max: dmax[l] = max_i cl[l][i][i], merged (max) into dmax when merge != 0. */
+ * workspace: cora_b200_root_multi_workspace_bytes(nblocks, nl, nz) (smaller: the fallback runs in waves guarded by
+ * the device-side failure count -- the host never synchronises).  cora_b200_diag_max: dmax[l] = max_i cl[l][i][i], merged (max) into dmax when merge != 0. */
 int cora_b200_diag_max(const double* cl, int nl, int nz, double* dmax, int merge, void* stream);
 long long cora_b200_root_multi_workspace_bytes(int nblocks, int nl, int nz);
 int cora_b200_root_batched_multi(const double* const* cl_blocks, int nblocks, int nl, int nz, double jitter_rel,
@@ -211,6 +211,13 @@ int cora_b200_eigh_batched(const double* a, int nl, int nz, double* evecs, doubl
  * Output rows nu in [nu0, nu0+nnu) go to alm_panel[idx(l,m) * panel_stride + chan0 + (nu-nu0)].
  * The workspace holds the generated draws of a batch of l's; any size that fits one l works. */
 long long cora_b200_draw_apply_workspace_bytes(int nz, int lmax_in_batch, int nl_batch);
+/* The draws alone, for overlap with the C_l fill and the root on another stream (they do not depend on C_l):
+ * complex128 variates for the l's of l_list_h, block i = [nz][l_i + 1] (row nu', m contiguous), blocks back to
+ * back; cora_b200_draw_bytes gives the size.  Pass the buffer to cora_b200_draw_apply* as `gauss` with
+ * gauss_ld = -1 (same l_list): the result is bit-identical to letting draw_apply draw by itself.           */
+long long cora_b200_draw_bytes(const int* l_list_h, int nl, int nz);
+int cora_b200_draw(const int* l_list_h, int nl, int nz, unsigned long long seed, int draw_counter0,
+                   void* gauss_packed, long long bytes, void* stream);
 int cora_b200_draw_apply(const double* root, const int* l_list_h, const int* dense_flag, int nl, int nz,
                          int lmax, unsigned long long seed, const void* gauss, long long gauss_ld,
                          void* alm_panel, long long panel_stride, int chan0, int nu0, int nnu,

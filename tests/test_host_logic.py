@@ -159,3 +159,32 @@ def test_fused_fill_only_for_the_package_own_spectrum():
     m = My21.__new__(My21)
     assert skysim._fused_fill(m.angular_powerspectrum, m) is None
     assert skysim._fused_fill(lambda l, a, b: 1.0, None) is None
+
+
+def test_map_writer_layout_roundtrip(tmp_path):
+    """The sharded map writer (makesky.py:412-450 write_map's layout: [freq, pol, pixel] + index maps): two ranks'
+    blocks, unpolarised data padded to Stokes I/Q/U/V like the reference does."""
+    from cora_b200 import mapio
+    from cora_b200.dist import block_partition
+
+    freq = np.linspace(800.0, 400.0, 5, endpoint=False)
+    npix = 48
+    rng = np.random.default_rng(0)
+    full = rng.standard_normal((5, npix))
+    out = str(tmp_path / "map")
+    for r in (1, 0):
+        lo, hi = block_partition(5, 2, r)
+        mapio.write_map(out, full[lo:hi], freq, fwidth=80.0, include_pol=True, freq_start=lo, rank=r, size=2)
+    got, hdr = mapio.read_map(out)
+    assert got.shape == (5, 4, npix) and hdr["pol"] == ["I", "Q", "U", "V"] and hdr["axis"] == ["freq", "pol", "pixel"]
+    np.testing.assert_array_equal(got[:, 0], full)
+    assert not got[:, 1:].any()
+    assert hdr["freq"]["centre"] == freq.tolist() and hdr["freq"]["width"] == [80.0] * 5
+    assert [s["freq_start"] for s in hdr["shards"]] == [0, 3] and hdr["attrs"]["__memh5_distributed_file"] is True
+    # polarised block, no padding; intensity only
+    pol = rng.standard_normal((5, 4, npix))
+    mapio.write_map(str(tmp_path / "p"), pol, freq)
+    np.testing.assert_array_equal(mapio.read_map(str(tmp_path / "p"))[0], pol)
+    mapio.write_map(str(tmp_path / "i"), full, freq, include_pol=False)
+    g, h = mapio.read_map(str(tmp_path / "i"))
+    assert g.shape == (5, 1, npix) and h["pol"] == ["I"] and h["freq"]["width"][0] == 80.0
