@@ -465,7 +465,7 @@ def run_ours(args):
         if pol:
             parity_note = "not run: the single-GPU polarised path does not fit beside the sharded buffers"
         else:
-            need = 8.0 * (lmax + 1) * nchan * nchan * 2 + 16.0 * (lmax + 1) * (lmax + 2) / 2 * nchan * 2.2 + 8.0 * sh.cb * npix
+            need = 8.0 * (lmax + 1) * nchan * nchan * 2.3 + 16.0 * (lmax + 1) * (lmax + 2) / 2 * nchan + 8.0 * sh.cb * npix + (8 << 30)
             free = torch.cuda.mem_get_info()[0]
             if need > 0.8 * free:
                 parity_note = "not run: the single-GPU path needs %.0f GB, %.0f GB free" % (need / 1e9, free / 1e9)

@@ -494,17 +494,40 @@ class ShardedSky(object):
 def single_gpu_block(model, nside, frequencies, lmax, zromb, seed, chan_lo, chan_hi):
     """The single-GPU path (all l, all channels for fill / root / apply on this device) with the inverse SHT of
     channels [chan_lo, chan_hi) only: what a rank of a sharded run must reproduce for its channel block (Philox
-    counters are keyed by (l, m, nu), so the maps do not depend on the number of ranks).  CUDA ``float64[n, npix]``."""
+    counters are keyed by (l, m, nu), so the maps do not depend on the number of ranks).  CUDA ``float64[n, npix]``.
+    Buffers are released stage by stage and the workspaces are kept small (peak ~3 C_l tables), so that the check
+    fits beside a sharded run's own buffers."""
+    from . import skysim
+
     t = _dev.torch()
-    one = ShardedSky(model, nside, frequencies, lmax=lmax, zromb=zromb, rank=0, size=1, exchange="collective")
-    cla = one.fill()
-    panel = one.alm_local(cla, seed=seed)          # PANEL [nalm, nz]
+    lib = _lib.load()
+    freq = np.asarray(frequencies, dtype=np.float64)
+    nz, L = len(freq), int(lmax) + 1
+    nalm = L * (L + 1) // 2
+    npix = 12 * int(nside) ** 2
+    za, zint = skysim._sample_frequencies(freq, zromb, None)
+    inputs = model._b200_fill_inputs(za, skysim.romberg_weights(zromb))
+    cla = _dev.zeros((L, nz, nz), t.float64)
+    model._b200_fill(inputs, 0, 1, L, nz, zint, cla, lower_only=True)
+    rws = nputil.root_workspace(L, nz, max_eigh=max(4, L // 32))
+    root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16, ws=rws)
+    del cla, rws
+    panel = _dev.empty((nalm, nz), t.complex128)
+    l_list = np.arange(L, dtype=np.int32)
+    one = lib.cora_b200_draw_apply_workspace_bytes(nz, int(lmax), 1)
+    ws = _dev.workspace(max(one, min(lib.cora_b200_draw_apply_workspace_bytes(nz, int(lmax), L), 4 << 30)))
+    _lib.call("cora_b200_draw_apply", _lib.ptr(root), _lib.ptr(l_list), _lib.ptr(used), L, nz, int(lmax),
+              ctypes.c_ulonglong(int(seed)), None, 0, _lib.ptr(panel), nz, 0, 0, nz, _lib.ptr(ws), int(ws.numel()),
+              _lib.stream_ptr())
+    t.cuda.current_stream().synchronize()
+    del root, used, ws
     n = int(chan_hi) - int(chan_lo)
-    out = _dev.empty((n, one.npix), t.float64)
-    plan = _dev.sht_plan(one.nside, one.lmax)
-    ws, nbytes = _dev.sht_workspace(plan, _lib.ALM_PANEL, n)
-    _lib.call("cora_b200_alm2map", plan, _lib.ptr_off(panel, 16 * int(chan_lo)), _lib.ALM_PANEL, one.nz, n, _lib.ptr(out),
-              _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+    out = _dev.empty((n, npix), t.float64)
+    plan = _dev.sht_plan(int(nside), int(lmax))
+    nbytes = int(lib.cora_b200_alm2map_workspace_bytes(plan, _lib.ALM_PANEL, min(n, 64)))
+    ws = _dev.workspace(nbytes)
+    _lib.call("cora_b200_alm2map", plan, _lib.ptr_off(panel, 16 * int(chan_lo)), _lib.ALM_PANEL, nz, n, _lib.ptr(out),
+              _lib.ptr(ws), nbytes, _lib.stream_ptr())
     t.cuda.current_stream().synchronize()
     return out
 
