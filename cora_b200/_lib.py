@@ -26,6 +26,7 @@ SIGNATURES = {
     "cora_b200_timing_kinds": (_i, []),
     "cora_b200_timing_name": (_c.c_char_p, [_i]),
     "cora_b200_timing_read": (_i, [_c.POINTER(_d), _c.POINTER(_ll), _i]),
+    "cora_b200_timing_trace": (_i, [_c.POINTER(_i), _c.POINTER(_d), _c.POINTER(_d), _i]),
     "cora_b200_sht_plan_create": (_i, [_i, _i, _c.POINTER(_vp)]),
     "cora_b200_sht_plan_destroy": (_i, [_vp]),
     "cora_b200_alm2map_workspace_bytes": (_ll, [_vp, _i, _i]),
@@ -71,6 +72,8 @@ SIGNATURES = {
     "cora_b200_diag_max": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "cora_b200_root_multi_workspace_bytes": (_ll, [_i, _i, _i]),
     "cora_b200_root_batched_multi": (_i, [_vp, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "cora_b200_legendre_table": (_i, [_vp, _vp, _i, _i, _vp, _ll, _vp]),
+    "cora_b200_dgemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _vp]),
 }
 
 _lib = None

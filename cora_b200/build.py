@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcora_b200.so")
-SOURCES = ["abi.cu", "sht.cu", "layout.cu", "cl.cu", "root.cu", "apply.cu", "peer.cu"]
+SOURCES = ["abi.cu", "sht.cu", "layout.cu", "cl.cu", "root.cu", "apply.cu", "peer.cu", "corrfunc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -96,6 +96,22 @@ extern "C" int cora_b200_timing_read(double* ms_out, long long* launches_out, in
     return 0;
 }
 
+extern "C" int cora_b200_timing_trace(int* id_out, double* start_ms_out, double* dur_ms_out, int cap) {
+    // one entry per recorded span, in launch order: start relative to the first span's start.  Does not clear.
+    CB_REQUIRE(id_out && start_ms_out && dur_ms_out && cap >= 0, 1, "timing_trace: null output");
+    int n = 0;
+    for (auto& s : g_spans) {
+        if (n >= cap) break;
+        CB_CUDA(cudaEventSynchronize(s.e1));
+        float t0 = 0.f, dt = 0.f;
+        CB_CUDA(cudaEventElapsedTime(&t0, g_spans[0].e0, s.e0));
+        CB_CUDA(cudaEventElapsedTime(&dt, s.e0, s.e1));
+        id_out[n] = s.id; start_ms_out[n] = t0; dur_ms_out[n] = dt;
+        n++;
+    }
+    return -n;   // (negative count: non-negative returns are error codes everywhere else in this ABI)
+}
+
 extern "C" int cora_b200_fp64_peak(double ms_budget, double* tflops_out, void* stream) {
     CB_REQUIRE(tflops_out, 1, "fp64_peak: null output");
     cudaStream_t st = (cudaStream_t)stream;

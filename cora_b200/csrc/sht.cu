@@ -39,6 +39,7 @@ struct RingDesc {
 // rings launched together: all rings whose FFT fits Mmax points of shared memory per channel pair
 struct PhaseClass {
     int Mmax, P, threads;           // smem FFT capacity, channel pairs per CTA, CTA size
+    int blu;                        // 1: Bluestein rings only, 0: power-of-two rings only
     int nrings;
     int* d_rings;                   // ring indices of this class, longest ring first
 };
@@ -55,6 +56,7 @@ struct ShtPlan {
     double2* d_tw;                  // exp(2 pi i j / tw_n), j < tw_n/2
     int tw_n, log_tw;
     double2* d_chirp;               // Bluestein chirps  c_k = exp(i pi k^2 / nph), per cap ring
+    double2* d_shph;                // ring phase e^{i pi k / nph}, k <= nph/2, per Bluestein ring (offsets = chirp's)
     double2* d_bhat;                // FFT_M(conj chirp)/M in bit-reversed order, per cap ring
     long long *d_chirp_off, *d_bhat_off;   // [nside] offsets by cap ring number
     std::vector<PhaseClass> classes;
@@ -134,7 +136,7 @@ __device__ __forceinline__ double2 chirp_val(long long k, int n) {
 
 // One CTA per cap ring size: chirp table and bhat = DIF-FFT_M(b)/M with b_d = conj(c_d), d = -(n-1)..(n-1).
 __global__ void bluestein_setup_kernel(int nside, const long long* chirp_off, const long long* bhat_off,
-                                       double2* chirp, double2* bhat, const double2* tw, int log_tw) {
+                                       double2* chirp, double2* bhat, double2* shph, const double2* tw, int log_tw) {
     extern __shared__ __align__(16) double2 xs[];
     const int i = blockIdx.x + 1;  // cap ring number
     const int n = 4 * i;
@@ -146,6 +148,9 @@ __global__ void bluestein_setup_kernel(int nside, const long long* chirp_off, co
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double2 c = chirp_val(k, n);
         chirp[chirp_off[i] + k] = c;
+        double sn, cs;
+        sincospi((double)k / (double)n, &sn, &cs);
+        shph[chirp_off[i] + k] = make_double2(cs, sn);
         double2 b = cconj(c);
         xs[k] = b;
         if (k > 0) xs[M - k] = b;
@@ -805,6 +810,7 @@ struct PhaseParams {
     const double2* tw;
     const double2* chirp;
     const double2* bhat;
+    const double2* shph;      // e^{i pi k / nph} per Bluestein ring (same offsets as chirp)
     const long long *chirp_off, *bhat_off;
     int lmax, nb, ncg, P, Mmax, log_tw;
 };
@@ -836,7 +842,36 @@ template <int SIGN, int Q> __device__ __forceinline__ double2 mul_c8(double2 a) 
 }
 
 // Radix-2 decimation-in-frequency stages s, s-1, .. fused in registers (natural in -> bit-reversed
-// out, in place; identical data flow to one radix-2 stage after the other).
+// out, in place; identical data flow to one radix-2 stage after the other).  UNIT: all twiddles are 1
+// (the pass that covers stages 2, 1, 0 / 1, 0 / 0), so the multiplications by them are dropped.
+template <int SIGN, bool UNIT>
+__device__ __forceinline__ void dif8_core(double2 v[8], double2 w1, double2 w2, double2 w4) {
+    {   // stage s: pairs (j, j+4), twiddle w1 c8^j
+        double2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+        v[0] = cadd(v[0], v[4]); v[1] = cadd(v[1], v[5]); v[2] = cadd(v[2], v[6]); v[3] = cadd(v[3], v[7]);
+        if (UNIT) {
+            v[4] = d0; v[5] = mul_c8<SIGN, 1>(d1); v[6] = mul_c8<SIGN, 2>(d2); v[7] = mul_c8<SIGN, 3>(d3);
+        } else {
+            v[4] = cmul(d0, w1);
+            v[5] = cmul(mul_c8<SIGN, 1>(d1), w1);
+            v[6] = cmul(mul_c8<SIGN, 2>(d2), w1);
+            v[7] = cmul(mul_c8<SIGN, 3>(d3), w1);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {   // stage s-1: pairs (j, j+2), twiddle w2 (SIGN i)^j
+        double2 d0 = csub(v[h], v[h + 2]), d1 = csub(v[h + 1], v[h + 3]);
+        v[h] = cadd(v[h], v[h + 2]); v[h + 1] = cadd(v[h + 1], v[h + 3]);
+        if (UNIT) { v[h + 2] = d0; v[h + 3] = mul_i<SIGN>(d1); }
+        else { v[h + 2] = cmul(d0, w2); v[h + 3] = cmul(mul_i<SIGN>(d1), w2); }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {   // stage s-2: pairs (j, j+1), twiddle w4
+        double2 d = csub(v[h], v[h + 1]);
+        v[h] = cadd(v[h], v[h + 1]);
+        v[h + 1] = UNIT ? d : cmul(d, w4);
+    }
+}
 template <int SIGN>
 __device__ __forceinline__ void dif8(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
     const int S = 1 << (s - 2);
@@ -848,29 +883,22 @@ __device__ __forceinline__ void dif8(double2* x, int b, int s, const double2* __
     const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
     const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - s));
     const double2 w4 = ld_tw<SIGN>(tw, low << (log_tw - s + 1));
-    {   // stage s: pairs (j, j+4), twiddle w1 c8^j
-        double2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
-        v[0] = cadd(v[0], v[4]); v[1] = cadd(v[1], v[5]); v[2] = cadd(v[2], v[6]); v[3] = cadd(v[3], v[7]);
-        v[4] = cmul(d0, w1);
-        v[5] = cmul(mul_c8<SIGN, 1>(d1), w1);
-        v[6] = cmul(mul_c8<SIGN, 2>(d2), w1);
-        v[7] = cmul(mul_c8<SIGN, 3>(d3), w1);
-    }
-#pragma unroll
-    for (int h = 0; h < 8; h += 4) {   // stage s-1: pairs (j, j+2), twiddle w2 (SIGN i)^j
-        double2 d0 = csub(v[h], v[h + 2]), d1 = csub(v[h + 1], v[h + 3]);
-        v[h] = cadd(v[h], v[h + 2]); v[h + 1] = cadd(v[h + 1], v[h + 3]);
-        v[h + 2] = cmul(d0, w2);
-        v[h + 3] = cmul(mul_i<SIGN>(d1), w2);
-    }
-#pragma unroll
-    for (int h = 0; h < 8; h += 2) {   // stage s-2: pairs (j, j+1), twiddle w4
-        double2 d = csub(v[h], v[h + 1]);
-        v[h] = cadd(v[h], v[h + 1]);
-        v[h + 1] = cmul(d, w4);
-    }
+    dif8_core<SIGN, false>(v, w1, w2, w4);
 #pragma unroll
     for (int j = 0; j < 8; j++) x[pidx(base + j * S)] = v[j];
+}
+template <int SIGN, bool UNIT>
+__device__ __forceinline__ void dif4_core(double2 v[4], double2 w1, double2 w2) {
+    double2 d0 = csub(v[0], v[2]), d1 = csub(v[1], v[3]);
+    v[0] = cadd(v[0], v[2]); v[1] = cadd(v[1], v[3]);
+    if (UNIT) { v[2] = d0; v[3] = mul_i<SIGN>(d1); }
+    else { v[2] = cmul(d0, w1); v[3] = cmul(mul_i<SIGN>(d1), w1); }
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+        double2 d = csub(v[h], v[h + 1]);
+        v[h] = cadd(v[h], v[h + 1]);
+        v[h + 1] = UNIT ? d : cmul(d, w2);
+    }
 }
 template <int SIGN>
 __device__ __forceinline__ void dif4(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
@@ -882,16 +910,7 @@ __device__ __forceinline__ void dif4(double2* x, int b, int s, const double2* __
     for (int j = 0; j < 4; j++) v[j] = x[pidx(base + j * S)];
     const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
     const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - s));
-    double2 d0 = csub(v[0], v[2]), d1 = csub(v[1], v[3]);
-    v[0] = cadd(v[0], v[2]); v[1] = cadd(v[1], v[3]);
-    v[2] = cmul(d0, w1);
-    v[3] = cmul(mul_i<SIGN>(d1), w1);
-#pragma unroll
-    for (int h = 0; h < 4; h += 2) {
-        double2 d = csub(v[h], v[h + 1]);
-        v[h] = cadd(v[h], v[h + 1]);
-        v[h + 1] = cmul(d, w2);
-    }
+    dif4_core<SIGN, false>(v, w1, w2);
 #pragma unroll
     for (int j = 0; j < 4; j++) x[pidx(base + j * S)] = v[j];
 }
@@ -906,6 +925,32 @@ __device__ __forceinline__ void dif2(double2* x, int b, int s, const double2* __
 }
 
 // Decimation-in-time stages s, s+1, .. fused (bit-reversed in -> natural out, in place).
+template <int SIGN, bool UNIT>
+__device__ __forceinline__ void dit8_core(double2 v[8], double2 w4, double2 w2, double2 w1) {
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {   // stage s
+        const double2 t = UNIT ? v[h + 1] : cmul(v[h + 1], w4);
+        v[h + 1] = csub(v[h], t);
+        v[h] = cadd(v[h], t);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {   // stage s+1
+        const double2 t0 = UNIT ? v[h + 2] : cmul(v[h + 2], w2);
+        const double2 t1 = mul_i<SIGN>(UNIT ? v[h + 3] : cmul(v[h + 3], w2));
+        v[h + 2] = csub(v[h], t0); v[h] = cadd(v[h], t0);
+        v[h + 3] = csub(v[h + 1], t1); v[h + 1] = cadd(v[h + 1], t1);
+    }
+    {   // stage s+2
+        const double2 t0 = UNIT ? v[4] : cmul(v[4], w1);
+        const double2 t1 = mul_c8<SIGN, 1>(UNIT ? v[5] : cmul(v[5], w1));
+        const double2 t2 = mul_c8<SIGN, 2>(UNIT ? v[6] : cmul(v[6], w1));
+        const double2 t3 = mul_c8<SIGN, 3>(UNIT ? v[7] : cmul(v[7], w1));
+        v[4] = csub(v[0], t0); v[0] = cadd(v[0], t0);
+        v[5] = csub(v[1], t1); v[1] = cadd(v[1], t1);
+        v[6] = csub(v[2], t2); v[2] = cadd(v[2], t2);
+        v[7] = csub(v[3], t3); v[3] = cadd(v[3], t3);
+    }
+}
 template <int SIGN>
 __device__ __forceinline__ void dit8(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
     const int S = 1 << s;
@@ -917,31 +962,22 @@ __device__ __forceinline__ void dit8(double2* x, int b, int s, const double2* __
     const double2 w4 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
     const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - 2 - s));
     const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 3 - s));
+    dit8_core<SIGN, false>(v, w4, w2, w1);
 #pragma unroll
-    for (int h = 0; h < 8; h += 2) {   // stage s
-        const double2 t = cmul(v[h + 1], w4);
+    for (int j = 0; j < 8; j++) x[pidx(base + j * S)] = v[j];
+}
+template <int SIGN, bool UNIT>
+__device__ __forceinline__ void dit4_core(double2 v[4], double2 w2, double2 w1) {
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+        const double2 t = UNIT ? v[h + 1] : cmul(v[h + 1], w2);
         v[h + 1] = csub(v[h], t);
         v[h] = cadd(v[h], t);
     }
-#pragma unroll
-    for (int h = 0; h < 8; h += 4) {   // stage s+1
-        const double2 t0 = cmul(v[h + 2], w2);
-        const double2 t1 = mul_i<SIGN>(cmul(v[h + 3], w2));
-        v[h + 2] = csub(v[h], t0); v[h] = cadd(v[h], t0);
-        v[h + 3] = csub(v[h + 1], t1); v[h + 1] = cadd(v[h + 1], t1);
-    }
-    {   // stage s+2
-        const double2 t0 = cmul(v[4], w1);
-        const double2 t1 = mul_c8<SIGN, 1>(cmul(v[5], w1));
-        const double2 t2 = mul_c8<SIGN, 2>(cmul(v[6], w1));
-        const double2 t3 = mul_c8<SIGN, 3>(cmul(v[7], w1));
-        v[4] = csub(v[0], t0); v[0] = cadd(v[0], t0);
-        v[5] = csub(v[1], t1); v[1] = cadd(v[1], t1);
-        v[6] = csub(v[2], t2); v[2] = cadd(v[2], t2);
-        v[7] = csub(v[3], t3); v[3] = cadd(v[3], t3);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) x[pidx(base + j * S)] = v[j];
+    const double2 t0 = UNIT ? v[2] : cmul(v[2], w1);
+    const double2 t1 = mul_i<SIGN>(UNIT ? v[3] : cmul(v[3], w1));
+    v[2] = csub(v[0], t0); v[0] = cadd(v[0], t0);
+    v[3] = csub(v[1], t1); v[1] = cadd(v[1], t1);
 }
 template <int SIGN>
 __device__ __forceinline__ void dit4(double2* x, int b, int s, const double2* __restrict__ tw, int log_tw) {
@@ -953,16 +989,7 @@ __device__ __forceinline__ void dit4(double2* x, int b, int s, const double2* __
     for (int j = 0; j < 4; j++) v[j] = x[pidx(base + j * S)];
     const double2 w2 = ld_tw<SIGN>(tw, low << (log_tw - 1 - s));
     const double2 w1 = ld_tw<SIGN>(tw, low << (log_tw - 2 - s));
-#pragma unroll
-    for (int h = 0; h < 4; h += 2) {
-        const double2 t = cmul(v[h + 1], w2);
-        v[h + 1] = csub(v[h], t);
-        v[h] = cadd(v[h], t);
-    }
-    const double2 t0 = cmul(v[2], w1);
-    const double2 t1 = mul_i<SIGN>(cmul(v[3], w1));
-    v[2] = csub(v[0], t0); v[0] = cadd(v[0], t0);
-    v[3] = csub(v[1], t1); v[1] = cadd(v[1], t1);
+    dit4_core<SIGN, false>(v, w2, w1);
 #pragma unroll
     for (int j = 0; j < 4; j++) x[pidx(base + j * S)] = v[j];
 }
@@ -978,131 +1005,229 @@ __device__ __forceinline__ void dit2(double2* x, int b, int s, const double2* __
 }
 
 // P sequences of M points at xs + p * seq_stride (padded layout); whole CTA participates.
+// s_stop: the DIF stops before the pass that would start at stage s_stop (-1: run every pass).
 template <int SIGN>
-__device__ void fft_dif_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw) {
+__device__ void fft_dif_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw,
+                               bool skip_last = false) {
     int s = logM - 1;
+    const int rem = logM % 3;
     for (; s >= 2; s -= 3) {
-        const int nbf = M >> 3;
+        if (skip_last && rem == 0 && s == 2) return;
+        const int lg = logM - 3, nbf = 1 << lg;
         for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
-            const int p = w / nbf;
-            dif8<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, s, tw, log_tw);
+            const int p = w >> lg;
+            dif8<SIGN>(xs + (size_t)p * seq_stride, w & (nbf - 1), s, tw, log_tw);
         }
         __syncthreads();
     }
+    if (skip_last) return;
     if (s == 1) {
-        const int nbf = M >> 2;
+        const int lg = logM - 2, nbf = 1 << lg;
         for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
-            const int p = w / nbf;
-            dif4<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 1, tw, log_tw);
+            const int p = w >> lg;
+            dif4<SIGN>(xs + (size_t)p * seq_stride, w & (nbf - 1), 1, tw, log_tw);
         }
         __syncthreads();
     } else if (s == 0) {
-        const int nbf = M >> 1;
+        const int lg = logM - 1, nbf = 1 << lg;
         for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
-            const int p = w / nbf;
-            dif2<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 0, tw, log_tw);
+            const int p = w >> lg;
+            dif2<SIGN>(xs + (size_t)p * seq_stride, w & (nbf - 1), 0, tw, log_tw);
         }
         __syncthreads();
     }
 }
 template <int SIGN>
-__device__ void fft_dit_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw) {
+__device__ void fft_dit_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw,
+                               bool skip_first = false) {
     int s = 0;
     const int rem = logM % 3;
-    if (rem == 1) {
-        const int nbf = M >> 1;
+    if (skip_first) {
+        s = (rem == 0) ? 3 : rem;
+    } else if (rem == 1) {
+        const int lg = logM - 1, nbf = 1 << lg;
         for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
-            const int p = w / nbf;
-            dit2<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 0, tw, log_tw);
+            const int p = w >> lg;
+            dit2<SIGN>(xs + (size_t)p * seq_stride, w & (nbf - 1), 0, tw, log_tw);
         }
         __syncthreads();
         s = 1;
     } else if (rem == 2) {
-        const int nbf = M >> 2;
+        const int lg = logM - 2, nbf = 1 << lg;
         for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
-            const int p = w / nbf;
-            dit4<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, 0, tw, log_tw);
+            const int p = w >> lg;
+            dit4<SIGN>(xs + (size_t)p * seq_stride, w & (nbf - 1), 0, tw, log_tw);
         }
         __syncthreads();
         s = 2;
     }
     for (; s + 2 < logM; s += 3) {
-        const int nbf = M >> 3;
+        const int lg = logM - 3, nbf = 1 << lg;
         for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
-            const int p = w / nbf;
-            dit8<SIGN>(xs + (size_t)p * seq_stride, w - p * nbf, s, tw, log_tw);
+            const int p = w >> lg;
+            dit8<SIGN>(xs + (size_t)p * seq_stride, w & (nbf - 1), s, tw, log_tw);
         }
         __syncthreads();
     }
 }
 
+// Bluestein convolution  x <- IFFT_M( FFT_M(x) . bhat )  on P padded sequences.  The last DIF pass, the pointwise
+// product and the first DIT pass touch the same R = 8 / 2 / 4 (logM mod 3 = 0 / 1 / 2) consecutive elements and all
+// their twiddles are 1: they run as one register pass (two shared-memory round trips and two barriers fewer).
+template <int R>
+__device__ __forceinline__ void blu_mid(double2* x, int b, const double2* __restrict__ bh) {
+    double2 v[R];
+    const int base = b * R;
+#pragma unroll
+    for (int j = 0; j < R; j++) v[j] = x[pidx(base + j)];
+    const double2 one = make_double2(1.0, 0.0);
+    if (R == 8) dif8_core<-1, true>(v, one, one, one);
+    else if (R == 4) dif4_core<-1, true>(v, one, one);
+    else { const double2 u = v[0]; v[0] = cadd(u, v[1]); v[1] = csub(u, v[1]); }
+#pragma unroll
+    for (int j = 0; j < R; j++) v[j] = cmul(v[j], bh[base + j]);
+    if (R == 8) dit8_core<+1, true>(v, one, one, one);
+    else if (R == 4) dit4_core<+1, true>(v, one, one);
+    else { const double2 u = v[0]; v[0] = cadd(u, v[1]); v[1] = csub(u, v[1]); }
+#pragma unroll
+    for (int j = 0; j < R; j++) x[pidx(base + j)] = v[j];
+}
+__device__ void bluestein_conv_padded(double2* xs, int seq_stride, int M, int logM, int P, const double2* __restrict__ tw, int log_tw,
+                                      const double2* __restrict__ bh) {
+    fft_dif_padded<-1>(xs, seq_stride, M, logM, P, tw, log_tw, true);
+    const int rem = logM % 3;
+    const int lgr = (rem == 0) ? 3 : rem;          // log2 R
+    const int lg = logM - lgr, nbf = 1 << lg;
+    for (int w = threadIdx.x; w < P * nbf; w += blockDim.x) {
+        double2* x = xs + (size_t)(w >> lg) * seq_stride;
+        const int b = w & (nbf - 1);
+        if (rem == 0) blu_mid<8>(x, b, bh);
+        else if (rem == 1) blu_mid<2>(x, b, bh);
+        else blu_mid<4>(x, b, bh);
+    }
+    __syncthreads();
+    fft_dit_padded<+1>(xs, seq_stride, M, logM, P, tw, log_tw, true);
+}
+
 constexpr int PH_MAXSLICE_ITEMS = 512;   // fold work items (bin, pair, slice) staged for the slice reduction
 
-template <int THREADS>
+// One fold work item: the aliased copies q = q0, q0 + qstep, .. of bin k (m = k + q n) and of its twin n - k, for the
+// channel pair (c, c + 1) of the group.  The bin and its twin (n - k >= k, so its copies are a subset of the bin's) are
+// walked together: the four F loads of an iteration are independent and in flight at once.
+__device__ __forceinline__ void fold_bin(const double2* __restrict__ Fr, int c, bool has2, int k, int kk, bool twin, int n, int lmax,
+                                         bool shifted, int q0, int qstep, double2& a1, double2& a2, double2& b1, double2& b2) {
+    for (int q = q0; k + q * n <= lmax; q += qstep) {
+        const int m = k + q * n, m2 = kk + q * n;
+        const bool v2 = twin && (m2 <= lmax);
+        double2 f1 = Fr[m * 4 + c];
+        double2 f2 = has2 ? Fr[m * 4 + c + 1] : make_double2(0, 0);
+        const double2 g1 = v2 ? Fr[m2 * 4 + c] : make_double2(0, 0);
+        const double2 g2 = (v2 && has2) ? Fr[m2 * 4 + c + 1] : make_double2(0, 0);
+        if (m == 0) { f1.y = 0.0; f2.y = 0.0; }
+        double sg = (m == 0) ? 1.0 : 2.0;
+        if (shifted && (q & 1)) sg = -sg;   // (-1)^q of the aliased copy on shifted rings
+        a1.x += sg * f1.x; a1.y += sg * f1.y;
+        a2.x += sg * f2.x; a2.y += sg * f2.y;
+        if (v2) {
+            const double sg2 = (shifted && (q & 1)) ? -2.0 : 2.0;
+            b1.x += sg2 * g1.x; b1.y += sg2 * g1.y;
+            b2.x += sg2 * g2.x; b2.y += sg2 * g2.y;
+        }
+    }
+}
+
+// PP: channel pairs per CTA (1 or 2); BLU: the class holds Bluestein rings (else power-of-two rings).
+template <int THREADS, int PP, bool BLU>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_phase_kernel(PhaseParams Q) {
-    extern __shared__ __align__(16) double2 xs[];   // [P][pidx(Mmax)] + slice partials
+    extern __shared__ __align__(16) double2 xs[];   // [PP][pidx(Mmax)] + slice partials
     const int r = Q.ring_list[blockIdx.x];
     const RingDesc rd = Q.rings[r];
-    const int n = rd.nph, logM = rd.logM, M = 1 << logM, Pp = Q.P;
-    const bool blu = rd.bluestein != 0;
+    const int n = rd.nph, logM = rd.logM, M = 1 << logM;
     const int seq = pidx(Q.Mmax) + 1;               // padded sequence stride
-    double2* part = xs + (size_t)Pp * seq;          // [PH_MAXSLICE_ITEMS][4]
-    const int gpc = 2 / Pp;                         // CTAs per channel group
+    double2* part = xs + (size_t)PP * seq;          // [PH_MAXSLICE_ITEMS][4]
+    constexpr int gpc = 2 / PP;                     // CTAs per channel group
     const int cg = blockIdx.y / gpc;
-    const int pair0 = (blockIdx.y % gpc) * Pp;      // first pair (of the group's two) handled here
+    const int pair0 = (blockIdx.y % gpc) * PP;      // first pair (of the group's two) handled here
     const int L = Q.lmax + 1;
     const double2* Fr = Q.F + (((long long)r * Q.ncg + cg) * L) * 4;
     const int half = n >> 1;
-    const double2* chirp = blu ? Q.chirp + Q.chirp_off[rd.cap] : nullptr;
+    const double2* chirp = BLU ? Q.chirp + Q.chirp_off[rd.cap] : nullptr;
+    const double2* shph = BLU ? Q.shph + Q.chirp_off[rd.cap] : nullptr;   // e^{i pi k / n}, k <= n/2
+    const bool shifted = rd.shifted != 0;
+    const bool tw_phase = !BLU && (logM + 1 <= Q.log_tw);                  // e^{i pi k/n} = tw[k * tw_n / (2n)]
 
-    if (blu) {
-        for (int w = threadIdx.x; w < Pp * (M - n); w += blockDim.x) {
-            const int p = w / (M - n), k = n + (w - p * (M - n));
-            xs[(size_t)p * seq + pidx(k)] = make_double2(0.0, 0.0);
-        }
+    if (BLU) {
+#pragma unroll
+        for (int p = 0; p < PP; p++)
+            for (int k = n + threadIdx.x; k < M; k += THREADS) xs[(size_t)p * seq + pidx(k)] = make_double2(0.0, 0.0);
     }
+
+    // bin sums -> the two points (k, n - k) of the pair's complex sequence
+    auto finish = [&](int k, int kk, bool twin, int pair, double2 a1, double2 a2, double2 b1, double2 b2) {
+        if (twin) {
+            if (shifted) {
+                // e^{i pi k/n} on bin k;  e^{i pi (n-k)/n} = -conj(e^{i pi k/n}) on bin n-k
+                double2 ph;
+                if (BLU) ph = shph[k];
+                else if (tw_phase) ph = Q.tw[k << (Q.log_tw - 1 - logM)];
+                else { double sn, cs; sincospi((double)k / (double)n, &sn, &cs); ph = make_double2(cs, sn); }
+                const double2 phb = make_double2(-ph.x, ph.y);
+                a1 = cmul(a1, ph); a2 = cmul(a2, ph);
+                b1 = cmul(b1, phb); b2 = cmul(b2, phb);
+            }
+        } else {
+            if (shifted && k != 0) {   // k == n/2: phase e^{i pi/2} = i
+                a1 = make_double2(-a1.y, a1.x);
+                a2 = make_double2(-a2.y, a2.x);
+            }
+            b1 = a1; b2 = a2;
+        }
+        // H = (G_k + conj(G_{n-k}))/2
+        const double2 h1 = make_double2(0.5 * (a1.x + b1.x), 0.5 * (a1.y - b1.y));
+        const double2 h2 = make_double2(0.5 * (a2.x + b2.x), 0.5 * (a2.y - b2.y));
+        const double2 zk = make_double2(h1.x - h2.y, h1.y + h2.x);
+        const double2 zn = make_double2(h1.x + h2.y, -h1.y + h2.x);
+        double2* xp = xs + (size_t)pair * seq;
+        if (BLU) {
+            xp[pidx(k)] = cmul(zk, chirp[k]);
+            if (twin) xp[pidx(kk)] = cmul(zn, chirp[kk]);
+        } else {
+            xp[pidx(bitrev(k, logM))] = zk;
+            if (twin) xp[pidx(bitrev(kk, logM))] = zn;
+        }
+    };
+
     // ---- fold m -> m mod nph.  Work item = (bin k <= n/2, pair, slice): a slice sums every
     // nsl-th aliased m of its bin; short rings get several slices per bin so the CTA stays busy.
-    const int nbin = (half + 1) * Pp;
+    const int nbin = (half + 1) * PP;
     int nsl = 1;
-    while (nsl * 2 * nbin <= min((int)blockDim.x, PH_MAXSLICE_ITEMS) && nsl * 2 * n <= L) nsl *= 2;
-    for (int w0 = 0; w0 < nbin * nsl; w0 += blockDim.x) {
-        const int w = w0 + threadIdx.x;
-        const bool act = w < nbin * nsl;
-        const int sl = act ? w / nbin : 0;
-        const int wb = act ? w - sl * nbin : 0;
-        const int pair = wb % Pp, k = wb / Pp;
-        const int c = 2 * (pair0 + pair);                      // channel inside the group of 4
-        const int ch = cg * 4 + c;
-        const bool has1 = act && ch < Q.nb, has2 = act && ch + 1 < Q.nb;
-        double2 a1 = make_double2(0, 0), a2 = a1, b1 = a1, b2 = a1;
-        const int kk = n - k;
-        const bool twin = (k != 0 && kk != k);
-        if (has1) {
-            // (-1)^q of the aliased copy q (m = k + q n) on shifted rings.  The bin and its twin (n - k >= k, so
-            // its copies are a subset of the bin's) are walked together: the four F loads of an iteration are
-            // independent and in flight at once (the fold is load-latency bound: 19 % of the kernel's stall
-            // samples sat on the DFMAs consuming them one bin at a time).
-            for (int q = sl; k + q * n <= Q.lmax; q += nsl) {
-                const int m = k + q * n, m2 = kk + q * n;
-                const bool v2 = twin && (m2 <= Q.lmax);
-                double2 f1 = Fr[m * 4 + c];
-                double2 f2 = has2 ? Fr[m * 4 + c + 1] : make_double2(0, 0);
-                const double2 g1 = v2 ? Fr[m2 * 4 + c] : make_double2(0, 0);
-                const double2 g2 = (v2 && has2) ? Fr[m2 * 4 + c + 1] : make_double2(0, 0);
-                if (m == 0) { f1.y = 0.0; f2.y = 0.0; }
-                double sg = (m == 0) ? 1.0 : 2.0;
-                if (rd.shifted && (q & 1)) sg = -sg;
-                a1.x += sg * f1.x; a1.y += sg * f1.y;
-                a2.x += sg * f2.x; a2.y += sg * f2.y;
-                if (v2) {
-                    const double sg2 = (rd.shifted && (q & 1)) ? -2.0 : 2.0;
-                    b1.x += sg2 * g1.x; b1.y += sg2 * g1.y;
-                    b2.x += sg2 * g2.x; b2.y += sg2 * g2.y;
-                }
-            }
+    while (nsl * 2 * nbin <= min(THREADS, PH_MAXSLICE_ITEMS) && nsl * 2 * n <= L) nsl *= 2;
+    if (nsl == 1) {
+        for (int w = threadIdx.x; w < nbin; w += THREADS) {
+            const int pair = w % PP, k = w / PP;                   // PP is a compile-time 1 or 2
+            const int c = 2 * (pair0 + pair);                      // channel inside the group of 4
+            const int ch = cg * 4 + c;
+            if (ch >= Q.nb) continue;
+            const int kk = n - k;
+            const bool twin = (k != 0 && kk != k);
+            double2 a1 = make_double2(0, 0), a2 = a1, b1 = a1, b2 = a1;
+            fold_bin(Fr, c, ch + 1 < Q.nb, k, kk, twin, n, Q.lmax, shifted, 0, 1, a1, a2, b1, b2);
+            finish(k, kk, twin, pair, a1, a2, b1, b2);
         }
-        if (nsl > 1) {
+    } else {
+        for (int w0 = 0; w0 < nbin * nsl; w0 += THREADS) {
+            const int w = w0 + threadIdx.x;
+            const bool act = w < nbin * nsl;
+            const int sl = act ? w / nbin : 0;
+            const int wb = act ? w - sl * nbin : 0;
+            const int pair = wb % PP, k = wb / PP;
+            const int c = 2 * (pair0 + pair);
+            const int ch = cg * 4 + c;
+            const bool has1 = act && ch < Q.nb;
+            const int kk = n - k;
+            const bool twin = (k != 0 && kk != k);
+            double2 a1 = make_double2(0, 0), a2 = a1, b1 = a1, b2 = a1;
+            if (has1) fold_bin(Fr, c, ch + 1 < Q.nb, k, kk, twin, n, Q.lmax, shifted, sl, nsl, a1, a2, b1, b2);
             // fixed-order reduction over the slices (deterministic)
             if (act) {
                 double2* pp = part + (size_t)w * 4;
@@ -1114,66 +1239,30 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_phase_ker
                     const double2* pp = part + (size_t)(s2 * nbin + wb) * 4;
                     a1 = cadd(a1, pp[0]); a2 = cadd(a2, pp[1]); b1 = cadd(b1, pp[2]); b2 = cadd(b2, pp[3]);
                 }
+                finish(k, kk, twin, pair, a1, a2, b1, b2);
             }
+            __syncthreads();   // partials consumed before the next round overwrites them
         }
-        if (act && sl == 0) {
-            if (twin) {
-                if (rd.shifted) {
-                    // e^{i pi k/n} on bin k;  e^{i pi (n-k)/n} = -conj(e^{i pi k/n}) on bin n-k
-                    double sn, cs;
-                    sincospi((double)k / (double)n, &sn, &cs);
-                    const double2 ph = make_double2(cs, sn), phb = make_double2(-cs, sn);
-                    a1 = cmul(a1, ph); a2 = cmul(a2, ph);
-                    b1 = cmul(b1, phb); b2 = cmul(b2, phb);
-                }
-            } else {
-                if (rd.shifted && k != 0) {   // k == n/2: phase e^{i pi/2} = i
-                    a1 = make_double2(-a1.y, a1.x);
-                    a2 = make_double2(-a2.y, a2.x);
-                }
-                b1 = a1; b2 = a2;
-            }
-            // H = (G_k + conj(G_{n-k}))/2
-            const double2 h1 = make_double2(0.5 * (a1.x + b1.x), 0.5 * (a1.y - b1.y));
-            const double2 h2 = make_double2(0.5 * (a2.x + b2.x), 0.5 * (a2.y - b2.y));
-            double2 zk = make_double2(h1.x - h2.y, h1.y + h2.x);
-            double2 zn = make_double2(h1.x + h2.y, -h1.y + h2.x);
-            double2* xp = xs + (size_t)pair * seq;
-            if (blu) {
-                xp[pidx(k)] = cmul(zk, chirp[k]);
-                if (twin) xp[pidx(kk)] = cmul(zn, chirp[kk]);
-            } else {
-                xp[pidx(bitrev(k, logM))] = zk;
-                if (twin) xp[pidx(bitrev(kk, logM))] = zn;
-            }
-        }
-        if (nsl > 1) __syncthreads();   // partials consumed before the next round overwrites them
     }
     __syncthreads();
 
-    if (blu) {
-        fft_dif_padded<-1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
-        const double2* bh = Q.bhat + Q.bhat_off[rd.cap];
-        for (int w = threadIdx.x; w < Pp * M; w += blockDim.x) {
-            const int p = w >> logM, k = w & (M - 1);
-            double2* e = xs + (size_t)p * seq + pidx(k);
-            *e = cmul(*e, bh[k]);
-        }
-        __syncthreads();
-        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
-    } else {
-        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
-    }
+    if (BLU) bluestein_conv_padded(xs, seq, M, logM, PP, Q.tw, Q.log_tw, Q.bhat + Q.bhat_off[rd.cap]);
+    else fft_dit_padded<+1>(xs, seq, M, logM, PP, Q.tw, Q.log_tw);
 
     // ---- store: real part -> first channel of the pair, imaginary part -> second
-    for (int w = threadIdx.x; w < n * Pp; w += blockDim.x) {
-        const int pair = w / n, j = w - pair * n;
+#pragma unroll
+    for (int pair = 0; pair < PP; pair++) {
         const int ch = cg * 4 + 2 * (pair0 + pair);
         if (ch >= Q.nb) continue;
-        double2 v = xs[(size_t)pair * seq + pidx(j)];
-        if (blu) v = cmul(v, chirp[j]);
-        Q.map[(long long)ch * Q.npix + rd.start + j] = v.x;
-        if (ch + 1 < Q.nb) Q.map[(long long)(ch + 1) * Q.npix + rd.start + j] = v.y;
+        double* o1 = Q.map + (long long)ch * Q.npix + rd.start;
+        double* o2 = (ch + 1 < Q.nb) ? o1 + Q.npix : nullptr;
+        const double2* xp = xs + (size_t)pair * seq;
+        for (int j = threadIdx.x; j < n; j += THREADS) {
+            double2 v = xp[pidx(j)];
+            if (BLU) v = cmul(v, chirp[j]);
+            o1[j] = v.x;
+            if (o2) o2[j] = v.y;
+        }
     }
 }
 
@@ -1232,19 +1321,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_ring_anal
         else xp[pidx(bitrev(j, logM))] = v;
     }
     __syncthreads();
-    if (blu) {
-        fft_dif_padded<-1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
-        const double2* bh = Q.bhat + Q.bhat_off[rd.cap];
-        for (int w = threadIdx.x; w < Pp * M; w += blockDim.x) {
-            const int p = w >> logM, k = w & (M - 1);
-            double2* e = xs + (size_t)p * seq + pidx(k);
-            *e = cmul(*e, bh[k]);
-        }
-        __syncthreads();
-        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
-    } else {
-        fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
-    }
+    if (blu) bluestein_conv_padded(xs, seq, M, logM, Pp, Q.tw, Q.log_tw, Q.bhat + Q.bhat_off[rd.cap]);
+    else fft_dit_padded<+1>(xs, seq, M, logM, Pp, Q.tw, Q.log_tw);
     // xs[k] (times chirp[k] for Bluestein) = Y_k = conj(Z_k), Z = DFT_n(z).
     const int nring = 4 * Q.nside - 1;
     const int north = min(r, nring - 1 - r);
@@ -1757,6 +1835,7 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
     twiddle_kernel<<<ceil_div(maxM / 2, 256), 256>>>(pl->d_tw, maxM); count_launch();
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaMalloc(&pl->d_chirp, sizeof(double2) * std::max(1LL, nchirp)));
+    CB_CUDA(cudaMalloc(&pl->d_shph, sizeof(double2) * std::max(1LL, nchirp)));
     CB_CUDA(cudaMalloc(&pl->d_bhat, sizeof(double2) * std::max(1LL, nbhat)));
     CB_CUDA(cudaMalloc(&pl->d_chirp_off, sizeof(long long) * (nside + 1)));
     CB_CUDA(cudaMalloc(&pl->d_bhat_off, sizeof(long long) * (nside + 1)));
@@ -1765,12 +1844,16 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
     if (nbhat > 0) {
         CB_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
         bluestein_setup_kernel<<<nside, 256, (size_t)maxM * 16>>>(nside, pl->d_chirp_off, pl->d_bhat_off, pl->d_chirp,
-                                                                  pl->d_bhat, pl->d_tw, pl->log_tw);
+                                                                  pl->d_bhat, pl->d_shph, pl->d_tw, pl->log_tw);
         count_launch();
         CB_LAUNCH_CHECK();
     }
-    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
     // per-ring FFT size; rings launched together by shared-memory footprint, longest first
     for (auto& rd : pl->h_rings) {
@@ -1781,13 +1864,16 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
     }
     CB_CUDA(cudaMemcpy(pl->d_rings, pl->h_rings.data(), sizeof(RingDesc) * nring, cudaMemcpyHostToDevice));
     {
-        std::vector<std::vector<int>> bycls(16);
-        for (int r = 0; r < nring; r++) bycls[std::max(9, pl->h_rings[r].logM)].push_back(r);
-        for (int lg = 15; lg >= 9; lg--) {
-            auto& v = bycls[lg];
+        // classes: (shared-memory FFT size, Bluestein or power-of-two ring) -- one kernel instantiation each
+        std::vector<std::vector<int>> bycls(32);
+        for (int r = 0; r < nring; r++) bycls[2 * std::max(9, pl->h_rings[r].logM) + pl->h_rings[r].bluestein].push_back(r);
+        for (int ci = 31; ci >= 18; ci--) {
+            auto& v = bycls[ci];
             if (v.empty()) continue;
+            const int lg = ci / 2;
             std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return pl->h_rings[x].nph > pl->h_rings[y].nph; });
             PhaseClass pc;
+            pc.blu = ci & 1;
             pc.Mmax = 1 << lg;
             pc.P = (pc.Mmax <= 4096) ? 2 : 1;          // 2 pairs x 4096 points (padded) = 147 KB
             pc.threads = (pc.Mmax >= 4096) ? 512 : 256;
@@ -1807,7 +1893,7 @@ extern "C" int cora_b200_sht_plan_destroy(void* plan) {
     ShtPlan* pl = (ShtPlan*)plan;
     cudaFree(pl->d_rc);
     cudaFree(pl->d_cth); cudaFree(pl->d_sth); cudaFree(pl->d_nm_mant); cudaFree(pl->d_nm_exp);
-    cudaFree(pl->d_rings); cudaFree(pl->d_tw); cudaFree(pl->d_chirp); cudaFree(pl->d_bhat);
+    cudaFree(pl->d_rings); cudaFree(pl->d_tw); cudaFree(pl->d_chirp); cudaFree(pl->d_shph); cudaFree(pl->d_bhat);
     cudaFree(pl->d_chirp_off); cudaFree(pl->d_bhat_off);
     for (auto& pc : pl->classes) cudaFree(pc.d_rings);
     delete pl;
@@ -1911,10 +1997,20 @@ static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, c
         Q.rings = pl->d_rings; Q.ring_list = pc.d_rings;
         Q.tw = pl->d_tw; Q.chirp = pl->d_chirp; Q.bhat = pl->d_bhat;
         Q.chirp_off = pl->d_chirp_off; Q.bhat_off = pl->d_bhat_off;
+        Q.shph = pl->d_shph;
         Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
         dim3 grid(pc.nrings, Q.ncg * (2 / pc.P));
-        if (pc.threads == 256) sht_phase_kernel<256><<<grid, 256, phase_smem(pc), st>>>(Q);
-        else sht_phase_kernel<512><<<grid, 512, phase_smem(pc), st>>>(Q);
+        const size_t sm = phase_smem(pc);
+        if (pc.threads == 256) {
+            if (pc.blu) sht_phase_kernel<256, 2, true><<<grid, 256, sm, st>>>(Q);
+            else sht_phase_kernel<256, 2, false><<<grid, 256, sm, st>>>(Q);
+        } else if (pc.P == 2) {
+            if (pc.blu) sht_phase_kernel<512, 2, true><<<grid, 512, sm, st>>>(Q);
+            else sht_phase_kernel<512, 2, false><<<grid, 512, sm, st>>>(Q);
+        } else {
+            if (pc.blu) sht_phase_kernel<512, 1, true><<<grid, 512, sm, st>>>(Q);
+            else sht_phase_kernel<512, 1, false><<<grid, 512, sm, st>>>(Q);
+        }
         count_launch();
         CB_LAUNCH_CHECK();
     }

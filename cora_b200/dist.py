@@ -93,6 +93,20 @@ class ShardPlan(object):
     def nalm_total(self):
         return int(self.rows.sum())
 
+    # ---- all-gather of the alm (``alms=True``, skysim.py:123-125) -------------------------------
+    def gather_tables(self):
+        """(nu_base[nz], nu_width[nz]) that make ``cora_b200_draw_apply_slabs`` write ONE slab ``[rows_r][nz]``
+        (every channel, not per-destination slabs): what each rank contributes to the all-gather."""
+        return np.arange(self.nz, dtype=np.int64), np.full(self.nz, self.nz, dtype=np.int32)
+
+    def gather_rows(self):
+        """Rows of the padded per-rank block of the gathered buffer ``[size][gather_rows][nz]``."""
+        return int(self.rows.max()) if self.size else 0
+
+    def gather_l_offsets(self):
+        """Complex offset of row (l, m=0) in the gathered buffer, for every l (``cora_b200_alm_slabs_to_panel``)."""
+        return np.ascontiguousarray((self.owner * self.gather_rows() + self.row0) * self.nz, dtype=np.int64)
+
 
 def _dist():
     import torch.distributed as dist
@@ -114,6 +128,23 @@ def exchange(send, plan, rank, group=None, out=None):
     dist.all_to_all_single(r_r, s_r, output_split_sizes=[2 * n for n in plan.recv_splits(rank)],
                            input_split_sizes=[2 * n for n in plan.send_splits(rank)], group=group)
     return recv
+
+
+def allgather_alm(slab, plan, rank, group=None):
+    """``alm_array.allgather()`` (``skysim.py:125``): every rank contributes its ``[rows_r][nz]`` slab (rows = the
+    (l, m <= l) of its l's), padded to ``plan.gather_rows()`` rows, and receives ``[size][gather_rows][nz]``.
+    ``slab``: complex128 tensor (CUDA under NCCL, CPU under gloo)."""
+    import torch
+
+    dist = _dist()
+    n = plan.gather_rows() * plan.nz
+    if plan.size == 1:
+        return slab
+    mine = torch.zeros(n, dtype=slab.dtype, device=slab.device)
+    mine[: slab.numel()] = slab.reshape(-1)
+    parts = [torch.empty(2 * n, dtype=torch.float64, device=slab.device) for _ in range(plan.size)]
+    dist.all_gather(parts, torch.view_as_real(mine).reshape(-1), group=group)
+    return torch.view_as_complex(torch.cat(parts).reshape(-1, 2))
 
 
 class ShardedSky(object):
@@ -272,6 +303,35 @@ class ShardedSky(object):
                   self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(self.row0), _lib.ptr(self.nu_base),
                   _lib.ptr(self.nu_width), _lib.ptr(send), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
         return send
+
+    def alm_gathered(self, cla, seed=0, gauss=None, roots=None):
+        """root + draw/apply for the local l's, then the all-gather over ranks: the whole
+        ``complex128[nz, 1, L, L]`` alm array on every rank (``mkfullsky(..., alms=True)``, ``skysim.py:123-125``),
+        as a CUDA tensor."""
+        t = _dev.torch()
+        L = self.lmax + 1
+        nalm = L * (L + 1) // 2
+        if self.size == 1:
+            panel = self.alm_local(cla, seed=seed, gauss=gauss, roots=roots)
+        else:
+            # one slab [rows_r][nz] instead of per-destination slabs: swap the slab tables for the call
+            base, width = self.plan.gather_tables()
+            keep = (self.nu_base, self.nu_width, self._buf.pop("send", None))
+            self.nu_base, self.nu_width = _dev.to_device(base, t.int64), _dev.to_device(width, t.int32)
+            try:
+                slab = self.alm_local(cla, seed=seed, gauss=gauss, roots=roots).clone() if self.nl else \
+                    _dev.empty((0,), t.complex128)
+            finally:
+                self.nu_base, self.nu_width = keep[0], keep[1]
+                self._buf.pop("send", None)
+                if keep[2] is not None:
+                    self._buf["send"] = keep[2]
+            allb = allgather_alm(slab, self.plan, self.rank, self.group)
+            panel = _dev.empty((nalm, self.nz), t.complex128)
+            loff = _dev.to_device(self.plan.gather_l_offsets(), t.int64)
+            _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(allb), _lib.ptr(loff), self.lmax, self.nz, _lib.ptr(panel),
+                      self.nz, 0, _lib.stream_ptr())
+        return hputil.panel_to_dense(panel, self.lmax, self.nz).reshape(self.nz, 1, L, L)
 
     def synthesize(self, recv, out=None):
         """received slabs -> PANEL -> maps of this rank's channels."""
@@ -533,12 +593,13 @@ def single_gpu_block(model, nside, frequencies, lmax, zromb, seed, chan_lo, chan
 
 
 def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, partition="interleaved", seed=0, gauss=None,
-                      roots=None, device_out=True):
+                      roots=None, device_out=True, alms=False):
     """``mkfullsky`` for an l-distributed ``corr`` (the MPIArray branch of ``skysim.py:97-134``).
 
     ``corr_local``: this rank's ``float64[nl_local, nz, nz]`` rows, for the l's of
     ``ShardPlan(lmax, nz, G, partition).l_lists[rank]``.  Returns this rank's channels
-    ``float64[cb, npix]`` (the reference returns the frequency-distributed ``MPIArray``)."""
+    ``float64[cb, npix]`` (the reference returns the frequency-distributed ``MPIArray``), or with ``alms`` the
+    all-gathered ``complex128[nz, 1, L, L]`` alm array (``skysim.py:123-125``: the same on every rank)."""
     t = _dev.torch()
     dist = _dist()
     size = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -551,12 +612,16 @@ def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, parti
         def _b200_fill_inputs(self, za, w):
             return None
 
-    sh = ShardedSky(_NoModel(), nside, np.zeros(nz), lmax=lmax, zromb=0, group=group, partition=partition, rank=rank, size=size)
+    sh = ShardedSky(_NoModel(), nside, np.zeros(nz), lmax=lmax, zromb=0, group=group, partition=partition, rank=rank, size=size,
+                    exchange="collective" if alms else "auto")     # the all-gather needs no peer buffers
     if l_list is not None and not np.array_equal(np.asarray(l_list), sh.l_list):
         raise Exception("l_list does not match the %s partition of rank %d" % (partition, rank))
     if corr_local.shape[0] != sh.nl:
         raise Exception("Correlation matrix is incorrect shape.")
     cla = _dev.to_device(corr_local, t.float64)
+    if alms:
+        out = sh.alm_gathered(cla, seed=seed, gauss=gauss, roots=roots)
+        return out if device_out else _dev.to_host(out)
     if sh.exchange == "p2p":
         sh.p2p_alm(0, seed=seed, gauss=gauss, roots=roots, cla=cla)
         sh.peers.barrier()
@@ -568,6 +633,51 @@ def mkfullsky_sharded(corr_local, nside, l_list=None, *, lmax, group=None, parti
         recv = exchange(send, sh.plan, rank, group)
         sky = sh.synthesize(recv)
     return sky if device_out else _dev.to_host(sky)
+
+
+def mkfullsky_mpi(corr, nside, alms=False, rng=None, seed=None, group=None):
+    """``skysim.mkfullsky`` for a distributed ``corr`` (``cora/core/skysim.py:97-134``; the caller is
+    ``cora/signal/lss.py:450``): ``corr`` exposes ``local_array`` (this rank's ``float64[nl_local, nz, nz]`` block of
+    l's, caput's contiguous split), ``global_shape`` and -- for this package's ``mpiarray.MPIArray`` -- ``comm``, the
+    ``torch.distributed`` group.  Returns what the reference returns: the maps as an array distributed over
+    frequency (``wrap(sky, axis=0)``), or with ``alms`` the all-gathered ``complex128[nz, 1, L, L]`` numpy array.
+
+    ``rng``: each rank draws ``complex_std_normal((nz, l + 1), rng)`` for its local l's in ascending order, exactly
+    as ``skysim.py:114-121`` does (the pipeline caller seeds every rank identically, SURVEY App. C.5: kept, because
+    it is the identical-draw parity path).  Without ``rng`` the draws are the device Philox stream keyed by
+    (l, m, nu): independent of the number of ranks."""
+    from . import mpiarray
+
+    if group is None:
+        group = getattr(corr, "comm", None)
+    dist = _dist()
+    if group is not None and not (dist.is_available() and isinstance(group, dist.ProcessGroup)):
+        group = None         # an mpi4py communicator cannot drive torch.distributed: use the default group
+    size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if size > 1 else 0
+    L = int(corr.global_shape[0])
+    loc = np.asarray(corr.local_array, dtype=np.float64)
+    nz = loc.shape[1]
+    if loc.ndim != 3 or loc.shape[2] != nz:
+        raise Exception("Correlation matrix is incorrect shape.")
+    lo, hi = block_partition(L, size, rank)
+    if loc.shape[0] != hi - lo:
+        raise Exception("Correlation matrix is incorrect shape.")
+    gauss = None
+    if rng is not None:
+        gauss = np.zeros((hi - lo, nz, L), dtype=np.complex128)
+        for i, l in enumerate(range(lo, hi)):
+            gauss[i, :, : l + 1] = nputil.complex_std_normal((nz, l + 1), rng=rng)
+    elif seed is None:
+        seed = int(np.random.randint(0, 2**31 - 1))
+    out = mkfullsky_sharded(loc, nside, lmax=L - 1, group=group, partition="block", seed=seed or 0, gauss=gauss,
+                            device_out=False, alms=alms)
+    if alms:
+        return out
+    wrap = getattr(type(corr), "wrap", None)
+    if wrap is not None and not isinstance(corr, mpiarray.MPIArray):
+        return wrap(out, axis=0)                 # caput's MPIArray.wrap(array, axis)
+    return mpiarray.MPIArray.wrap(out, axis=0, comm=group)
 
 
 class ShardedPolSky(object):

@@ -143,7 +143,9 @@ def mkfullsky(corr, nside, alms=False, rng=None, *, seed=None, roots=None, gauss
     Parameters
     ----------
     corr : np.ndarray or CUDA tensor (lmax+1, numz, numz)
-        The correlation matrix C_l(z, z').
+        The correlation matrix C_l(z, z').  A distributed array (``cora_b200.mpiarray.MPIArray`` or caput's,
+        split over l) takes the multi-GPU path and returns the maps distributed over frequency, as the
+        reference does (``skysim.py:97-103,128-134``).
     nside : integer
         The resolution of the Healpix maps.
     alms : boolean, optional
@@ -163,8 +165,11 @@ def mkfullsky(corr, nside, alms=False, rng=None, *, seed=None, roots=None, gauss
     hpmaps : np.ndarray (numz, npix)   -- or the alm array if ``alms``.
     """
     t = _dev.torch()
-    if hasattr(corr, "local_array"):
-        raise Exception("MPIArray input: use cora_b200.dist.mkfullsky_sharded for the multi-GPU path.")
+    if hasattr(corr, "local_array") and hasattr(corr, "global_shape"):
+        # distributed corr (caput MPIArray / cora_b200.mpiarray.MPIArray, split over l): skysim.py:97-134
+        from . import dist as _cdist
+
+        return _cdist.mkfullsky_mpi(corr, nside, alms=alms, rng=rng, seed=seed)
     numz = corr.shape[1]
     maxl = corr.shape[0] - 1
     if corr.shape[2] != numz:

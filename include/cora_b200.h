@@ -42,6 +42,9 @@ int cora_b200_timing_enable(int on);
 int cora_b200_timing_kinds(void);
 const char* cora_b200_timing_name(int id);
 int cora_b200_timing_read(double* ms_out_h, long long* launches_out_h, int n);
+/* Timeline of the recorded spans in launch order (family id, start relative to the first span, duration; ms).
+ * Returns MINUS the number of entries written (<= cap), or a positive error code.  Does not clear the record. */
+int cora_b200_timing_trace(int* id_out_h, double* start_ms_out_h, double* dur_ms_out_h, int cap);
 
 /* ------------------------------------------------------------------ alm layouts -- */
 /* PACKED: healpy order per channel, alm[chan * stride + idx(l,m)],
@@ -313,6 +316,18 @@ int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const in
                                int lmax, unsigned long long seed, int draw_counter0, const void* gauss,
                                long long gauss_ld, const void* nu_ptr, const int* nu_width, void* workspace,
                                long long ws_bytes, void* stream);
+
+/* ---- xi(r) -> C_l(chi, chi') front end --------------------------------------------------------
+ * replaces: legendre_array + the weighted Legendre contraction of corr_to_clarray
+ *           (cora/signal/corrfunc.py:265-287, :384-396).
+ * legendre_table: out[l * ld + i] = P_l(mu[i]) * scale[i] (scale may be null), l = 0..lmax, i < n, by the
+ * three-term recurrence scipy.special.lpn uses.  mu, scale, out: device pointers.
+ * dgemm: C[m x n] (+)= A[m x k] B[k x n], row-major FP64 on the tensor cores (DMMA.8x8x4); accumulate != 0 adds to C
+ * (corr_to_clarray feeds the Gauss-Legendre nodes chunk by chunk: np.dot(lm, corr_array), corrfunc.py:395).   */
+int cora_b200_legendre_table(const double* mu, const double* scale, int n, int lmax, double* out, long long ld,
+                             void* stream);
+int cora_b200_dgemm(const double* A, const double* B, double* C, int m, int n, int k, long long lda, long long ldb,
+                    long long ldc, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,16 @@ def install_shims():
         def wrap(cls, arr, axis):
             return arr.view(cls)
 
+        @property
+        def local_offset(self):
+            return (0,) * self.ndim
+
+        def reshape(self, *shape):        # caput allows None = "keep this (distributed) axis"
+            if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+                shape = tuple(shape[0])
+            shape = tuple(self.shape[i] if v is None else v for i, v in enumerate(shape))
+            return np.ndarray.reshape(self, shape)
+
     def zeros(shape, dtype=np.float64, axis=0):
         return np.zeros(shape, dtype=dtype).view(MPIArray)
 
@@ -95,6 +105,20 @@ def install_shims():
     caput.mpiarray = mpiarray
 
     healpy = types.ModuleType("healpy")  # import-only stub; alm2map is never called here
+
+    # corrfunc.py imports hankl / hankel / pyfftlog at module level (not used by corr_to_clarray) and takes
+    # cosine_rule from caput.astro.coordinates: import-only stubs + the oracle's restatement of cosine_rule
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import corrfunc as ocf
+
+    coords = types.ModuleType("caput.astro.coordinates")
+    sph = types.ModuleType("caput.astro.coordinates.spherical")
+    sph.cosine_rule = ocf.cosine_rule
+    coords.spherical = sph
+    astro.coordinates = coords
+    for name in ("hankl", "hankel", "pyfftlog"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules.update({"caput.astro.coordinates": coords, "caput.astro.coordinates.spherical": sph})
 
     sys.modules.update(
         {"caput": caput, "caput.astro": astro, "caput.astro.constants": const,
@@ -313,6 +337,37 @@ def extra_root_large():
     print("root_large.npz written:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+def corr_test_function(r):
+    """A smooth correlation function with a finite r -> 0 limit (stands in for the LSS xi(r) interpolators)."""
+    return np.exp(-((r / 60.0) ** 2)) / (1.0 + (r / 15.0) ** 2) + 0.05 * np.cos(r / 35.0) * np.exp(-r / 400.0)
+
+
+def extra_corr_to_clarray():
+    """``cora.signal.corrfunc.corr_to_clarray`` and ``legendre_array`` (the unmodified reference functions) on a
+    small radial grid, with and without the radial bin quadrature."""
+    build_reference()
+    install_shims()
+    import scipy.special as ss
+
+    if not hasattr(ss, "lpn"):
+        # the reference calls scipy.special.lpn (corrfunc.py:285), removed from this image's scipy (1.18):
+        # legendre_p_all is its replacement (same recurrence, same values)
+        ss.lpn = lambda n, z: (np.asarray(ss.legendre_p_all(n, z))[0], None)
+    from cora.signal import corrfunc
+
+    xarray = np.linspace(2900.0, 3400.0, 6)
+    lmax = 40
+    out = {"xarray": xarray, "lmax": lmax}
+    out["cl_romb2_q2"] = np.asarray(corrfunc.corr_to_clarray(corr_test_function, lmax, xarray, xromb=2, q=2, chunksize=16))
+    out["cl_romb0_q3"] = np.asarray(corrfunc.corr_to_clarray(corr_test_function, lmax, xarray, xromb=0, q=3, chunksize=50))
+    out["cl_romb1_w40"] = np.asarray(corrfunc.corr_to_clarray(corr_test_function, lmax, xarray, xromb=1, xwidth=40.0, q=2, chunksize=20))
+    mu = np.array([-0.99, -0.5, 0.0, 0.3, 0.77, 0.999])
+    out["leg_mu"] = mu
+    out["leg"] = corrfunc.legendre_array(60, mu)
+    np.savez(os.path.join(HERE, "corr_to_clarray.npz"), **out)
+    print("corr_to_clarray.npz written:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "all":
@@ -321,5 +376,7 @@ if __name__ == "__main__":
         extra_c2rows()
     elif what == "root_large":
         extra_root_large()
+    elif what == "corr_to_clarray":
+        extra_corr_to_clarray()
     else:
-        raise SystemExit("usage: make_golden.py [all|c2rows|root_large]")
+        raise SystemExit("usage: make_golden.py [all|c2rows|root_large|corr_to_clarray]")

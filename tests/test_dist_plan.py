@@ -124,3 +124,102 @@ def test_exchange_gloo_world2(partition):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# --------------------------------------------------------------------------- alms=True: the all-gather
+def _emulate_gather_slab(plan, r):
+    """What cora_b200_draw_apply_slabs writes on rank r with the gather tables: one slab [rows_r][nz]."""
+    base, width = plan.gather_tables()
+    slab = np.full(int(plan.rows[r]) * plan.nz, np.nan + 0j, dtype=np.complex128)
+    row0 = plan.send_row0(r)
+    for i, l in enumerate(plan.l_lists[r]):
+        for m in range(l + 1):
+            for nu in range(plan.nz):
+                slab[base[nu] + (row0[i] + m) * width[nu]] = _encode(int(l), m, nu)
+    return slab
+
+
+def _check_gathered(plan, allb):
+    off = plan.gather_l_offsets()
+    for l in range(plan.lmax + 1):
+        for m in range(l + 1):
+            row = allb[off[l] + m * plan.nz : off[l] + (m + 1) * plan.nz]
+            if not np.array_equal(row, _encode(l, m, np.arange(plan.nz))):
+                return False
+    return True
+
+
+@pytest.mark.parametrize("partition", ["interleaved", "block"])
+@pytest.mark.parametrize("size,lmax,nz", [(2, 7, 5), (3, 6, 4), (8, 10, 3)])
+def test_gather_tables_numpy(partition, size, lmax, nz):
+    from cora_b200 import dist as cdist
+
+    plan = cdist.ShardPlan(lmax, nz, size, partition)
+    n = plan.gather_rows() * nz
+    allb = np.zeros(size * n, dtype=np.complex128)
+    for r in range(size):
+        slab = _emulate_gather_slab(plan, r)
+        assert not np.isnan(slab).any()
+        allb[r * n : r * n + slab.size] = slab
+    assert _check_gathered(plan, allb)
+
+
+def _gloo_gather_worker(rank, size, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from cora_b200 import dist as cdist
+    from cora_b200 import mpiarray
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        ok = True
+        for partition in ("interleaved", "block"):
+            plan = cdist.ShardPlan(9, 5, size, partition)
+            allb = cdist.allgather_alm(torch.from_numpy(_emulate_gather_slab(plan, rank)), plan, rank).numpy()
+            ok &= _check_gathered(plan, allb)
+        # the MPIArray shim: wrap / allgather / redistribute against a global array every rank can build
+        glob = np.arange(7 * 3 * 5, dtype=np.float64).reshape(7, 3, 5) + 0.25
+        lo, hi = mpiarray.split_block(7, size, rank)
+        a = mpiarray.MPIArray.wrap(glob[lo:hi].copy(), axis=0)
+        ok &= a.global_shape == (7, 3, 5) and a.local_offset == (lo, 0, 0)
+        ok &= bool(np.array_equal(a.allgather(), glob))
+        b = a.redistribute(axis=2)
+        lo2, hi2 = mpiarray.split_block(5, size, rank)
+        ok &= b.axis == 2 and bool(np.array_equal(b.local_array, glob[:, :, lo2:hi2]))
+        ok &= bool(np.array_equal(b.redistribute(axis=0).local_array, glob[lo:hi]))
+        ok &= [g for _, g in a.enumerate(0)] == list(range(lo, hi))
+        z = mpiarray.zeros((7, 2), dtype=np.complex128, axis=0)
+        ok &= z.local_array.shape == (hi - lo, 2) and z.dtype == np.complex128
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_and_mpiarray_gloo_world2():
+    """alms=True all-gather (plan tables + torch.distributed.all_gather) and the MPIArray shim on a real
+    world_size-2 gloo group."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_mpiarray_single_rank():
+    from cora_b200 import mpiarray
+
+    a = mpiarray.MPIArray.wrap(np.arange(12.0).reshape(4, 3), axis=0)
+    assert a.global_shape == (4, 3) and a.local_shape == (4, 3) and mpiarray.is_distributed(a)
+    assert np.array_equal(a.allgather(), np.arange(12.0).reshape(4, 3))
+    assert a.redistribute(axis=1).axis == 1
+    assert not mpiarray.is_distributed(np.zeros(3))

@@ -85,6 +85,60 @@ def test_sharded_injected_draws_match_oracle():
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-10
 
 
+# --------------------------------------------------------------------------- alms=True (all-gather) and MPIArray input
+@pytest.mark.parametrize("size,partition", [(2, "interleaved"), (3, "block")])
+def test_alms_allgather_virtual_ranks(size, partition):
+    """mkfullsky(alms=True) over ranks (skysim.py:123-125): every rank's gather slab, padded and stacked the way
+    torch.distributed.all_gather delivers them, must unpack to the single-GPU alm array."""
+    import torch
+    from cora_b200 import _dev, _lib, galaxy, hputil, skysim
+    from cora_b200 import dist as cdist
+
+    nside, nz = 8, 5
+    lmax = 3 * nside - 1
+    L = lmax + 1
+    freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+    model = galaxy.FullSkySynchrotron()
+    cla = skysim.clarray(model.angular_powerspectrum, lmax, freq, device_out=True)
+    ref = skysim.mkfullsky(cla, nside, alms=True, seed=9)
+    assert ref.shape == (nz, 1, L, L)
+    plan = cdist.ShardPlan(lmax, nz, size, partition)
+    n = plan.gather_rows() * nz
+    allb = torch.zeros(size * n, dtype=torch.complex128, device="cuda")
+    base, width = plan.gather_tables()
+    for r in range(size):
+        sh = cdist.ShardedSky(model, nside, freq, lmax=lmax, rank=r, size=size, partition=partition, exchange="collective")
+        sh.nu_base, sh.nu_width = _dev.to_device(base, torch.int64), _dev.to_device(width, torch.int32)
+        slab = sh.alm_local(sh.fill(), seed=9)
+        allb[r * n : r * n + slab.numel()] = slab
+    panel = torch.empty((L * (L + 1) // 2, nz), dtype=torch.complex128, device="cuda")
+    loff = _dev.to_device(plan.gather_l_offsets(), torch.int64)
+    _lib.call("cora_b200_alm_slabs_to_panel", _lib.ptr(allb), _lib.ptr(loff), lmax, nz, _lib.ptr(panel), nz, 0, _lib.stream_ptr())
+    got = hputil.panel_to_dense(panel, lmax, nz).reshape(nz, 1, L, L).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_mkfullsky_accepts_distributed_corr_single_rank():
+    """The MPIArray branch of mkfullsky (skysim.py:97-103,128-134) with one rank: same draws from the same rng as
+    the dense call, maps come back wrapped and distributed over frequency; alms=True returns the full array."""
+    from cora_b200 import galaxy, mpiarray, skysim
+
+    nside, nz = 8, 4
+    lmax = 3 * nside - 1
+    freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+    cla = skysim.clarray(galaxy.FullSkySynchrotron().angular_powerspectrum, lmax, freq)
+    want = skysim.mkfullsky(cla, nside, rng=np.random.default_rng(11))
+    dcorr = mpiarray.MPIArray.wrap(cla, axis=0)
+    got = skysim.mkfullsky(dcorr, nside, rng=np.random.default_rng(11))
+    assert mpiarray.is_distributed(got) and got.axis == 0 and got.global_shape == want.shape
+    np.testing.assert_allclose(got.local_array, want, rtol=0, atol=1e-13 * np.abs(want).max())
+    alm_want = skysim.mkfullsky(cla, nside, alms=True, rng=np.random.default_rng(11))
+    alm_got = skysim.mkfullsky(dcorr, nside, alms=True, rng=np.random.default_rng(11))
+    np.testing.assert_allclose(alm_got, alm_want, rtol=0, atol=1e-13 * np.abs(alm_want).max())
+    with pytest.raises(Exception, match="incorrect shape"):
+        skysim.mkfullsky(mpiarray.MPIArray.wrap(np.zeros((lmax + 1, nz, nz + 1)), axis=0), nside)
+
+
 # --------------------------------------------------------------------------- fused exchange (p2p)
 def _run_virtual_p2p(model, nside, freq, lmax, size, partition, seed, zromb=3, steps=1):
     """Drive the multi-GPU p2p path with `size` virtual ranks on one GPU (cora_b200.peer.LocalPeers):
@@ -181,6 +235,18 @@ def _p2p_worker(rank, size, port, q):
             sky2 = sh2.step(seed=22)
             res[name] = (sky.cpu().numpy(), sky2.cpu().numpy())
             sh.peers.close()
+        # the reference's MPI call: l-distributed corr in, frequency-distributed maps out / all-gathered alms
+        from cora_b200 import mpiarray, skysim
+
+        nside, nz = 8, 6
+        lmax = 3 * nside - 1
+        freq = np.linspace(800.0, 400.0, nz, endpoint=False)
+        cla = skysim.clarray(galaxy.FullSkySynchrotron().angular_powerspectrum, lmax, freq)
+        lo, hi = mpiarray.split_block(lmax + 1, size, rank)
+        dcorr = mpiarray.MPIArray.wrap(cla[lo:hi].copy(), axis=0)
+        sky = skysim.mkfullsky(dcorr, nside, seed=77)
+        alm = skysim.mkfullsky(dcorr, nside, alms=True, seed=77)
+        res["mpi"] = (sky.allgather(), skysim.mkfullsky(cla, nside, seed=77), alm, skysim.mkfullsky(cla, nside, alms=True, seed=77))
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -213,6 +279,9 @@ def test_p2p_two_processes():
         for name in ("sck", "21cm"):
             a, b = got[r][name]
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-13 * np.abs(b).max())
+        sky, sky_ref, alm, alm_ref = got[r]["mpi"]
+        np.testing.assert_allclose(sky, sky_ref, rtol=0, atol=1e-13 * np.abs(sky_ref).max())
+        np.testing.assert_array_equal(alm, alm_ref)
 
 
 # --------------------------------------------------------------------------- polarised, block-sharded
