@@ -22,6 +22,29 @@ def cosine_rule(mu, x1, x2):
     return np.sqrt((a - b) ** 2 + 2.0 * a * b * (1.0 - mu))
 
 
+class TabulatedCorrelation(object):
+    """A correlation function given by samples: ``xi(r)`` piecewise linear in ``r`` (``kind="linear"``) or in
+    ``ln r`` (``kind="log"``), constant beyond both ends -- ``numpy.interp`` semantics.  Callable on the host like
+    any ``corr`` the reference takes; ``corr_to_clarray`` recognises it and evaluates cosine rule, interpolation and
+    the radial-bin quadrature in one CUDA kernel (``cora_b200_corr_bins``) instead of calling back to the host."""
+
+    def __init__(self, r, xi, kind="linear"):
+        if kind not in ("linear", "log"):
+            raise ValueError("kind must be 'linear' or 'log'")
+        self.kind = kind
+        r = np.asarray(r, dtype=np.float64)
+        self.knots = np.ascontiguousarray(np.log(r) if kind == "log" else r)
+        self.values = np.ascontiguousarray(xi, dtype=np.float64)
+        if self.knots.ndim != 1 or self.knots.shape != self.values.shape or self.knots.size < 2 or np.any(np.diff(self.knots) <= 0):
+            raise ValueError("r must be 1-D, increasing, and match xi")
+
+    def __call__(self, r):
+        r = np.asarray(r, dtype=np.float64)
+        with np.errstate(divide="ignore"):
+            x = np.log(r) if self.kind == "log" else r
+        return np.interp(x, self.knots, self.values)
+
+
 def legendre_array(lmax, mu, scale=None, device_out=False):
     """Legendre polynomials ``P_l(mu_i)`` up to ``lmax``: ``float64[lmax + 1, len(mu)]`` (``corrfunc.py:265-287``),
     optionally times ``scale[i]``; three-term recurrence on the GPU (``cora_b200_legendre_table``)."""
@@ -82,18 +105,30 @@ def corr_to_clarray(corr, lmax, xarray, xromb=3, xwidth=None, q=2, chunksize=50,
     lm = legendre_array(lmax, mu[clo:chi_], scale=(w * 4.0 * np.pi / wsum)[clo:chi_], device_out=True)
     out = _dev.zeros((L, xlen * xlen), t.float64)
     wd = _dev.to_device(np.ascontiguousarray(x_w), t.float64)
+    fused = type(corr) is TabulatedCorrelation       # (a subclass may override __call__: take the generic path)
+    if fused:
+        tr, tv = _dev.to_device(corr.knots, t.float64), _dev.to_device(corr.values, t.float64)
+        xad = _dev.to_device(np.ascontiguousarray(xa), t.float64)
+        mud = _dev.to_device(np.ascontiguousarray(mu[clo:chi_]), t.float64)
     first = True
     # (fewer local nodes than one chunk: np.array_split(..., 0) raises ValueError, as in the reference, corrfunc.py:367)
     for msec in np.array_split(np.arange(nloc), nloc // int(chunksize)):
-        rc = cosine_rule(mu[clo + msec], xa, xa)
-        corr1 = np.ascontiguousarray(np.broadcast_to(corr(rc), rc.shape), dtype=np.float64)
-        blk = _dev.to_device(corr1, t.float64)
         nm = len(msec)
-        if xromb > 0:
+        blk = None
+        if fused:
             red = _dev.empty((nm, xlen * xlen), t.float64)
-            _lib.call("cora_b200_cl_romberg_reduce", _lib.ptr(blk), _lib.ptr(wd), nm, xlen, xint, _lib.ptr(red), _lib.stream_ptr())
+            _lib.call("cora_b200_corr_bins", _lib.ptr_off(mud, 8 * int(msec[0])), nm, _lib.ptr(xad), _lib.ptr(wd), xlen, xint,
+                      _lib.ptr(tr), _lib.ptr(tv), int(corr.knots.size), 1 if corr.kind == "log" else 0, _lib.ptr(red),
+                      _lib.stream_ptr())
         else:
-            red = blk.reshape(nm, xlen * xlen)
+            rc = cosine_rule(mu[clo + msec], xa, xa)
+            corr1 = np.ascontiguousarray(np.broadcast_to(corr(rc), rc.shape), dtype=np.float64)
+            blk = _dev.to_device(corr1, t.float64)
+            if xromb > 0:
+                red = _dev.empty((nm, xlen * xlen), t.float64)
+                _lib.call("cora_b200_cl_romberg_reduce", _lib.ptr(blk), _lib.ptr(wd), nm, xlen, xint, _lib.ptr(red), _lib.stream_ptr())
+            else:
+                red = blk.reshape(nm, xlen * xlen)
         # out += lm[:, msec] @ red     (A = the chunk's columns of the weighted Legendre table, row pitch nloc)
         _lib.call("cora_b200_dgemm", _lib.ptr_off(lm, 8 * int(msec[0])), _lib.ptr(red), _lib.ptr(out), L, xlen * xlen, nm,
                   nloc, xlen * xlen, xlen * xlen, 0 if first else 1, _lib.stream_ptr())

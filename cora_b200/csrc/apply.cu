@@ -247,7 +247,7 @@ static int cached_descs(const std::vector<LDesc>& hd, LDesc** out) {
             *out = e.dd;
             return 0;
         }
-    if (g_desc_cache.size() >= 64) {   // evict the oldest (never one in flight: a sync precedes the free)
+    if (g_desc_cache.size() >= 512) {   // evict the oldest (never one in flight: a sync precedes the free)
         CB_CUDA(cudaDeviceSynchronize());
         cudaFree(g_desc_cache.front().dd);
         g_desc_cache.erase(g_desc_cache.begin());
@@ -333,7 +333,9 @@ static int draw_apply_impl(const double* root, const int* l_list_h, const int* d
         }
         count_launch();
         CB_LAUNCH_CHECK();
-        if (i1 < nl) CB_CUDA(cudaStreamSynchronize(st));   // workspace reuse
+        // the next batch's draws overwrite this batch's in the same workspace: safe without any host
+        // synchronisation, because the draw kernel is ordered behind this apply on the same stream and the
+        // descriptor tables are immutable, content-keyed device copies
         i0 = i1;
     }
     return 0;

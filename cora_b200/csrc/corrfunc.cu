@@ -30,6 +30,59 @@ __global__ void legendre_table_kernel(const double* __restrict__ mu, const doubl
     }
 }
 
+// Fused integrand for tabulated correlation functions (cora_b200.corrfunc.TabulatedCorrelation): one thread per
+// output (node i, bin a, bin b): cosine rule -> piecewise-linear xi(r) (numpy.interp semantics: clamped at both
+// ends) -> the two-sided radial quadrature, all in registers.  Replaces, for such functions, the host evaluation
+// `corr(cosine_rule(mu, xa, xa))` and the two matmuls of corrfunc.py:369-379.
+//   out[i][a][b] = sum_{p,q} w_p w_q xi( sqrt((x_ap - x_bq)^2 + 2 x_ap x_bq (1 - mu_i)) )
+// logx: the table abscissa is ln r (interpolation linear in ln r; r = 0 clamps to the first knot).
+__global__ void __launch_bounds__(256) corr_bins_kernel(const double* __restrict__ mu, int nmu, const double* __restrict__ xa,
+                                                        const double* __restrict__ xw, int nx, int xint,
+                                                        const double* __restrict__ tr, const double* __restrict__ tv, int nt,
+                                                        int logx, double* __restrict__ out) {
+    extern __shared__ double cb_smem[];   // [2 nt] knots, values (when they fit: nt <= 4096)
+    const bool tab_smem = nt <= 4096;
+    double* sr = cb_smem;
+    double* sv = sr + (tab_smem ? nt : 0);
+    if (tab_smem)
+        for (int k = threadIdx.x; k < nt; k += blockDim.x) { sr[k] = tr[k]; sv[k] = tv[k]; }
+    __syncthreads();
+    const double* R = tab_smem ? sr : tr;
+    const double* V = tab_smem ? sv : tv;
+    const long long n2 = (long long)nx * nx;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (e >= n2) return;
+    const int a = (int)(e / nx), b = (int)(e - (long long)a * nx);
+    const double om = 1.0 - mu[i];
+    double acc = 0.0;
+    for (int p = 0; p < xint; p++) {
+        const double xp = xa[a * xint + p];
+        double accq = 0.0;
+        for (int q = 0; q < xint; q++) {
+            const double xq = xa[b * xint + q];
+            const double d = xp - xq;
+            double r = sqrt(d * d + 2.0 * xp * xq * om);
+            if (logx) r = log(r);          // log(0) = -inf clamps to the first knot below
+            double v;
+            if (!(r > R[0])) v = V[0];
+            else if (r >= R[nt - 1]) v = V[nt - 1];
+            else {
+                int lo = 0, hi = nt - 1;   // R[lo] < r < R[hi]... invariant R[lo] <= r < R[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (R[mid] <= r) lo = mid; else hi = mid;
+                }
+                const double slope = (V[lo + 1] - V[lo]) / (R[lo + 1] - R[lo]);
+                v = slope * (r - R[lo]) + V[lo];
+            }
+            accq += xw[q] * v;
+        }
+        acc += xw[p] * accq;
+    }
+    out[(long long)i * n2 + e] = acc;
+}
+
 constexpr int GM_TM = 128, GM_TN = 64, GM_KC = 16, GM_ALD = 20, GM_BLD = 68, GM_STAGES = 3;
 constexpr int GM_STAGE_DOUBLES = GM_TM * GM_ALD + GM_KC * GM_BLD;
 
@@ -143,6 +196,20 @@ extern "C" int cora_b200_legendre_table(const double* mu, const double* scale, i
     cudaStream_t st = (cudaStream_t)stream;
     KTimer kt(K_TABLE, st);
     legendre_table_kernel<<<ceil_div(n, 128), 128, 0, st>>>(mu, scale, n, lmax, out, ld);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cora_b200_corr_bins(const double* mu, int nmu, const double* xa, const double* xw, int nx, int xint,
+                                   const double* tab_r, const double* tab_v, int nt, int logx, double* out, void* stream) {
+    CB_REQUIRE(mu && xa && xw && tab_r && tab_v && out && nmu >= 1 && nx >= 1 && xint >= 1 && nt >= 2, 1, "corr_bins: bad arguments");
+    CB_REQUIRE(nmu <= 65535, 3, "corr_bins: more than 65535 nodes per call");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (nt <= 4096) ? sizeof(double) * 2 * (size_t)nt : 0;
+    CB_CUDA(cudaFuncSetAttribute(corr_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    KTimer kt(K_CL_FILL, st);
+    corr_bins_kernel<<<dim3(ceil_div((long long)nx * nx, 256), nmu), 256, smem, st>>>(mu, nmu, xa, xw, nx, xint, tab_r, tab_v, nt, logx, out);
     count_launch();
     CB_LAUNCH_CHECK();
     return 0;

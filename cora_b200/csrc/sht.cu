@@ -49,6 +49,7 @@ struct ShtPlan {
     long long npix, nalm;
     double *d_cth, *d_sth;          // [nrn]
     double2* d_rc;                  // [nalm] recurrence coefficients, row idx(l, m) holds those of step l -> l+1
+    double* d_rc2;                  // [nalm][4] spin-2 coefficients of (l, m), built on first polarised use
     double* d_nm_mant;              // [lmax+1]   N_m = mant * 2^exp
     int* d_nm_exp;                  // [lmax+1]
     RingDesc* d_rings;              // [4*nside-1]
@@ -115,6 +116,27 @@ __global__ void recur_coef_kernel(double2* rc, int lmax) {
         }
     }
     rc[(long long)m * (2 * lmax + 1 - m) / 2 + l] = make_double2(a, r);
+}
+
+// spin-2 coefficients of (l, m) (the same expressions as sht_legendre_kernel<2>): with
+// tn = 2 / sqrt((l+2)(l+1) l (l-1)),  tg = tn sqrt((2l+1)/(2l-1) (l^2 - m^2)):
+//   X1 = -(c0 / sin^2 + c1) lam_l + c3 cos / sin^2 lam_{l-1},   X2 = -c2 cos / sin^2 lam_l + m c3 / sin^2 lam_{l-1}
+// c = (tn (l - m^2), tn l (l-1) / 2, tn m (l-1), tg); zero for l < 2.
+__global__ void spin2_coef_kernel(double* rc2, int lmax) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (l < m || l > lmax) return;
+    const double ll = (double)l, mm = (double)m;
+    double tn = 0.0, tg = 0.0;
+    if (l >= 2) {
+        tn = 2.0 / sqrt((ll + 2.0) * (ll + 1.0) * ll * (ll - 1.0));
+        tg = tn * sqrt((2.0 * ll + 1.0) / (2.0 * ll - 1.0) * (ll * ll - mm * mm));
+    }
+    double* o = rc2 + 4 * ((long long)m * (2 * lmax + 1 - m) / 2 + l);
+    o[0] = tn * (ll - mm * mm);
+    o[1] = 0.5 * tn * ll * (ll - 1.0);
+    o[2] = tn * mm * (ll - 1.0);
+    o[3] = tg;
 }
 
 __global__ void twiddle_kernel(double2* tw, int n) {
@@ -204,6 +226,7 @@ struct LegParams {
     const double* nm_mant;
     const int* nm_exp;
     const double2* rc;        // [nalm] recurrence coefficients (a_{l+1}, a_{l+1}/a_l) at idx(l, m)  (ws kernel)
+    const double* rc2;        // [nalm][4] spin-2 coefficients of (l, m): tn (l - m^2), tn l (l-1) / 2, tn m (l-1), tg  (ws kernel)
     int nside, lmax, nrn, nrb, ncb, Lpad, ncg;   // ncg = ceil(nb / 4) channel groups in F
 };
 
@@ -492,8 +515,11 @@ constexpr int RT = 32 * NVP;     // rings per work item
 constexpr int NCOL = 64;         // real columns per work item (32 channels)
 constexpr int GPC = 4;           // 8-l groups per B chunk
 constexpr int KC = 8 * GPC;      // l's per B chunk
-constexpr int NSB = 4, NSA = 3;   // B ring / A ring depth, both in chunks of GPC groups
-constexpr int ALD = 36;          // A tile [8][36]
+constexpr int NSB = 4;           // B ring depth in chunks of GPC groups
+// A ring depth: 3 chunks for the scalar transform; 2 for spin 2, whose A tiles hold X1 and X2 (16 rows per
+// 8-l group, 147 KB for two stages)
+template <int SPIN> struct Cfg { static constexpr int NSA = SPIN ? 2 : 3; static constexpr int AROWS = SPIN ? 16 : 8; };
+constexpr int ALD = 36;          // A tile [AROWS][36]
 // B tile of one chunk: NCOL/16 column blocks of [KC rows][16 doubles = 128 B], each written by one
 // 2-D TMA box with the 128-byte swizzle (16-byte unit u of row r lands at unit u ^ (r & 7)), which
 // makes the DMMA fragment reads below conflict-free without padding.
@@ -553,15 +579,28 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
                  : "memory");
 }
 
+// SPIN = 0: scalar synthesis, a work item = (m, 128 rings, 32 channels).
+// SPIN = 2: (E, B) -> (Q, U), a work item = (m, 128 rings, 16 channels).  The producers emit the HEALPix X1 / X2
+//   functions from lambda_l, lambda_{l-1} and four per-(l, m) coefficients that arrive with the
+//   chunk; the 64 GEMM columns of an item are, per consumer half h (8 channels): [Q of 4 channels | Q of the next 4 |
+//   U of 4 | U of the next 4], each channel a (re, im) pair.  Q = -(X1 aE + i X2 aB), U = -(X1 aB - i X2 aE): the X1
+//   product reads the E tile for the Q blocks and the B tile for the U blocks; the X2 product reads the OTHER tile with
+//   re <-> im swapped inside the channel's 16-byte unit and a sign, and -- X2 having the opposite theta parity --
+//   feeds the other parity accumulator.  Both alm panels arrive through their own tensor map (blocks 0,1 = E tile,
+//   2,3 = B tile of the B stage).
+template <int SPIN>
 __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegParams P, int nitems,
-                                                                           const __grid_constant__ CUtensorMap tmapB) {
+                                                                           const __grid_constant__ CUtensorMap tmapB,
+                                                                           const __grid_constant__ CUtensorMap tmapB2) {
     using namespace lws;
+    constexpr int NSA = Cfg<SPIN>::NSA, AROWS = Cfg<SPIN>::AROWS;
     extern __shared__ __align__(16) double smem[];
     // the 128-byte swizzle pattern repeats every 1024 bytes of shared-memory address: align the B ring explicitly
     double* Bs = (double*)((char*)smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u));   // [NSB][NCOL/16][KC][16]
     double2* Cs = (double2*)(Bs + NSB * BSTAGE);                    // [NSB][KC] recurrence coefficients of the chunk
-    double* As = (double*)(Cs + NSB * KC);                          // [NVP][NSA][GPC][8][ALD]
-    unsigned* balA = (unsigned*)(As + NVP * NSA * GPC * 8 * ALD);   // [NVP][NSA][GPC] live-lane ballots
+    double* Cs2 = (double*)(Cs + NSB * KC);                         // [NSB][KC][4] spin-2 coefficients of the chunk
+    double* As = Cs2 + (SPIN ? NSB * KC * 4 : 0);                   // [NVP][NSA][GPC][AROWS][ALD]
+    unsigned* balA = (unsigned*)(As + NVP * NSA * GPC * AROWS * ALD);   // [NVP][NSA][GPC] live-lane ballots
     unsigned long long* bars = (unsigned long long*)(balA + NVP * NSA * GPC);
     unsigned long long* fullA = bars;                               // [NPROD][NSA]
     unsigned long long* emptyA = fullA + NPROD * NSA;               // [NPROD][NSA]
@@ -607,14 +646,30 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
             const int nrows = min(KC, bnk - b_c * KC);
             // coefficient rows past lmax: zeros (the alm rows there are finite -- they belong to the next m or
             // are zero-filled by the TMA unit beyond the tensor -- and meet lambda = 0)
-            if (lane >= nrows) Cs[sb * KC + lane] = make_double2(0.0, 0.0);
+            if (lane >= nrows) {
+                Cs[sb * KC + lane] = make_double2(0.0, 0.0);
+                if (SPIN) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) Cs2[(sb * KC + lane) * 4 + q] = 0.0;
+                }
+            }
             if (lane == 0) {
                 double* dst = Bs + (size_t)sb * BSTAGE;
                 const int row = (int)(brow0 + (long long)b_c * KC);
+                if (SPIN == 0) {
 #pragma unroll
-                for (int jb = 0; jb < NCOL / 16; jb++) tma_load_2d(dst + jb * BBLK, &tmapB, bcb * NCOL + 16 * jb, row, fullB + sb);
+                    for (int jb = 0; jb < NCOL / 16; jb++) tma_load_2d(dst + jb * BBLK, &tmapB, bcb * NCOL + 16 * jb, row, fullB + sb);
+                } else {
+                    // 16 channels = 32 doubles of each panel row: two boxes per panel
+#pragma unroll
+                    for (int jb = 0; jb < 2; jb++) {
+                        tma_load_2d(dst + jb * BBLK, &tmapB, bcb * (NCOL / 2) + 16 * jb, row, fullB + sb);
+                        tma_load_2d(dst + (2 + jb) * BBLK, &tmapB2, bcb * (NCOL / 2) + 16 * jb, row, fullB + sb);
+                    }
+                }
                 bulk_g2s(Cs + sb * KC, P.rc + brow0 + (long long)b_c * KC, (unsigned)nrows * 16u, fullB + sb);
-                mbar_arrive_expect_tx(fullB + sb, (unsigned)(BSTAGE * 8) + (unsigned)nrows * 16u);
+                if (SPIN) bulk_g2s(Cs2 + sb * KC * 4, P.rc2 + 4 * (brow0 + (long long)b_c * KC), (unsigned)nrows * 32u, fullB + sb);
+                mbar_arrive_expect_tx(fullB + sb, (unsigned)(BSTAGE * 8) + (unsigned)nrows * (SPIN ? 48u : 16u));
             } else {
                 mbar_arrive(fullB + sb);
             }
@@ -628,16 +683,18 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
             // RPL rings per lane (independent recurrence chains -> the FP64 latency overlaps): ring group
             // v = p * RPL + u; inside a group the lane owns octet (lane/8)*NVP + v of the item's octets
             double x[RPL], p_cur[RPL], p_prev[RPL];
+            double is2[RPL], cs2[RPL];   // spin 2: 1/sin^2, cos/sin^2
             int e[RPL];
 #pragma unroll
             for (int u = 0; u < RPL; u++) {
                 const int v = p * RPL + u;
                 const int rn = rb * RT + (((lane >> 3) * NVP + v) << 3) + (lane & 7);
-                x[u] = 0.0; p_cur[u] = 0.0; p_prev[u] = 0.0;
+                x[u] = 0.0; p_cur[u] = 0.0; p_prev[u] = 0.0; is2[u] = 0.0; cs2[u] = 0.0;
                 e[u] = -(1 << 20);
                 if (rn < P.nrn) {
                     x[u] = P.cth[rn];
                     double bm = P.sth[rn];
+                    if (SPIN) { is2[u] = 1.0 / (bm * bm); cs2[u] = x[u] * is2[u]; }
                     long long be = 0;
                     norm_frexp(bm, be);
                     double rm = 1.0;
@@ -657,6 +714,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                     p_cur[u] = ldexp(rm, (int)(re - (long long)e[u]));
                 }
             }
+            const double mm = (double)m;
             const int nchunk = (ngroups + GPC - 1) / GPC;
             for (int c = 0; c < nchunk; c++, cglob++) {
                 const int sa = cglob % NSA, sbc = cglob % NSB;
@@ -677,7 +735,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
 #pragma unroll
                     for (int u = 0; u < RPL; u++) {
                         live[u] = (e[u] == 0);
-                        Ab[u] = As + ((size_t)((p * RPL + u) * NSA + sa) * GPC + grp) * 8 * ALD;
+                        Ab[u] = As + ((size_t)((p * RPL + u) * NSA + sa) * GPC + grp) * AROWS * ALD;
                     }
                     double2 cf[8];
 #pragma unroll
@@ -685,9 +743,21 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int arow = (j & 1) * 4 + (j >> 1);
+                        double sa1 = 0.0, sb1 = 0.0, sd1 = 0.0, sg1 = 0.0;
+                        if (SPIN) {
+                            const double* q4 = Cs2 + (size_t)(sbc * KC + grp * 8 + j) * 4;
+                            sa1 = q4[0]; sb1 = q4[1]; sd1 = q4[2]; sg1 = q4[3];
+                        }
 #pragma unroll
                         for (int u = 0; u < RPL; u++) {
-                            Ab[u][arow * ALD + lane] = live[u] ? p_cur[u] : 0.0;
+                            if (SPIN == 0) {
+                                Ab[u][arow * ALD + lane] = live[u] ? p_cur[u] : 0.0;
+                            } else {
+                                const double x1 = -(sa1 * is2[u] + sb1) * p_cur[u] + sg1 * cs2[u] * p_prev[u];
+                                const double x2 = -sd1 * cs2[u] * p_cur[u] + mm * sg1 * is2[u] * p_prev[u];
+                                Ab[u][arow * ALD + lane] = live[u] ? x1 : 0.0;
+                                Ab[u][(8 + arow) * ALD + lane] = live[u] ? x2 : 0.0;
+                            }
                             const double pn = fma(cf[j].x * x[u], p_cur[u], -cf[j].y * p_prev[u]);
                             p_prev[u] = p_cur[u];
                             p_cur[u] = pn;
@@ -717,7 +787,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
         const int v = warp >> 1, h = warp & 1;     // ring group, column half
         const int p = v / RPL;                       // the producer warp that feeds this ring group
         const int g = lane >> 2, t = lane & 3;
-        const double* Ap = As + (size_t)v * NSA * GPC * 8 * ALD;
+        const double* Ap = As + (size_t)v * NSA * GPC * AROWS * ALD;
         const int L = lmax + 1;
         const int nring_tot = 4 * P.nside - 1;
         unsigned cglob = 0;
@@ -745,7 +815,7 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                 for (int grp = 0; grp < ng; grp++) {
                     const unsigned bal = balA[(v * NSA + sa) * GPC + grp];
                     if (!bal) continue;
-                    const double* Ac = Ap + (sa * GPC + grp) * 8 * ALD;
+                    const double* Ac = Ap + (sa * GPC + grp) * AROWS * ALD;
                     const double* Bb = Bs + (size_t)sb * BSTAGE;
                     int pm[4];
 #pragma unroll
@@ -757,10 +827,12 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                         for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(par * 4 + t) * ALD + 8 * mb + g];
 #pragma unroll
                         for (int nb = 0; nb < 4; nb++) {
-                            // column 32h + 8nb + g of row r: block 2h + nb/2, 16-byte unit 4(nb&1) + g/2, swizzled
+                            // scalar: column 32h + 8nb + g of row r: block 2h + nb/2, 16-byte unit 4(nb&1) + g/2, swizzled
+                            // spin 2: blocks 0,1 = E tile, 2,3 = B tile; Q columns (nb < 2) read E, U columns read B
                             const int r = grp * 8 + 2 * t + par;
                             const int unit = (4 * (nb & 1) + (g >> 1)) ^ (r & 7);
-                            bf[par][nb] = Bb[(2 * h + (nb >> 1)) * BBLK + r * 16 + unit * 2 + (g & 1)];
+                            const int blk = SPIN ? (2 * (nb >> 1) + h) : (2 * h + (nb >> 1));
+                            bf[par][nb] = Bb[blk * BBLK + r * 16 + unit * 2 + (g & 1)];
                         }
                     }
 #pragma unroll
@@ -770,6 +842,31 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
 #pragma unroll
                             for (int nb = 0; nb < 4; nb++)
                                 dmma884_p(acc[par][mb][nb][0], acc[par][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
+                    if (SPIN) {
+                        // X2 rows of l-parity `par` have theta-parity 1 - par.  Q columns: (-aB_im, +aB_re) from the B tile,
+                        // U columns: (+aE_im, -aE_re) from the E tile -- the channel's other component, signed
+#pragma unroll
+                        for (int par = 0; par < 2; par++) {
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(8 + par * 4 + t) * ALD + 8 * mb + g];
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++) {
+                                const int r = grp * 8 + 2 * t + par;
+                                const int unit = (4 * (nb & 1) + (g >> 1)) ^ (r & 7);
+                                const int blk = 2 * (1 - (nb >> 1)) + h;
+                                const double vsw = Bb[blk * BBLK + r * 16 + unit * 2 + ((g & 1) ^ 1)];
+                                const bool neg = (nb < 2) ? ((g & 1) == 0) : ((g & 1) == 1);
+                                bf[par][nb] = neg ? -vsw : vsw;
+                            }
+                        }
+#pragma unroll
+                        for (int par = 0; par < 2; par++)
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                                for (int nb = 0; nb < 4; nb++)
+                                    dmma884_p(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -785,13 +882,22 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                 const int r_s = nring_tot - 1 - rr;                      // mirror ring
 #pragma unroll
                 for (int nb = 0; nb < 4; nb++) {
-                    const int ch = cb * (NCOL / 2) + 16 * h + 4 * nb + t;
-                    if (ch >= P.nb) continue;
                     const double er = acc[0][mb][nb][0], ei = acc[0][mb][nb][1];
                     const double orr = acc[1][mb][nb][0], oi = acc[1][mb][nb][1];
-                    const int cg = ch >> 2, cq = ch & 3;
-                    P.F[(((long long)rr * P.ncg + cg) * L + m) * 4 + cq] = make_double2(er + orr, ei + oi);
-                    if (r_s != rr) P.F[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cq] = make_double2(er - orr, ei - oi);
+                    if (SPIN == 0) {
+                        const int ch = cb * (NCOL / 2) + 16 * h + 4 * nb + t;
+                        if (ch >= P.nb) continue;
+                        const int cg = ch >> 2, cq = ch & 3;
+                        P.F[(((long long)rr * P.ncg + cg) * L + m) * 4 + cq] = make_double2(er + orr, ei + oi);
+                        if (r_s != rr) P.F[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cq] = make_double2(er - orr, ei - oi);
+                    } else {
+                        const int ch = cb * (NCOL / 4) + 8 * h + 4 * (nb & 1) + t;
+                        if (ch >= P.nb) continue;
+                        double2* Fo = (nb >> 1) ? P.F2 : P.F;             // column blocks 0,1: Q; 2,3: U
+                        const int cg = ch >> 2, cq = ch & 3;
+                        Fo[(((long long)rr * P.ncg + cg) * L + m) * 4 + cq] = make_double2(-(er + orr), -(ei + oi));
+                        if (r_s != rr) Fo[(((long long)r_s * P.ncg + cg) * L + m) * 4 + cq] = make_double2(-(er - orr), -(ei - oi));
+                    }
                 }
             }
         }
@@ -1892,6 +1998,7 @@ extern "C" int cora_b200_sht_plan_destroy(void* plan) {
     if (!plan) return 0;
     ShtPlan* pl = (ShtPlan*)plan;
     cudaFree(pl->d_rc);
+    if (pl->d_rc2) cudaFree(pl->d_rc2);
     cudaFree(pl->d_cth); cudaFree(pl->d_sth); cudaFree(pl->d_nm_mant); cudaFree(pl->d_nm_exp);
     cudaFree(pl->d_rings); cudaFree(pl->d_tw); cudaFree(pl->d_chirp); cudaFree(pl->d_shph); cudaFree(pl->d_bhat);
     cudaFree(pl->d_chirp_off); cudaFree(pl->d_bhat_off);
@@ -1914,61 +2021,82 @@ extern "C" long long cora_b200_alm2map_workspace_bytes(void* plan, int layout, i
     return ws_per_chan((ShtPlan*)plan, layout) * round4(nchan_batch) + 256;
 }
 
-// 1: warp-specialised scalar Legendre kernel (default); 0: the single-role kernel.  Switchable
-// (CORA_B200_LEGENDRE_WS=0) so the two can be compared on the device.
-static int g_legendre_ws = [] { const char* e = getenv("CORA_B200_LEGENDRE_WS"); return (e && e[0] == '0') ? 0 : 1; }();
+// Bit 0: warp-specialised scalar Legendre kernel, bit 1: warp-specialised spin-2 kernel (default 3: both); cleared bits
+// fall back to the single-role kernel.  Switchable (CORA_B200_LEGENDRE_WS=0|1|2|3) so the kernels can be compared on
+// the device.
+static int g_legendre_ws = [] { const char* e = getenv("CORA_B200_LEGENDRE_WS"); return (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 3; }();
+
+extern "C" int cora_b200_set_legendre_ws(int mask) {
+    const int old = g_legendre_ws;
+    if (mask >= 0) g_legendre_ws = mask & 3;
+    return old;
+}
+
+// tensor map over a batch's alm panel columns: [nalm rows][2 nb doubles], row pitch = panel stride; columns past
+// the batch are out of bounds -> zero-filled by the TMA unit
+static int make_alm_tmap(CUtensorMap* tmap, const double2* base, int nb, long long nalm, long long alm_stride) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        CB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, 5, "alm2map: cuTensorMapEncodeTiled is not available");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)nb * 2, (cuuint64_t)nalm};
+    const cuuint64_t gstr[1] = {(cuuint64_t)alm_stride * 16};
+    const cuuint32_t box[2] = {16, (cuuint32_t)lws::KC};
+    const cuuint32_t estr[2] = {1, 1};
+    CB_REQUIRE(((uintptr_t)base % 16) == 0, 5, "alm2map: alm panel must be 16-byte aligned");
+    CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CB_REQUIRE(cr == CUDA_SUCCESS, 5, "alm2map: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return 0;
+}
 
 template <int SPIN>
-static int run_legendre(const ShtPlan* pl, const double2* almT, const double2* almB, long long alm_stride, int chan0, int nb,
+static int run_legendre(ShtPlan* pl, const double2* almT, const double2* almB, long long alm_stride, int chan0, int nb,
                         double2* F, double2* F2, cudaStream_t st) {
     LegParams P;
     P.almT = almT; P.almB = almB; P.alm_stride = alm_stride; P.chan0 = chan0; P.nb = nb; P.F = F; P.F2 = F2;
     P.cth = pl->d_cth; P.sth = pl->d_sth; P.nm_mant = pl->d_nm_mant; P.nm_exp = pl->d_nm_exp; P.rc = pl->d_rc;
+    P.rc2 = nullptr;
     P.nside = pl->nside; P.lmax = pl->lmax; P.nrn = pl->nrn;
     P.nrb = ceil_div(pl->nrn, LEG_RT);
     P.ncb = ceil_div(nb, SPIN ? LEG_NCH / 2 : LEG_NCH);
     P.ncg = ceil_div(nb, 4);
     P.Lpad = ((pl->lmax + 1 + 7) / 8 + 2) * 8 + 8;   // recur8 runs one group past the end
-    if (SPIN == 0 && g_legendre_ws) {
+    if (g_legendre_ws & (SPIN ? 2 : 1)) {
         using namespace lws;
+        constexpr int NSA = Cfg<SPIN>::NSA, AROWS = Cfg<SPIN>::AROWS;
         P.nrb = ceil_div(pl->nrn, RT);
-        P.ncb = ceil_div(nb, NCOL / 2);
-        size_t smem = 16 * (size_t)NSB * KC + 8 * ((size_t)NSB * BSTAGE + (size_t)NVP * NSA * GPC * 8 * ALD) +
-                      4 * NVP * NSA * GPC + 8 * (2 * NPROD * NSA + 2 * NSB) + 1024;
-        // tensor map over this batch's alm panel columns: [nalm rows][2 nb doubles], row pitch = panel stride;
-        // columns past the batch are out of bounds -> zero-filled by the TMA unit
-        CUtensorMap tmap;
-        {
-            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-            static EncodeFn encode = nullptr;
-            if (!encode) {
-                void* fn = nullptr;
-                cudaDriverEntryPointQueryResult qres;
-                CB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-                CB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, 5, "alm2map: cuTensorMapEncodeTiled is not available");
-                encode = (EncodeFn)fn;
-            }
-            const cuuint64_t gdim[2] = {(cuuint64_t)nb * 2, (cuuint64_t)pl->nalm};
-            const cuuint64_t gstr[1] = {(cuuint64_t)alm_stride * 16};
-            const cuuint32_t box[2] = {16, (cuuint32_t)KC};
-            const cuuint32_t estr[2] = {1, 1};
-            CB_REQUIRE(alm_stride % 1 == 0 && ((uintptr_t)(almT + chan0) % 16) == 0, 5, "alm2map: alm panel must be 16-byte aligned");
-            CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)(almT + chan0), gdim, gstr, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            CB_REQUIRE(cr == CUDA_SUCCESS, 5, "alm2map: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        P.ncb = ceil_div(nb, SPIN ? NCOL / 4 : NCOL / 2);
+        if (SPIN && !pl->d_rc2) {
+            CB_CUDA(cudaMalloc(&pl->d_rc2, sizeof(double) * 4 * pl->nalm));
+            spin2_coef_kernel<<<dim3(ceil_div(pl->lmax + 1, 128), pl->lmax + 1), 128, 0, st>>>(pl->d_rc2, pl->lmax);
+            count_launch();
+            CB_LAUNCH_CHECK();
         }
-        CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: lmax %d needs %zu B of shared memory (> 227 KB)", pl->lmax, smem);
-        CB_CUDA(cudaFuncSetAttribute(sht_legendre_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        P.rc2 = pl->d_rc2;
+        size_t smem = 16 * (size_t)NSB * KC + (SPIN ? 32 * (size_t)NSB * KC : 0) +
+                      8 * ((size_t)NSB * BSTAGE + (size_t)NVP * NSA * GPC * AROWS * ALD) +
+                      4 * NVP * NSA * GPC + 8 * (2 * NPROD * NSA + 2 * NSB) + 1024;
+        CUtensorMap tmap, tmap2;
+        if (int rc = make_alm_tmap(&tmap, almT + chan0, nb, pl->nalm, alm_stride)) return rc;
+        if (int rc = make_alm_tmap(&tmap2, (SPIN ? almB : almT) + chan0, nb, pl->nalm, alm_stride)) return rc;
+        CB_REQUIRE(smem <= 227 * 1024, 3, "alm2map: the Legendre stage needs %zu B of shared memory (> 227 KB)", smem);
+        CB_CUDA(cudaFuncSetAttribute(sht_legendre_ws_kernel<SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long nitems = (long long)(pl->lmax + 1) * P.nrb * P.ncb;
         CB_REQUIRE(nitems < 2147483647LL, 3, "alm2map: too many Legendre work items (%lld)", nitems);
         int dev, nsm;
         CB_CUDA(cudaGetDevice(&dev));
         CB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         const unsigned grid = (unsigned)std::min<long long>(nitems, nsm);   // persistent: one CTA per SM
-        { KTimer kt(K_LEGENDRE, st); sht_legendre_ws_kernel<<<grid, THREADS, smem, st>>>(P, (int)nitems, tmap); }
+        { KTimer kt(K_LEGENDRE, st); sht_legendre_ws_kernel<SPIN><<<grid, THREADS, smem, st>>>(P, (int)nitems, tmap, tmap2); }
         count_launch();
         CB_LAUNCH_CHECK();
         return 0;

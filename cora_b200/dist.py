@@ -130,6 +130,20 @@ def exchange(send, plan, rank, group=None, out=None):
     return recv
 
 
+DRAW_WS_BYTES = int(os.environ.get("CORA_B200_DRAW_WS_MB", "2048")) << 20
+
+
+def draw_workspace_bytes(nz, lmax_loc, nl):
+    """Workspace of the draw + apply stage: the Philox draws of a BATCH of l's, regenerated batch after batch in the
+    same buffer (stream order is the only synchronisation).  Bounded (default 2 GB, ``CORA_B200_DRAW_WS_MB``) instead
+    of holding every local l's draws (19 GB per GPU at nside 1024 x 2048 channels): a batch only has to be large
+    enough that its apply launch fills the GPU for many waves."""
+    lib = _lib.load()
+    full = lib.cora_b200_draw_apply_workspace_bytes(nz, lmax_loc, nl)
+    one = lib.cora_b200_draw_apply_workspace_bytes(nz, lmax_loc, 1)
+    return int(min(full, max(one, min(DRAW_WS_BYTES, _dev.free_bytes() - (4 << 30)))))
+
+
 def allgather_alm(slab, plan, rank, group=None):
     """``alm_array.allgather()`` (``skysim.py:125``): every rank contributes its ``[rows_r][nz]`` slab (rows = the
     (l, m <= l) of its l's), padded to ``plan.gather_rows()`` rows, and receives ``[size][gather_rows][nz]``.
@@ -279,9 +293,7 @@ class ShardedSky(object):
         gptr, gld = self._draw_take(seed) if gauss is None else (None, 0)
         if gauss is None and gptr is None:
             def mk():
-                full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
-                one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
-                return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
+                return _dev.workspace(draw_workspace_bytes(self.nz, lmax_loc, self.nl))
 
             ws = self._persistent("draw_ws", mk)
         elif gauss is None:
@@ -442,9 +454,7 @@ class ShardedSky(object):
         gptr, gld = self._draw_take(seed) if gauss is None else (None, 0)
         if gauss is None and gptr is None:
             def mk():
-                full = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, self.nl)
-                one = lib.cora_b200_draw_apply_workspace_bytes(self.nz, lmax_loc, 1)
-                return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
+                return _dev.workspace(draw_workspace_bytes(self.nz, lmax_loc, self.nl))
 
             ws = self._persistent("draw_ws", mk)
         elif gauss is None:
@@ -791,9 +801,7 @@ class ShardedPolSky(object):
         lmax_loc = int(self.l_list.max())
 
         def mk():
-            full = lib.cora_b200_draw_apply_workspace_bytes(nz, lmax_loc, nl)
-            one = lib.cora_b200_draw_apply_workspace_bytes(nz, lmax_loc, 1)
-            return _dev.workspace(min(full, max(one, _dev.free_bytes() - (4 << 30))))
+            return _dev.workspace(draw_workspace_bytes(nz, lmax_loc, nl))
 
         ws = self._persistent("draw_ws", mk)
         tabs = self._nu_ptr(k)

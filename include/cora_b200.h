@@ -317,6 +317,11 @@ int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const in
                                long long gauss_ld, const void* nu_ptr, const int* nu_width, void* workspace,
                                long long ws_bytes, void* stream);
 
+/* Which Legendre kernels the inverse SHT launches: bit 0 = warp-specialised scalar kernel, bit 1 = warp-specialised
+ * spin-2 kernel (default 3, or the CORA_B200_LEGENDRE_WS environment variable at load); cleared bits select the
+ * single-role kernel.  Returns the previous mask; mask < 0 only queries.  (A/B measurements and tests.)          */
+int cora_b200_set_legendre_ws(int mask);
+
 /* ---- xi(r) -> C_l(chi, chi') front end --------------------------------------------------------
  * replaces: legendre_array + the weighted Legendre contraction of corr_to_clarray
  *           (cora/signal/corrfunc.py:265-287, :384-396).
@@ -324,6 +329,12 @@ int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const in
  * three-term recurrence scipy.special.lpn uses.  mu, scale, out: device pointers.
  * dgemm: C[m x n] (+)= A[m x k] B[k x n], row-major FP64 on the tensor cores (DMMA.8x8x4); accumulate != 0 adds to C
  * (corr_to_clarray feeds the Gauss-Legendre nodes chunk by chunk: np.dot(lm, corr_array), corrfunc.py:395).   */
+/* corr_bins: the bin-averaged integrand for a TABULATED correlation function (piecewise linear in r, or in ln r when
+ * logx != 0; clamped at both ends like numpy.interp), fused with the cosine rule and the two-sided radial quadrature:
+ * out[i][a][b] = sum_{p,q} xw[p] xw[q] xi(|x_ap - x_bq| at angle mu_i), xa[nx * xint] the radial samples, i < nmu
+ * (corrfunc.py:369-379 for callables of that form).  All pointers are device pointers.                          */
+int cora_b200_corr_bins(const double* mu, int nmu, const double* xa, const double* xw, int nx, int xint,
+                        const double* tab_r, const double* tab_v, int nt, int logx, double* out, void* stream);
 int cora_b200_legendre_table(const double* mu, const double* scale, int n, int lmax, double* out, long long ld,
                              void* stream);
 int cora_b200_dgemm(const double* A, const double* B, double* C, int m, int n, int k, long long lda, long long ldb,

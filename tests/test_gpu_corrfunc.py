@@ -75,3 +75,27 @@ def test_corr_to_clarray_feeds_mkfullsky():
     assert sky.shape == (5, 12 * nside**2) and np.isfinite(sky).all()
     with pytest.raises(ValueError):     # fewer nodes than one chunk: the reference dies in np.array_split(..., 0)
         corrfunc.corr_to_clarray(corr_test_function, 8, x, xromb=0, q=2, chunksize=50)
+
+
+@pytest.mark.parametrize("kind", ["linear", "log"])
+def test_tabulated_correlation_fused_path_vs_oracle(kind):
+    """A tabulated xi(r) takes the fused kernel (cosine rule + interpolation + radial quadrature on the GPU); the
+    oracle evaluates the same object as a plain host callable."""
+    from cora_b200 import corrfunc
+
+    r = np.concatenate([[1e-3], np.logspace(-1, 4, 300)])
+    tab = corrfunc.TabulatedCorrelation(r, corr_test_function(r), kind=kind)
+    x = np.linspace(2800.0, 3300.0, 7)
+    for xromb in (0, 2):
+        want = ocf.corr_to_clarray(tab, 63, x, xromb=xromb, q=2, chunksize=25)
+        got = corrfunc.corr_to_clarray(tab, 63, x, xromb=xromb, q=2, chunksize=25)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.abs(want).max())
+    # host call semantics = numpy.interp (clamped), including r = 0 on the log grid
+    np.testing.assert_allclose(tab(np.array([0.0, 5e-4, 2e4])), [tab.values[0], tab.values[0], tab.values[-1]])
+
+    class Sub(corrfunc.TabulatedCorrelation):      # an overriding subclass must be evaluated through the callable
+        def __call__(self, rr):
+            return 2.0 * corrfunc.TabulatedCorrelation.__call__(self, rr)
+
+    got2 = corrfunc.corr_to_clarray(Sub(r, corr_test_function(r), kind=kind), 63, x, xromb=2, q=2, chunksize=25)
+    np.testing.assert_allclose(got2, 2.0 * want, rtol=0, atol=1e-12 * np.abs(want).max())

@@ -469,3 +469,26 @@ def test_map2alm_production_size_vs_oracle_ms(nside, lmax):
     for m, v in ref.items():
         g = got[:, osht.alm_index(lmax, m, m) : osht.alm_index(lmax, lmax, m) + 1]
         assert np.max(np.abs(g - v)) / scale < TOL, m
+
+
+def test_single_role_legendre_kernels_agree_with_warp_specialised():
+    """Both Legendre implementations stay covered: the warp-specialised kernels (default) and the single-role
+    kernel (cora_b200_set_legendre_ws(0)) give the same maps to rounding, scalar and spin 2."""
+    import torch
+    from cora_b200 import _lib, hputil
+
+    lib = _lib.load()
+    nside, lmax, nchan = 32, 95, 19
+    rng = np.random.default_rng(5)
+    aT, aE, aB = (torch.from_numpy(_rand_alm(rng, nchan, lmax)).cuda() for _ in range(3))
+    old = lib.cora_b200_set_legendre_ws(3)
+    try:
+        t1 = hputil.alm2map_device(aT, nside, lmax, _lib.ALM_PACKED, aT.shape[1], nchan).clone()
+        q1, u1 = (x.clone() for x in hputil.alm2map_spin2_device(aE, aB, nside, lmax, _lib.ALM_PACKED, aE.shape[1], nchan))
+        lib.cora_b200_set_legendre_ws(0)
+        t0 = hputil.alm2map_device(aT, nside, lmax, _lib.ALM_PACKED, aT.shape[1], nchan)
+        q0, u0 = hputil.alm2map_spin2_device(aE, aB, nside, lmax, _lib.ALM_PACKED, aE.shape[1], nchan)
+    finally:
+        lib.cora_b200_set_legendre_ws(old)
+    for a, b in ((t1, t0), (q1, q0), (u1, u0)):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-12
