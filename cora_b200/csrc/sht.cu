@@ -63,6 +63,9 @@ struct ShtPlan {
     std::vector<PhaseClass> classes;
 };
 
+// M = 4096 phase classes: 1 = one channel pair per 256-thread CTA (3 CTAs per SM), 0 = two pairs per 512-thread CTA
+static int g_phase_4096_split = [] { const char* e = getenv("CORA_B200_PHASE_4096_SPLIT"); return (e && e[0] == '1') ? 1 : 0; }();
+
 static int ilog2(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
@@ -1960,6 +1963,8 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
     CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(sht_phase_kernel<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
     // per-ring FFT size; rings launched together by shared-memory footprint, longest first
     for (auto& rd : pl->h_rings) {
@@ -1983,6 +1988,7 @@ extern "C" int cora_b200_sht_plan_create(int nside, int lmax, void** plan_out) {
             pc.Mmax = 1 << lg;
             pc.P = (pc.Mmax <= 4096) ? 2 : 1;          // 2 pairs x 4096 points (padded) = 147 KB
             pc.threads = (pc.Mmax >= 4096) ? 512 : 256;
+            if (pc.Mmax == 4096 && g_phase_4096_split) { pc.P = 1; pc.threads = 256; }   // 74 KB: 3 CTAs of 256 threads per SM
             pc.nrings = (int)v.size();
             CB_CUDA(cudaMalloc(&pc.d_rings, sizeof(int) * v.size()));
             CB_CUDA(cudaMemcpy(pc.d_rings, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
@@ -2129,9 +2135,12 @@ static int run_phase(const ShtPlan* pl, const double2* F, int nb, double* map, c
         Q.lmax = pl->lmax; Q.nb = nb; Q.ncg = ceil_div(nb, 4); Q.P = pc.P; Q.Mmax = pc.Mmax; Q.log_tw = pl->log_tw;
         dim3 grid(pc.nrings, Q.ncg * (2 / pc.P));
         const size_t sm = phase_smem(pc);
-        if (pc.threads == 256) {
+        if (pc.threads == 256 && pc.P == 2) {
             if (pc.blu) sht_phase_kernel<256, 2, true><<<grid, 256, sm, st>>>(Q);
             else sht_phase_kernel<256, 2, false><<<grid, 256, sm, st>>>(Q);
+        } else if (pc.threads == 256) {
+            if (pc.blu) sht_phase_kernel<256, 1, true><<<grid, 256, sm, st>>>(Q);
+            else sht_phase_kernel<256, 1, false><<<grid, 256, sm, st>>>(Q);
         } else if (pc.P == 2) {
             if (pc.blu) sht_phase_kernel<512, 2, true><<<grid, 512, sm, st>>>(Q);
             else sht_phase_kernel<512, 2, false><<<grid, 512, sm, st>>>(Q);
