@@ -33,7 +33,8 @@ ms = (ctypes.c_double * nk)()
 cnt = (ctypes.c_longlong * nk)()
 lib.cora_b200_timing_read(ms, cnt, nk)
 k = {lib.cora_b200_timing_name(i).decode(): round(ms[i] / reps, 3) for i in range(nk) if cnt[i]}
-used = [int((r[1] > 0).sum().item()) for r in sh._buf["root"]]
+used_all = sh._buf["root"][1]   # int32[2 blocks, nl]: > 0 = eigen branch
+used = [int((used_all[b] > 0).sum().item()) for b in range(2)]
 print(json.dumps({"shape": {"nside": nside, "nchan": nchan, "lmax": sh.lmax, "npol": 4}, "ms_per_step": e0.elapsed_time(e1) / reps,
                   "voxels_per_s": 4.0 * nchan * sh.npix / (e0.elapsed_time(e1) / reps * 1e-3), "kernels_ms": k,
                   "l_on_eigen_branch": {"T": used[0], "P": used[1], "of": sh.nl}}))
