@@ -61,7 +61,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    # link next to the target and rename: a snapshot of the tree (gpurun) never sees a half-written library
+    subprocess.check_call([nvcc, "-shared", "-o", LIB + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    os.replace(LIB + ".tmp", LIB)
     return LIB
 
 

@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
 // mirror element (j, i) is not written: the root stage reads the lower triangle only (LAPACK-style).
 constexpr int F3_THREADS = 320;
 constexpr int F3_TILE = 4;        // j-adjacent channel pairs per CTA
+constexpr int F3_NSLOTS = 1024;   // scratch rows for the parked pair results (>> resident CTAs: 3 per SM)
 constexpr int F3_GMAX = 4;        // shift groups per channel pair: 4 for short y windows, 2 for tall ones
 constexpr int F3_YSPLIT = 64;     // y windows taller than this use 2 groups (the band pass costs 2 G FMAs per table entry)
 constexpr int F3_WMAX = 352;      // widest x band
@@ -451,17 +452,44 @@ struct F3Ctx {
     double* const* out_ptrs;
     const int* l_owner;
     const int* l_row;
-    long long nz2, oij, oji;
+    long long nz2;
     double xscale;
-    int l0, l_step, nl, li_first, lfirst, llast, npair, mirror;
+    int l0, l_step, nl, li_first, lfirst, llast, npair;
+    // The tile's pairs (i, j0 .. j0 + pp_last) are evaluated one after the other, but their results leave the CTA
+    // together: pairs before the last park their value of every l in a per-CTA scratch row (global memory, L2
+    // resident), the last pair's store picks them up and writes ONE run per l -- a single 32-byte vector store for a
+    // full tile (SASS STG.256).  Over NVLink (tile-sharded fill: row l lives on the GPU that owns l) that is one
+    // 32-byte write where four 8-byte writes used to go out, each with its own packet header.
+    double* scratch;          // [F3_TILE - 1][nl]
+    int pp, pp_last, full, ic, j0c, nzc;
+    long long oi0;            // offset of (i, j0) inside a matrix
     __device__ __forceinline__ void store(int li, double v) const {
+        if (pp < pp_last) { scratch[(long long)pp * nl + li] = v; return; }
         double* o = out + (long long)li * nz2;
-        if (out_ptrs) {   // tile-sharded fill: row l lives on the GPU that owns l (peer store over NVLink)
+        if (out_ptrs) {
             const int l = l0 + li * l_step;
             o = out_ptrs[l_owner[l]] + (long long)l_row[l] * nz2;
         }
-        __stcs(o + oij, v);               // streaming store: the table is written once and read by a later kernel
-        if (mirror) __stcs(o + oji, v);
+        double h[F3_TILE];
+#pragma unroll
+        for (int q = 0; q < F3_TILE - 1; q++) h[q] = (q < pp_last) ? __ldcg(scratch + (long long)q * nl + li) : 0.0;
+        double* run = o + oi0;
+        if (pp_last == F3_TILE - 1 && (((uintptr_t)run) & 31) == 0) {
+            // streaming 256-bit store: the table is written once and read by a later kernel
+            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(run), "d"(h[0]), "d"(h[1]), "d"(h[2]), "d"(v) : "memory");
+        } else {
+#pragma unroll
+            for (int q = 0; q < F3_TILE - 1; q++)
+                if (q < pp_last) __stcs(run + q, h[q]);
+            __stcs(run + pp_last, v);
+        }
+        if (full) {             // symmetric table requested: the (j, i) entries, one column of the rows j0 .. j0 + pp_last
+#pragma unroll
+            for (int q = 0; q < F3_TILE; q++) {
+                if (q > pp_last || j0c + q == ic) continue;
+                __stcs(o + (long long)(j0c + q) * nzc + ic, q == pp_last ? v : h[q]);
+            }
+        }
     }
 };
 
@@ -682,7 +710,8 @@ __global__ void __launch_bounds__(F3_THREADS, 3) cl21_fill3_kernel(const double*
                                                                    int l0, int l_step, int nl, int nz, int zint,
                                                                    double* __restrict__ out, long long tile0, int lower_only,
                                                                    double* const* __restrict__ out_ptrs,
-                                                                   const int* __restrict__ l_owner, const int* __restrict__ l_row) {
+                                                                   const int* __restrict__ l_owner, const int* __restrict__ l_row,
+                                                                   double* __restrict__ scratch_all, int* __restrict__ slot_busy) {
     extern __shared__ __align__(16) unsigned char smraw[];
     F3Smem& sm = *(F3Smem*)smraw;
     const int npair = zint * zint;
@@ -732,13 +761,25 @@ __global__ void __launch_bounds__(F3_THREADS, 3) cl21_fill3_kernel(const double*
         return p;
     };
 
+    // scratch row of this CTA: claim one of the F3_NSLOTS slots (at most 3 x #SM CTAs are resident, far fewer than slots)
+    __shared__ int s_slot;
+    if (tid == 0) {
+        int sl = (int)(blockIdx.x % F3_NSLOTS);
+        while (atomicCAS(slot_busy + sl, 0, 1) != 0) sl = (sl + 1) % F3_NSLOTS;
+        s_slot = sl;
+    }
+    __syncthreads();
+    c.scratch = scratch_all + (long long)s_slot * (F3_TILE - 1) * nl;
+    c.pp_last = min(F3_TILE - 1, i - j0);
+    c.full = lower_only ? 0 : 1;
+    c.ic = i; c.j0c = j0; c.nzc = nz;
+    c.oi0 = (long long)i * nz + j0;
+
     for (int pp = 0; pp < F3_TILE; pp++) {
         const int j = j0 + pp;
         if (j > i) break;                      // uniform: partial tile on the diagonal
-        c.oij = (long long)i * nz + j;
-        c.oji = (long long)j * nz + i;
-        c.mirror = (i != j && !lower_only) ? 1 : 0;
-        __syncthreads();                       // the previous pair's shared state is no longer read
+        c.pp = pp;
+        __syncthreads();                       // the previous pair's shared state is no longer read (and its parked values are visible)
         const bool small = (npair <= F3_NPMAX);
         if (small) {
             for (int e = tid; e < npair; e += F3_THREADS) { sm.pre[e] = make_pre(j, e); sm.rank[e] = 0; }
@@ -803,6 +844,8 @@ __global__ void __launch_bounds__(F3_THREADS, 3) cl21_fill3_kernel(const double*
             }
         }
     }
+    __syncthreads();
+    if (tid == 0) atomicExch(slot_busy + s_slot, 0);
 }
 
 // upper triangle <- lower triangle (32 x 32 tiles through shared memory, full-sector writes)
@@ -982,6 +1025,34 @@ static int fill_tile_table(int nz, const long long** out) {
 
 extern "C" long long cora_b200_cl_fill_21cm_ntiles(int nz) { return nz >= 1 ? fill_ntiles(nz) : 0; }
 
+// per-device scratch of the fill kernel (parked pair results, F3_NSLOTS rows of (F3_TILE - 1) nl doubles) and the slot
+// flags; grows with nl, never shrinks
+struct FillScratch { int dev; int nl; double* d; int* busy; };
+static std::vector<FillScratch> g_fill_scratch;
+static int fill_scratch(int nl, double** d, int** busy) {
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    for (auto& f : g_fill_scratch)
+        if (f.dev == dev) {
+            if (f.nl < nl) {
+                CB_CUDA(cudaDeviceSynchronize());
+                cudaFree(f.d);
+                CB_CUDA(cudaMalloc(&f.d, sizeof(double) * (size_t)F3_NSLOTS * (F3_TILE - 1) * nl));
+                f.nl = nl;
+            }
+            *d = f.d; *busy = f.busy;
+            return 0;
+        }
+    FillScratch f;
+    f.dev = dev; f.nl = nl; f.d = nullptr; f.busy = nullptr;
+    CB_CUDA(cudaMalloc(&f.d, sizeof(double) * (size_t)F3_NSLOTS * (F3_TILE - 1) * nl));
+    CB_CUDA(cudaMalloc(&f.busy, sizeof(int) * F3_NSLOTS));
+    CB_CUDA(cudaMemset(f.busy, 0, sizeof(int) * F3_NSLOTS));
+    g_fill_scratch.push_back(f);
+    *d = f.d; *busy = f.busy;
+    return 0;
+}
+
 static int fill21_launch(const double* tab, const double* chi, const double* b, const double* f, const double* pf,
                          const double* D, const double* w, int l0, int l_step, int nl, int nz, int zint, double* out_cl,
                          int lower_only, int variant, long long tile0, long long ntiles, double* const* out_ptrs,
@@ -998,6 +1069,9 @@ static int fill21_launch(const double* tab, const double* chi, const double* b, 
         CB_LAUNCH_CHECK();
         return 0;
     }
+    double* scratch = nullptr;
+    int* busy = nullptr;
+    if (int rc = fill_scratch(nl, &scratch, &busy)) return rc;
     double* lx = nullptr;
     CB_CUDA(cudaMallocAsync(&lx, sizeof(double) * (size_t)nl, st));
     log10_table_kernel<<<ceil_div(nl, 256), 256, 0, st>>>(l0, l_step, nl, lx);
@@ -1005,7 +1079,7 @@ static int fill21_launch(const double* tab, const double* chi, const double* b, 
     const size_t smem = sizeof(F3Smem);
     CB_CUDA(cudaFuncSetAttribute(cl21_fill3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cl21_fill3_kernel<<<(unsigned)ntiles, F3_THREADS, smem, st>>>(tab, chi, b, f, pf, D, w, lx, tstart, l0, l_step, nl, nz, zint, out_cl,
-                                                                 tile0, lower_only, out_ptrs, l_owner, l_row);
+                                                                 tile0, lower_only, out_ptrs, l_owner, l_row, scratch, busy);
     count_launch();
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaFreeAsync(lx, st));

@@ -217,6 +217,194 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky_kernel(double* __restr
     if (tid == 0) fail[blockIdx.x] = s_fail;
 }
 
+// ----------------------------------------------------------------- Cholesky, fused tile passes
+// Same left-looking algorithm and the same arithmetic per element as cholesky_kernel, restructured around what the
+// ncu source page of the 1024-channel case showed (profiles/r02/ncu_chol_c3_pass1.txt): 14 % of the stall samples sat
+// on the scattered global read-modify-write that ended the panel update, another ~8 % on re-reading the panel from
+// global memory for the diagonal block and the row solve.  Here every 256-row tile of a block column makes ONE pass:
+//   DMMA update into registers -> the tile (A - update) assembled in shared memory (coalesced 256-byte row reads) ->
+//   [first tile: diagonal block factored by warp 0] -> row solve from shared memory, one row per thread ->
+//   coalesced store of the finished L rows.
+// The panel tile lives in the operand stage buffers, which are idle between two K loops.
+constexpr int CH_PLD = 33;     // panel tile pitch: one row per thread reads conflict-free
+
+// doubles of the operand ring of cholesky2_kernel (at least the 256 x 33 panel tile that aliases it)
+__host__ __device__ constexpr int ch2_stage_doubles(int KC, int LD, int NST) {
+    return (NST * (CH_ROWS + CH_NB) * LD > CH_ROWS * CH_PLD) ? NST * (CH_ROWS + CH_NB) * LD : CH_ROWS * CH_PLD;
+}
+
+// KC: k per staged chunk, LD: row pitch of the [row][k] operand tiles, NST: stages of the cp.async ring.
+// (16, 20, 2): 64 DMMAs per warp between two CTA barriers, one chunk of prefetch; (8, 12, 3): 32 DMMAs, two chunks.
+template <bool FAST, int KC, int LD, int NST>
+__global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(double* __restrict__ root, int nz, int* __restrict__ fail) {
+    constexpr int STAGE = (CH_ROWS + CH_NB) * LD;
+    extern __shared__ __align__(16) double ch_smem[];
+    double* stage = ch_smem;                              // [NST][STAGE]; aliased by the panel tile P[256][CH_PLD]
+    double* Pt = ch_smem;
+    double (*Ld)[CH_NB + 1] = (double (*)[CH_NB + 1])(ch_smem + ch2_stage_doubles(KC, LD, NST));   // factored diagonal block
+    __shared__ int s_fail;
+    __shared__ double Linv[CH_NB];                        // reciprocals of the diagonal block's pivots
+    double* A = root + (long long)blockIdx.x * nz * nz;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+
+    for (int kb = 0; kb < nz; kb += CH_NB) {
+        const int nbk = min(CH_NB, nz - kb);
+        const int nchunk = (kb + KC - 1) / KC;
+        for (int r0 = kb; r0 < nz; r0 += CH_ROWS) {
+            // ---- (1) update of this tile's 256 x 32 panel entries on the tensor cores
+            double acc[4][4][2];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            if (kb > 0) {
+                auto load = [&](int ck, int slot) {
+                    double* S = stage + slot * STAGE;
+                    const int p0 = ck * KC;
+                    // rows 0..255: the row tile; rows 256..287: the block column's own rows kb..kb+31
+                    for (int e = tid; e < (CH_ROWS + CH_NB) * (KC / 2); e += CH_THREADS) {
+                        const int rr = e / (KC / 2), kk = (e % (KC / 2)) * 2;
+                        const int r = (rr < CH_ROWS) ? r0 + rr : kb + (rr - CH_ROWS);
+                        const int k = p0 + kk;
+                        double* dst = S + rr * LD + kk;
+                        if (FAST) {
+                            const bool ok = (r < nz) && (k < kb);   // kb is a multiple of 32: k, k+1 < kb together
+                            cp_async16(dst, A + (ok ? ((long long)r * nz + k) : 0), ok);
+                        } else {
+                            dst[0] = (r < nz && k < kb) ? A[(long long)r * nz + k] : 0.0;
+                            dst[1] = (r < nz && k + 1 < kb) ? A[(long long)r * nz + k + 1] : 0.0;
+                        }
+                    }
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int st = 0; st < NST - 1; st++) {
+                    if (st < nchunk) load(st, st); else cp_async_commit();
+                }
+                for (int ck = 0; ck < nchunk; ck++) {
+                    cp_async_wait<NST - 2>();
+                    __syncthreads();   // chunk ck landed for everyone; the slot refilled below was consumed one iteration ago
+                    if (ck + NST - 1 < nchunk) load(ck + NST - 1, (ck + NST - 1) % NST); else cp_async_commit();
+                    const double* S = stage + (ck % NST) * STAGE;
+                    const double* Sa = S + warp * 32 * LD;
+                    const double* Sb = S + CH_ROWS * LD;
+                    if (r0 + warp * 32 < nz) {
+#pragma unroll
+                        for (int k4 = 0; k4 < KC / 4; k4++) {
+                            double af[4], bf[4];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++) af[mb] = Sa[(8 * mb + g) * LD + k4 * 4 + t];
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++) bf[nb] = Sb[(8 * nb + g) * LD + k4 * 4 + t];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                                for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+                        }
+                    }
+                }
+                cp_async_wait<0>();
+                __syncthreads();   // all fragment reads done: the stage buffers become the panel tile
+            }
+            // ---- (2) P = A[tile, kb:kb+32] - update.  The update is scattered from the fragments (C[g][2t], C[g][2t+1]:
+            // row 8 mb + g, columns 8 nb + 2t, + 1), the matrix entries are added by coalesced row reads.
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                double* pr = Pt + (warp * 32 + 8 * mb + g) * CH_PLD;
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) {
+                    pr[8 * nb + 2 * t] = -acc[mb][nb][0];
+                    pr[8 * nb + 2 * t + 1] = -acc[mb][nb][1];
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < CH_ROWS * CH_NB; e += CH_THREADS) {
+                const int rr = e >> 5, c = e & 31;
+                const int r = r0 + rr;
+                double v = 0.0;
+                if (r < nz && c < nbk && kb + c <= r) v = Pt[rr * CH_PLD + c] + A[(long long)r * nz + kb + c];
+                Pt[rr * CH_PLD + c] = v;
+            }
+            __syncthreads();
+            // ---- (3) first tile: the 32 x 32 diagonal block, one warp, lane = row (rows in registers, columns
+            // broadcast by shuffles, one reciprocal square root per pivot)
+            if (r0 == kb) {
+                if (warp == 0) {
+                    double r[CH_NB];
+#pragma unroll
+                    for (int c = 0; c < CH_NB; c++) r[c] = Pt[lane * CH_PLD + c];
+                    bool bad = false;
+                    double myinv = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < CH_NB; jj++) {
+                        const double d = __shfl_sync(0xffffffffu, r[jj], jj);
+                        if (jj < nbk && !bad) {                       // warp-uniform
+                            if (!(d > 0.0)) {
+                                bad = true;
+                            } else {
+                                const double dinv = rsqrt(d);
+                                const double dj = d * dinv;
+                                double lij = r[jj] * dinv;            // rows above jj hold 0 here and stay 0
+                                if (lane == jj) { lij = dj; myinv = dinv; }
+                                r[jj] = lij;
+#pragma unroll
+                                for (int c = jj + 1; c < CH_NB; c++) {
+                                    const double lc = __shfl_sync(0xffffffffu, lij, c);   // L[c][jj]
+                                    r[c] -= lij * lc;                 // meaningful for lane >= c (lower triangle)
+                                }
+                            }
+                        }
+                    }
+                    if (bad && lane == 0) s_fail = 1;
+#pragma unroll
+                    for (int c = 0; c < CH_NB; c++) {
+                        const double v = (c <= lane && lane < nbk) ? r[c] : 0.0;
+                        Ld[lane][c] = v;
+                        Pt[lane * CH_PLD + c] = v;
+                    }
+                    Linv[lane] = myinv;
+                }
+                __syncthreads();
+                if (s_fail) break;
+            }
+            // ---- (4) rows below the diagonal block: X L_kk^T = B by substitution, one row per thread, right-looking
+            {
+                const int r = r0 + tid;
+                if (r >= kb + nbk && r < nz) {
+                    double* pr = Pt + tid * CH_PLD;
+                    double v[CH_NB];
+#pragma unroll
+                    for (int cc = 0; cc < CH_NB; cc++) v[cc] = pr[cc];
+#pragma unroll
+                    for (int pp = 0; pp < CH_NB; pp++) {
+                        if (pp < nbk) {
+                            const double xp = v[pp] * Linv[pp];
+                            v[pp] = xp;
+#pragma unroll
+                            for (int cc = pp + 1; cc < CH_NB; cc++) v[cc] -= xp * Ld[cc][pp];   // Ld rows >= nbk are zero
+                        }
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < CH_NB; cc++) pr[cc] = v[cc];
+                }
+            }
+            __syncthreads();
+            // ---- (5) finished rows of L back to global memory, 256-byte runs
+            for (int e = tid; e < CH_ROWS * CH_NB; e += CH_THREADS) {
+                const int rr = e >> 5, c = e & 31;
+                const int r = r0 + rr;
+                if (r < nz && c < nbk && kb + c <= r) A[(long long)r * nz + kb + c] = Pt[rr * CH_PLD + c];
+            }
+            __syncthreads();   // the next K loop refills the stage buffers
+        }
+        if (s_fail) break;
+    }
+    if (tid == 0) fail[blockIdx.x] = s_fail;
+}
+
 // ================================================================= eigen fallback
 // Reference semantics (cora/util/nputil.py:86-96): eigh of the jittered matrix, eigenvalues below
 // clip_rel * (largest eigenvalue) set to zero, root = evecs sqrt(evals), every column kept, ascending
@@ -688,6 +876,10 @@ static long long root_fixed_bytes(int nb, int nl, int nz) {
 
 // Matrices up to this size always take the exact Jacobi eigen fallback; larger ones the low-rank route first.
 // CORA_B200_JACOBI_MAX_NZ overrides (e.g. a huge value forces the exact route everywhere).
+// 1: the first Cholesky kernel (separate read-modify-write / diagonal / row-solve phases), for A/B runs
+static const bool g_chol_v1 = [] { const char* e = getenv("CORA_B200_CHOL_V1"); return e && e[0] == '1'; }();
+// operand ring of the fused-tile Cholesky: 0 = 2 stages of 16 k, 1 = 3 stages of 8 k (deeper prefetch, more barriers)
+static const bool g_chol_deep = [] { const char* e = getenv("CORA_B200_CHOL_DEEP"); return e && e[0] == '1'; }();
 static int g_jacobi_max_nz = [] { const char* e = getenv("CORA_B200_JACOBI_MAX_NZ"); return e ? atoi(e) : 128; }();
 
 extern "C" long long cora_b200_root_workspace_bytes(int nl, int nz) {
@@ -777,7 +969,19 @@ extern "C" int cora_b200_root_batched_multi(const double* const* cl_blocks, int 
         CB_LAUNCH_CHECK();
         KTimer kt(K_CHOLESKY, st);
         const size_t smem = sizeof(double) * (2 * CH_STAGE + CH_NB * (CH_NB + 1));
-        if (nz % 2 == 0) {
+        if (!g_chol_v1) {
+            auto launch2 = [&](auto kern, size_t sm) -> int {
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                kern<<<nl, CH_THREADS, sm, st>>>(B.root[b], nz, fail + (long long)b * nl);
+                return 0;
+            };
+            const size_t sm_a = sizeof(double) * (ch2_stage_doubles(16, 20, 2) + CH_NB * (CH_NB + 1));
+            const size_t sm_b = sizeof(double) * (ch2_stage_doubles(8, 12, 3) + CH_NB * (CH_NB + 1));
+            int rc2;
+            if (nz % 2 == 0) rc2 = g_chol_deep ? launch2(cholesky2_kernel<true, 8, 12, 3>, sm_b) : launch2(cholesky2_kernel<true, 16, 20, 2>, sm_a);
+            else rc2 = g_chol_deep ? launch2(cholesky2_kernel<false, 8, 12, 3>, sm_b) : launch2(cholesky2_kernel<false, 16, 20, 2>, sm_a);
+            if (rc2) return rc2;
+        } else if (nz % 2 == 0) {
             CB_CUDA(cudaFuncSetAttribute(cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cholesky_kernel<true><<<nl, CH_THREADS, smem, st>>>(B.root[b], nz, fail + (long long)b * nl);
         } else {
