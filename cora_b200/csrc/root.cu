@@ -236,7 +236,13 @@ __host__ __device__ constexpr int ch2_stage_doubles(int KC, int LD, int NST) {
 // KC: k per staged chunk, LD: row pitch of the [row][k] operand tiles, NST: stages of the cp.async ring.
 // (16, 20, 2): 64 DMMAs per warp between two CTA barriers, one chunk of prefetch; (8, 12, 3): 32 DMMAs, two chunks.
 template <bool FAST, int KC, int LD, int NST>
-__global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(double* __restrict__ root, int nz, int* __restrict__ fail) {
+__global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(const double* __restrict__ cl, double* __restrict__ root, int nz,
+                                                                  double jitter_rel, const double* __restrict__ dmax,
+                                                                  int* __restrict__ fail) {
+    // Reads the covariance (lower triangle of cl, + jitter_rel * dmax[l] on the diagonal: cora/core/skysim.py:116-117)
+    // the one time each entry is needed and writes the finished root -- L below, exact zeros above the diagonal --
+    // into `root`: the separate jitter-and-copy pass (root_prepare_kernel: 4 MB read + 8 MB written per 1024^2 matrix)
+    // is gone.
     constexpr int STAGE = (CH_ROWS + CH_NB) * LD;
     extern __shared__ __align__(16) double ch_smem[];
     double* stage = ch_smem;                              // [NST][STAGE]; aliased by the panel tile P[256][CH_PLD]
@@ -245,6 +251,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(double* __rest
     __shared__ int s_fail;
     __shared__ double Linv[CH_NB];                        // reciprocals of the diagonal block's pivots
     double* A = root + (long long)blockIdx.x * nz * nz;
+    const double* C = cl + (long long)blockIdx.x * nz * nz;
+    const double cjit = dmax[blockIdx.x] * jitter_rel;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     if (tid == 0) s_fail = 0;
@@ -253,6 +261,11 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(double* __rest
     for (int kb = 0; kb < nz; kb += CH_NB) {
         const int nbk = min(CH_NB, nz - kb);
         const int nchunk = (kb + KC - 1) / KC;
+        // zeros above the diagonal block of this block column (rows 0 .. kb-1), 256-byte runs
+        for (int e = tid; e < kb * CH_NB; e += CH_THREADS) {
+            const int rr = e >> 5, c = e & 31;
+            if (c < nbk) A[(long long)rr * nz + kb + c] = 0.0;
+        }
         for (int r0 = kb; r0 < nz; r0 += CH_ROWS) {
             // ---- (1) update of this tile's 256 x 32 panel entries on the tensor cores
             double acc[4][4][2];
@@ -325,7 +338,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(double* __rest
                 const int rr = e >> 5, c = e & 31;
                 const int r = r0 + rr;
                 double v = 0.0;
-                if (r < nz && c < nbk && kb + c <= r) v = Pt[rr * CH_PLD + c] + A[(long long)r * nz + kb + c];
+                if (r < nz && c < nbk && kb + c <= r) v = Pt[rr * CH_PLD + c] + (C[(long long)r * nz + kb + c] + (kb + c == r ? cjit : 0.0));
                 Pt[rr * CH_PLD + c] = v;
             }
             __syncthreads();
@@ -396,7 +409,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) cholesky2_kernel(double* __rest
             for (int e = tid; e < CH_ROWS * CH_NB; e += CH_THREADS) {
                 const int rr = e >> 5, c = e & 31;
                 const int r = r0 + rr;
-                if (r < nz && c < nbk && kb + c <= r) A[(long long)r * nz + kb + c] = Pt[rr * CH_PLD + c];
+                // (rows of the diagonal block: the zeros right of the diagonal are written too)
+                if (r < nz && c < nbk && (kb + c <= r || r < kb + CH_NB)) A[(long long)r * nz + kb + c] = Pt[rr * CH_PLD + c];
             }
             __syncthreads();   // the next K loop refills the stage buffers
         }
@@ -964,15 +978,17 @@ extern "C" int cora_b200_root_batched_multi(const double* const* cl_blocks, int 
     }
     CB_LAUNCH_CHECK();
     for (int b = 0; b < nb; b++) {
-        { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<dim3(nl, nl >= 1024 ? 2 : 8), 256, 0, st>>>(B.cl[b], nz, jitter_rel, B.root[b], dmax2, dmax); }
-        count_launch();
-        CB_LAUNCH_CHECK();
+        if (g_chol_v1) {
+            { KTimer kt(K_ROOT_PREP, st); root_prepare_kernel<<<dim3(nl, nl >= 1024 ? 2 : 8), 256, 0, st>>>(B.cl[b], nz, jitter_rel, B.root[b], dmax2, dmax); }
+            count_launch();
+            CB_LAUNCH_CHECK();
+        }
         KTimer kt(K_CHOLESKY, st);
         const size_t smem = sizeof(double) * (2 * CH_STAGE + CH_NB * (CH_NB + 1));
         if (!g_chol_v1) {
             auto launch2 = [&](auto kern, size_t sm) -> int {
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                kern<<<nl, CH_THREADS, sm, st>>>(B.root[b], nz, fail + (long long)b * nl);
+                kern<<<nl, CH_THREADS, sm, st>>>(B.cl[b], B.root[b], nz, jitter_rel, dmax, fail + (long long)b * nl);
                 return 0;
             };
             const size_t sm_a = sizeof(double) * (ch2_stage_doubles(16, 20, 2) + CH_NB * (CH_NB + 1));

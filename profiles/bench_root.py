@@ -30,6 +30,6 @@ for nl in (1, 37, 74, 148, 296, 444, 592, 768):
     lib.cora_b200_timing_read(ms, cnt, nk)
     lib.cora_b200_timing_enable(0)
     k = {lib.cora_b200_timing_name(i).decode(): ms[i] / reps for i in range(nk) if cnt[i]}
-    out[nl] = {"cholesky_ms": round(k["cholesky"], 4), "prepare_ms": round(k["root_prepare"], 4),
+    out[nl] = {"cholesky_ms": round(k["cholesky"], 4), "prepare_ms": round(k.get("root_prepare", 0.0), 4),
                "gflops": round(nl * nz**3 / 3.0 / (k["cholesky"] * 1e-3) / 1e9, 1)}
 print(json.dumps({"nz": nz, "by_batch": out}))
