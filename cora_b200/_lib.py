@@ -65,7 +65,7 @@ SIGNATURES = {
     "cora_b200_peer_open": (_i, [_c.c_char_p, _c.POINTER(_vp)]),
     "cora_b200_peer_close": (_i, [_vp]),
     "cora_b200_peer_barrier": (_i, [_vp, _i, _i, _ull, _d, _vp, _i, _vp]),
-    "cora_b200_cl_fill_21cm_tiles": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp]),
+    "cora_b200_cl_fill_21cm_tiles": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _i, _vp, _vp, _vp, _vp]),
     "cora_b200_draw_apply_peers": (_i, [_vp, _vp, _vp, _i, _i, _i, _ull, _i, _vp, _ll, _vp, _vp, _vp, _ll, _vp]),
     "cora_b200_alm2map_strided": (_i, [_vp, _vp, _i, _ll, _i, _vp, _ll, _vp, _ll, _vp]),
     "cora_b200_alm2map_spin2_strided": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _ll, _vp, _ll, _vp]),

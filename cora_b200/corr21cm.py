@@ -207,12 +207,12 @@ class Corr21cm(maps.Sky3d):
                   _lib.ptr(out), int(bool(lower_only)), int(variant), _lib.stream_ptr(stream))
 
 
-    def _b200_fill_tiles(self, inputs, nl, nz, zint, tile0, ntiles, out_ptrs, l_owner, l_row, stream=None):
-        """Fill sharded over channel-pair tiles with the rows scattered to the GPUs owning each l (multi-GPU path;
-        lower triangle only)."""
+    def _b200_fill_tiles(self, inputs, nl, nz, zint, tile0, ntiles, out_ptrs, l_owner, l_row, stream=None, tile_step=1):
+        """Fill sharded over channel-pair tiles (tile0, tile0 + tile_step, ...: ntiles of them) with the rows scattered
+        to the GPUs owning each l (multi-GPU path; lower triangle only)."""
         tab, vec, wd, variant = inputs
         _lib.call("cora_b200_cl_fill_21cm_tiles", _lib.ptr(tab), _lib.ptr(vec[0]), _lib.ptr(vec[1]), _lib.ptr(vec[2]),
-                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(nl), int(nz), int(zint), int(tile0), int(ntiles), int(variant),
+                  _lib.ptr(vec[3]), _lib.ptr(vec[4]), _lib.ptr(wd), int(nl), int(nz), int(zint), int(tile0), int(ntiles), int(tile_step), int(variant),
                   _lib.ptr(out_ptrs), _lib.ptr(l_owner), _lib.ptr(l_row), _lib.stream_ptr(stream))
 
 

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
                                                         const double* __restrict__ bb, const double* __restrict__ ff,
                                                         const double* __restrict__ pf, const double* __restrict__ DD,
                                                         const double* __restrict__ w, int l0, int l_step, int nl, int nz,
-                                                        int zint, double* __restrict__ out, long long pair0,
+                                                        int zint, double* __restrict__ out, long long pair0, int tile_step,
                                                         double* const* __restrict__ out_ptrs,
                                                         const int* __restrict__ l_owner, const int* __restrict__ l_row,
                                                         const long long* __restrict__ tile_start, int lower_only) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) cl21_fill_kernel(const double* __restrict
     int i, j;
     if (tile_start) {
         // tile enumeration of the row-weight kernel (4 CTAs per tile (i; j0 .. j0+3), pair0 = first tile)
-        const long long tidx = pair0 + (blockIdx.x >> 2);
+        const long long tidx = pair0 + (long long)tile_step * (blockIdx.x >> 2);
         int lo = 0, hi = nz - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(F3_THREADS, 3) cl21_fill3_kernel(const double*
                                                                    const double* __restrict__ w, const double* __restrict__ lxtab,
                                                                    const long long* __restrict__ tile_start,
                                                                    int l0, int l_step, int nl, int nz, int zint,
-                                                                   double* __restrict__ out, long long tile0, int lower_only,
+                                                                   double* __restrict__ out, long long tile0, int tile_step, int lower_only,
                                                                    double* const* __restrict__ out_ptrs,
                                                                    const int* __restrict__ l_owner, const int* __restrict__ l_row,
                                                                    double* __restrict__ scratch_all, int* __restrict__ slot_busy) {
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(F3_THREADS, 3) cl21_fill3_kernel(const double*
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // tile (i; j0 .. j0+3): tiles are enumerated by dt = i - j0 first (tiles that run together share the band of
     // table rows, y ~ |chi_i - chi_j|), then by j0 / 4.  tile_start[dt] = index of the first tile of offset dt.
-    const long long tidx = tile0 + blockIdx.x;
+    const long long tidx = tile0 + (long long)tile_step * blockIdx.x;
     int lo = 0, hi = nz - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -1055,7 +1055,7 @@ static int fill_scratch(int nl, double** d, int** busy) {
 
 static int fill21_launch(const double* tab, const double* chi, const double* b, const double* f, const double* pf,
                          const double* D, const double* w, int l0, int l_step, int nl, int nz, int zint, double* out_cl,
-                         int lower_only, int variant, long long tile0, long long ntiles, double* const* out_ptrs,
+                         int lower_only, int variant, long long tile0, long long ntiles, int tile_step, double* const* out_ptrs,
                          const int* l_owner, const int* l_row, cudaStream_t st) {
     KTimer kt(K_CL_FILL, st);
     const long long* tstart = nullptr;
@@ -1063,7 +1063,7 @@ static int fill21_launch(const double* tab, const double* chi, const double* b, 
     if (g_fill_v1 || variant == 1) {
         size_t smem = sizeof(PairPre) * (size_t)zint * zint + sizeof(double) * FILL_EB * FILL_WMAX;
         CB_CUDA(cudaFuncSetAttribute(cl21_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cl21_fill_kernel<<<(unsigned)(ntiles * F3_TILE), 256, smem, st>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl, tile0,
+        cl21_fill_kernel<<<(unsigned)(ntiles * F3_TILE), 256, smem, st>>>(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl, tile0, tile_step,
                                                                          out_ptrs, l_owner, l_row, tstart, lower_only);
         count_launch();
         CB_LAUNCH_CHECK();
@@ -1079,7 +1079,7 @@ static int fill21_launch(const double* tab, const double* chi, const double* b, 
     const size_t smem = sizeof(F3Smem);
     CB_CUDA(cudaFuncSetAttribute(cl21_fill3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cl21_fill3_kernel<<<(unsigned)ntiles, F3_THREADS, smem, st>>>(tab, chi, b, f, pf, D, w, lx, tstart, l0, l_step, nl, nz, zint, out_cl,
-                                                                 tile0, lower_only, out_ptrs, l_owner, l_row, scratch, busy);
+                                                                 tile0, tile_step, lower_only, out_ptrs, l_owner, l_row, scratch, busy);
     count_launch();
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaFreeAsync(lx, st));
@@ -1093,22 +1093,23 @@ extern "C" int cora_b200_cl_fill_21cm(const double* tab, const double* chi, cons
     CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_21cm: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
     const long long ntiles = fill_ntiles(nz);
     CB_REQUIRE((long long)nz * (nz + 1) / 2 < 2147483647LL, 3, "cl_fill_21cm: too many channel pairs");
-    return fill21_launch(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl, lower_only, variant, 0, ntiles, nullptr, nullptr,
+    return fill21_launch(tab, chi, b, f, pf, D, w, l0, l_step, nl, nz, zint, out_cl, lower_only, variant, 0, ntiles, 1, nullptr, nullptr,
                          nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int cora_b200_cl_fill_21cm_tiles(const double* tab, const double* chi, const double* b, const double* f,
                                             const double* pf, const double* D, const double* w, int nl, int nz, int zint,
-                                            long long tile0, long long ntiles, int variant, const void* out_ptrs,
+                                            long long tile0, long long ntiles, int tile_step, int variant, const void* out_ptrs,
                                             const int* l_owner, const int* l_row, void* stream) {
     CB_REQUIRE(tab && chi && b && f && pf && D && w && out_ptrs && l_owner && l_row, 1, "cl_fill_21cm_tiles: null argument");
     CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT, 1, "cl_fill_21cm_tiles: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
     const long long all = fill_ntiles(nz);
-    CB_REQUIRE(tile0 >= 0 && ntiles >= 0 && tile0 + ntiles <= all && ntiles < 2147483647LL, 1,
-               "cl_fill_21cm_tiles: tile range [%lld, %lld) outside [0, %lld)", tile0, tile0 + ntiles, all);
+    CB_REQUIRE(tile0 >= 0 && ntiles >= 0 && tile_step >= 1 && ntiles < 2147483647LL &&
+                   (ntiles == 0 || tile0 + (ntiles - 1) * (long long)tile_step < all), 1,
+               "cl_fill_21cm_tiles: tiles %lld + %d k, k < %lld, outside [0, %lld)", tile0, tile_step, ntiles, all);
     if (ntiles == 0) return 0;
-    return fill21_launch(tab, chi, b, f, pf, D, w, 0, 1, nl, nz, zint, nullptr, 1, variant, tile0, ntiles, (double* const*)out_ptrs,
-                         l_owner, l_row, (cudaStream_t)stream);
+    return fill21_launch(tab, chi, b, f, pf, D, w, 0, 1, nl, nz, zint, nullptr, 1, variant, tile0, ntiles, tile_step,
+                         (double* const*)out_ptrs, l_owner, l_row, (cudaStream_t)stream);
 }
 
 extern "C" int cora_b200_cl_symmetrize(double* cl, int nl, int nz, void* stream) {

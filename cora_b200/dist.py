@@ -392,8 +392,10 @@ class ShardedSky(object):
             width[int(self.plan.chan_lo[s_]):int(self.plan.chan_hi[s_])] = int(self.plan.cb[s_])
         st["nu_width"] = _dev.to_device(width, t.int32)
         ntile = int(_lib.load().cora_b200_cl_fill_21cm_ntiles(self.nz)) if st["pairs"] else 0
-        st["pair0"] = ntile * self.rank // self.size
-        st["npairs"] = ntile * (self.rank + 1) // self.size - st["pair0"]
+        # tiles are dealt interleaved: a tile's cost grows along the enumeration (with |chi_i - chi_j|), so contiguous
+        # ranges leave the last rank with the expensive ones (measured at 2 GPUs: 29.3 ms each against 42.6 ms on one)
+        st["pair0"] = self.rank
+        st["npairs"] = (ntile - self.rank + self.size - 1) // self.size if ntile > self.rank else 0
         st["tables"] = [None, None]
         self._p2p = st
         return st
@@ -426,7 +428,7 @@ class ShardedSky(object):
         if st["pairs"]:
             tab = self._p2p_tables(k)
             self.model._b200_fill_tiles(self.fill_inputs, self.lmax + 1, self.nz, self.zint, st["pair0"], st["npairs"],
-                                        tab["cla_ptrs"], st["l_owner"], st["l_row"])
+                                        tab["cla_ptrs"], st["l_owner"], st["l_row"], tile_step=self.size)
             return True     # remote stores in flight: barrier before the root reads cla[k]
         self.fill()
         return False

@@ -295,14 +295,17 @@ int cora_b200_peer_close(void* ptr);
 int cora_b200_peer_barrier(const void* flags_ptrs, int rank, int size, unsigned long long epoch,
                            double timeout_s, int* status, int fatal, void* stream);
 
-/* 21cm fill for the channel-pair tiles [tile0, tile0 + ntiles) of cora_b200_cl_fill_21cm_ntiles(nz) tiles
- * (a tile = channel i against 4 consecutive channels j0 .. j0+3 <= i; tiles ordered by i - j0, then j0),
- * all l = 0..nl-1, lower triangle only.  out_ptrs: device array of per-GPU C_l buffers; element (l, i, j) goes
- * to out_ptrs[l_owner[l]][(l_row[l] * nz + i) * nz + j] (32-byte runs over NVLink).  l_owner / l_row: device int[nl]. */
+/* 21cm fill for the channel-pair tiles tile0, tile0 + tile_step, ... (ntiles of them) of the
+ * cora_b200_cl_fill_21cm_ntiles(nz) tiles (a tile = channel i against 4 consecutive channels j0 .. j0+3 <= i; tiles
+ * ordered by i - j0, then j0), all l = 0..nl-1, lower triangle only.  Ranks take tiles INTERLEAVED (tile0 = rank,
+ * tile_step = size): a tile's cost grows with |chi_i - chi_j|, i.e. along the enumeration, so contiguous ranges are
+ * unbalanced (measured: 29.3 ms on each of two GPUs against 42.6 ms on one).  out_ptrs: device array of per-GPU C_l
+ * buffers; element (l, i, j) goes to out_ptrs[l_owner[l]][(l_row[l] * nz + i) * nz + j], one 32-byte run per (l, tile)
+ * (over NVLink for remote owners).  l_owner / l_row: device int[nl]. */
 long long cora_b200_cl_fill_21cm_ntiles(int nz);
 int cora_b200_cl_fill_21cm_tiles(const double* tab, const double* chi, const double* b, const double* f,
                                  const double* pf, const double* D, const double* w, int nl, int nz, int zint,
-                                 long long tile0, long long ntiles, int variant, const void* out_ptrs,
+                                 long long tile0, long long ntiles, int tile_step, int variant, const void* out_ptrs,
                                  const int* l_owner, const int* l_row, void* stream);
 
 /* draw + apply for the local l's with the exchange fused into the epilogue: element (l, m, nu)
