@@ -792,6 +792,14 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
         const int p = v / RPL;                       // the producer warp that feeds this ring group
         const int g = lane >> 2, t = lane & 3;
         const double* Ap = As + (size_t)v * NSA * GPC * AROWS * ALD;
+        // lane constants of the fragment addresses (see the group loop)
+        const int a_lane = t * ALD + g;
+        int b_lane[2][2];
+#pragma unroll
+        for (int par = 0; par < 2; par++)
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                b_lane[par][q] = (2 * t + par) * 16 + (((4 * q + (g >> 1)) ^ ((2 * t + par) & 7)) << 1) + (g & 1);
         const int L = lmax + 1;
         const int nring_tot = 4 * P.nside - 1;
         unsigned cglob = 0;
@@ -819,57 +827,82 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                 for (int grp = 0; grp < ng; grp++) {
                     const unsigned bal = balA[(v * NSA + sa) * GPC + grp];
                     if (!bal) continue;
-                    const double* Ac = Ap + (sa * GPC + grp) * AROWS * ALD;
-                    const double* Bb = Bs + (size_t)sb * BSTAGE;
+                    // fragment addresses = lane constants (hoisted above the item loop) + group / stage offsets:
+                    //   A: row (par * 4 + t) of the group's tile, ring 8 mb + g
+                    //   B: row r = 8 grp + 2 t + par, 16-byte unit (4 (nb & 1) + g / 2) ^ (r & 7) of column block blk
+                    const double* Ac = Ap + (sa * GPC + grp) * AROWS * ALD + a_lane;
+                    const double* Bc = Bs + (size_t)sb * BSTAGE + grp * 128;
+                    if (bal == 0xffffffffu) {
+                        // every ring of the group is live (the common case away from the poles): no predicates
+#pragma unroll
+                        for (int par = 0; par < 2; par++) {
+                            double af[4], bf[4];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++) af[mb] = Ac[par * 4 * ALD + 8 * mb];
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++)
+                                bf[nb] = Bc[(SPIN ? (2 * (nb >> 1) + h) : (2 * h + (nb >> 1))) * BBLK + b_lane[par][nb & 1]];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                                for (int nb = 0; nb < 4; nb++) dmma884(acc[par][mb][nb][0], acc[par][mb][nb][1], af[mb], bf[nb]);
+                        }
+                        if (SPIN) {
+                            // X2 rows of l-parity `par` have theta-parity 1 - par.  Q columns: (-aB_im, +aB_re) from the B tile,
+                            // U columns: (+aE_im, -aE_re) from the E tile -- the channel's other component, signed
+#pragma unroll
+                            for (int par = 0; par < 2; par++) {
+                                double af[4], bf[4];
+#pragma unroll
+                                for (int mb = 0; mb < 4; mb++) af[mb] = Ac[(8 + par * 4) * ALD + 8 * mb];
+#pragma unroll
+                                for (int nb = 0; nb < 4; nb++) {
+                                    const double vsw = Bc[(2 * (1 - (nb >> 1)) + h) * BBLK + (b_lane[par][nb & 1] ^ 1)];
+                                    bf[nb] = ((nb < 2) == ((g & 1) == 0)) ? -vsw : vsw;
+                                }
+#pragma unroll
+                                for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                                    for (int nb = 0; nb < 4; nb++)
+                                        dmma884(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[mb], bf[nb]);
+                            }
+                        }
+                        continue;
+                    }
                     int pm[4];
 #pragma unroll
                     for (int mb = 0; mb < 4; mb++) pm[mb] = (int)((bal >> (8 * mb)) & 0xffu);
-                    double af[2][4], bf[2][4];
 #pragma unroll
                     for (int par = 0; par < 2; par++) {
+                        double af[4], bf[4];
 #pragma unroll
-                        for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(par * 4 + t) * ALD + 8 * mb + g];
+                        for (int mb = 0; mb < 4; mb++) af[mb] = Ac[par * 4 * ALD + 8 * mb];
 #pragma unroll
-                        for (int nb = 0; nb < 4; nb++) {
-                            // scalar: column 32h + 8nb + g of row r: block 2h + nb/2, 16-byte unit 4(nb&1) + g/2, swizzled
-                            // spin 2: blocks 0,1 = E tile, 2,3 = B tile; Q columns (nb < 2) read E, U columns read B
-                            const int r = grp * 8 + 2 * t + par;
-                            const int unit = (4 * (nb & 1) + (g >> 1)) ^ (r & 7);
-                            const int blk = SPIN ? (2 * (nb >> 1) + h) : (2 * h + (nb >> 1));
-                            bf[par][nb] = Bb[blk * BBLK + r * 16 + unit * 2 + (g & 1)];
-                        }
-                    }
-#pragma unroll
-                    for (int par = 0; par < 2; par++)
+                        for (int nb = 0; nb < 4; nb++)
+                            bf[nb] = Bc[(SPIN ? (2 * (nb >> 1) + h) : (2 * h + (nb >> 1))) * BBLK + b_lane[par][nb & 1]];
 #pragma unroll
                         for (int mb = 0; mb < 4; mb++)
 #pragma unroll
                             for (int nb = 0; nb < 4; nb++)
-                                dmma884_p(acc[par][mb][nb][0], acc[par][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
+                                dmma884_p(acc[par][mb][nb][0], acc[par][mb][nb][1], af[mb], bf[nb], pm[mb]);
+                    }
                     if (SPIN) {
-                        // X2 rows of l-parity `par` have theta-parity 1 - par.  Q columns: (-aB_im, +aB_re) from the B tile,
-                        // U columns: (+aE_im, -aE_re) from the E tile -- the channel's other component, signed
 #pragma unroll
                         for (int par = 0; par < 2; par++) {
+                            double af[4], bf[4];
 #pragma unroll
-                            for (int mb = 0; mb < 4; mb++) af[par][mb] = Ac[(8 + par * 4 + t) * ALD + 8 * mb + g];
+                            for (int mb = 0; mb < 4; mb++) af[mb] = Ac[(8 + par * 4) * ALD + 8 * mb];
 #pragma unroll
                             for (int nb = 0; nb < 4; nb++) {
-                                const int r = grp * 8 + 2 * t + par;
-                                const int unit = (4 * (nb & 1) + (g >> 1)) ^ (r & 7);
-                                const int blk = 2 * (1 - (nb >> 1)) + h;
-                                const double vsw = Bb[blk * BBLK + r * 16 + unit * 2 + ((g & 1) ^ 1)];
-                                const bool neg = (nb < 2) ? ((g & 1) == 0) : ((g & 1) == 1);
-                                bf[par][nb] = neg ? -vsw : vsw;
+                                const double vsw = Bc[(2 * (1 - (nb >> 1)) + h) * BBLK + (b_lane[par][nb & 1] ^ 1)];
+                                bf[nb] = ((nb < 2) == ((g & 1) == 0)) ? -vsw : vsw;
                             }
-                        }
-#pragma unroll
-                        for (int par = 0; par < 2; par++)
 #pragma unroll
                             for (int mb = 0; mb < 4; mb++)
 #pragma unroll
                                 for (int nb = 0; nb < 4; nb++)
-                                    dmma884_p(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[par][mb], bf[par][nb], pm[mb]);
+                                    dmma884_p(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[mb], bf[nb], pm[mb]);
+                        }
                     }
                 }
                 __syncwarp();
