@@ -823,52 +823,68 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
                 const int ng = min(GPC, ngroups - c * GPC);
                 mbar_wait(fullB + sb, (cglob / NSB) & 1);
                 mbar_wait(fullA + p * NSA + sa, (cglob / NSA) & 1);
-#pragma unroll 1
-                for (int grp = 0; grp < ng; grp++) {
-                    const unsigned bal = balA[(v * NSA + sa) * GPC + grp];
-                    if (!bal) continue;
-                    // fragment addresses = lane constants (hoisted above the item loop) + group / stage offsets:
-                    //   A: row (par * 4 + t) of the group's tile, ring 8 mb + g
-                    //   B: row r = 8 grp + 2 t + par, 16-byte unit (4 (nb & 1) + g / 2) ^ (r & 7) of column block blk
-                    const double* Ac = Ap + (sa * GPC + grp) * AROWS * ALD + a_lane;
-                    const double* Bc = Bs + (size_t)sb * BSTAGE + grp * 128;
-                    if (bal == 0xffffffffu) {
-                        // every ring of the group is live (the common case away from the poles): no predicates
+                // every ring of a group live (the common case away from the poles): no predicates
+                auto group_full = [&](const double* Ac, const double* Bc) {
+#pragma unroll
+                    for (int par = 0; par < 2; par++) {
+                        double af[4], bf[4];
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++) af[mb] = Ac[par * 4 * ALD + 8 * mb];
+#pragma unroll
+                        for (int nb = 0; nb < 4; nb++)
+                            bf[nb] = Bc[(SPIN ? (2 * (nb >> 1) + h) : (2 * h + (nb >> 1))) * BBLK + b_lane[par][nb & 1]];
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                            for (int nb = 0; nb < 4; nb++) dmma884(acc[par][mb][nb][0], acc[par][mb][nb][1], af[mb], bf[nb]);
+                    }
+                    if (SPIN) {
+                        // X2 rows of l-parity `par` have theta-parity 1 - par.  Q columns: (-aB_im, +aB_re) from the B tile,
+                        // U columns: (+aE_im, -aE_re) from the E tile -- the channel's other component, signed
 #pragma unroll
                         for (int par = 0; par < 2; par++) {
                             double af[4], bf[4];
 #pragma unroll
-                            for (int mb = 0; mb < 4; mb++) af[mb] = Ac[par * 4 * ALD + 8 * mb];
+                            for (int mb = 0; mb < 4; mb++) af[mb] = Ac[(8 + par * 4) * ALD + 8 * mb];
 #pragma unroll
-                            for (int nb = 0; nb < 4; nb++)
-                                bf[nb] = Bc[(SPIN ? (2 * (nb >> 1) + h) : (2 * h + (nb >> 1))) * BBLK + b_lane[par][nb & 1]];
+                            for (int nb = 0; nb < 4; nb++) {
+                                const double vsw = Bc[(2 * (1 - (nb >> 1)) + h) * BBLK + (b_lane[par][nb & 1] ^ 1)];
+                                bf[nb] = ((nb < 2) == ((g & 1) == 0)) ? -vsw : vsw;
+                            }
 #pragma unroll
                             for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-                                for (int nb = 0; nb < 4; nb++) dmma884(acc[par][mb][nb][0], acc[par][mb][nb][1], af[mb], bf[nb]);
+                                for (int nb = 0; nb < 4; nb++)
+                                    dmma884(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[mb], bf[nb]);
                         }
-                        if (SPIN) {
-                            // X2 rows of l-parity `par` have theta-parity 1 - par.  Q columns: (-aB_im, +aB_re) from the B tile,
-                            // U columns: (+aE_im, -aE_re) from the E tile -- the channel's other component, signed
+                    }
+                };
+                // fragment addresses = lane constants (hoisted above the item loop) + group / stage offsets:
+                //   A: row (par * 4 + t) of the group's tile, ring 8 mb + g
+                //   B: row r = 8 grp + 2 t + par, 16-byte unit (4 (nb & 1) + g / 2) ^ (r & 7) of column block blk
+                const double* Ac0 = Ap + sa * GPC * AROWS * ALD + a_lane;
+                const double* Bc0 = Bs + (size_t)sb * BSTAGE;
+                {
+                    // whole chunk live: the four groups run unrolled, their offsets are immediates
+                    const unsigned* bp = balA + (v * NSA + sa) * GPC;
+                    if (SPIN == 0 && ng == GPC && (bp[0] & bp[1] & bp[2] & bp[3]) == 0xffffffffu) {   // (spin 2: the unrolled chunk spills)
 #pragma unroll
-                            for (int par = 0; par < 2; par++) {
-                                double af[4], bf[4];
-#pragma unroll
-                                for (int mb = 0; mb < 4; mb++) af[mb] = Ac[(8 + par * 4) * ALD + 8 * mb];
-#pragma unroll
-                                for (int nb = 0; nb < 4; nb++) {
-                                    const double vsw = Bc[(2 * (1 - (nb >> 1)) + h) * BBLK + (b_lane[par][nb & 1] ^ 1)];
-                                    bf[nb] = ((nb < 2) == ((g & 1) == 0)) ? -vsw : vsw;
-                                }
-#pragma unroll
-                                for (int mb = 0; mb < 4; mb++)
-#pragma unroll
-                                    for (int nb = 0; nb < 4; nb++)
-                                        dmma884(acc[par ^ 1][mb][nb][0], acc[par ^ 1][mb][nb][1], af[mb], bf[nb]);
-                            }
+                        for (int grp = 0; grp < GPC; grp++) group_full(Ac0 + grp * AROWS * ALD, Bc0 + grp * 128);
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(emptyA + p * NSA + sa);
+                            mbar_arrive(emptyB + sb);
                         }
                         continue;
                     }
+                }
+#pragma unroll 1
+                for (int grp = 0; grp < ng; grp++) {
+                    const unsigned bal = balA[(v * NSA + sa) * GPC + grp];
+                    if (!bal) continue;
+                    const double* Ac = Ac0 + grp * AROWS * ALD;
+                    const double* Bc = Bc0 + grp * 128;
+                    if (bal == 0xffffffffu) { group_full(Ac, Bc); continue; }
                     int pm[4];
 #pragma unroll
                     for (int mb = 0; mb < 4; mb++) pm[mb] = (int)((bal >> (8 * mb)) & 0xffu);
