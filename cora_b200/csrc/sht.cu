@@ -804,6 +804,9 @@ __global__ void __launch_bounds__(lws::THREADS, 1) sht_legendre_ws_kernel(LegPar
         const int nring_tot = 4 * P.nside - 1;
         unsigned cglob = 0;
         for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+            // (channel block fastest.  Ring block fastest -- so that the CTAs running side by side share one (m, channel
+            // block) and its alm rows reach DRAM once instead of 2.3 times -- was measured SLOWER, 149 -> 164 ms at nside
+            // 512 x 1024 channels: DRAM is at 8 % of its peak here, and neighbouring CTAs then finish at different times.)
             const int cb = it % P.ncb;
             const int rb = (it / P.ncb) % P.nrb;
             const int m = it / (P.ncb * P.nrb);

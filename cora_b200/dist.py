@@ -495,7 +495,7 @@ class ShardedSky(object):
         self.peers.barrier()
         return self.p2p_sht(k, out=out)
 
-    def getsky(self, seed=None, nbatch=4):
+    def getsky(self, seed=None, nbatch=None):
         """The public end-to-end call of the sharded generator -- ``Sky3d.getsky`` (``cora/core/maps.py:227-235``)
         for one rank of a multi-GPU run: host frequency axis in, this rank's channels out as a numpy
         ``float64[cb, npix]`` array.  Every call uploads the per-sample vectors again (what ``clarray`` does per call),
