@@ -1300,7 +1300,7 @@ __device__ __forceinline__ void fold_bin(const double2* __restrict__ Fr, int c, 
 
 // PP: channel pairs per CTA (1 or 2); BLU: the class holds Bluestein rings (else power-of-two rings).
 template <int THREADS, int PP, bool BLU>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) sht_phase_kernel(PhaseParams Q) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (PP == 1 ? 3 : 4) : 1) sht_phase_kernel(PhaseParams Q) {
     extern __shared__ __align__(16) double2 xs[];   // [PP][pidx(Mmax)] + slice partials
     const int r = Q.ring_list[blockIdx.x];
     const RingDesc rd = Q.rings[r];
