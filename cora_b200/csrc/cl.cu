@@ -940,6 +940,8 @@ __global__ void ps21_gather_kernel(const double* __restrict__ tab, const int* __
 
 using namespace cb;
 
+static int dev_scratch(int id, size_t bytes, void** out);   // library-owned per-device scratch (defined below)
+
 extern "C" int cora_b200_cl_fill_sck(double A, double beta, double l_ref, double alpha, double nu_ref, double zeta,
                                      const double* nu_samples, const double* w, int l0, int l_step, int nl, int nz,
                                      int zint, double* out_cl, void* stream) {
@@ -947,8 +949,8 @@ extern "C" int cora_b200_cl_fill_sck(double A, double beta, double l_ref, double
     CB_REQUIRE(nl >= 1 && nz >= 1 && zint >= 1 && zint <= MAXZINT && l0 >= 0 && l_step >= 1, 1, "cl_fill_sck: bad sizes nl=%d nz=%d zint=%d", nl, nz, zint);
     cudaStream_t st = (cudaStream_t)stream;
     KTimer kt(K_CL_FILL, st);
-    double* bbar;
-    CB_CUDA(cudaMallocAsync(&bbar, sizeof(double) * (size_t)nz * nz, st));
+    double* bbar = nullptr;     // (one fill at a time per device: calls on different streams must not overlap)
+    if (int rc = dev_scratch(2, sizeof(double) * (size_t)nz * nz, (void**)&bbar)) return rc;
     sck_bbar_kernel<<<dim3(ceil_div(nz, 128), nz), 128, 0, st>>>(alpha, nu_ref, zeta, nu_samples, w, nz, zint, bbar);
     count_launch();
     CB_LAUNCH_CHECK();
@@ -956,7 +958,6 @@ extern "C" int cora_b200_cl_fill_sck(double A, double beta, double l_ref, double
     sck_scale_kernel<<<dim3(ceil_div(nz2, 256), nl), 256, 0, st>>>(A, beta, l_ref, bbar, l0, l_step, nl, nz2, out_cl);
     count_launch();
     CB_LAUNCH_CHECK();
-    CB_CUDA(cudaFreeAsync(bbar, st));
     return 0;
 }
 
@@ -1025,6 +1026,35 @@ static int fill_tile_table(int nz, const long long** out) {
 
 extern "C" long long cora_b200_cl_fill_21cm_ntiles(int nz) { return nz >= 1 ? fill_ntiles(nz) : 0; }
 
+// Small per-device scratch buffers owned by the library (grow-only, keyed by purpose).  NOT cudaMallocAsync: the
+// stream-ordered pool hands its memory back to the driver at every synchronisation (release threshold 0), so each step
+// paid a driver allocation -- measured as a 50 .. 850 ms stall of the fill launch one call in three when the device
+// memory is nearly full (profiles/e2e_diag.py), the jitter of the end-to-end numbers.
+struct DevScratch { int dev, id; size_t bytes; void* p; };
+static std::vector<DevScratch> g_dev_scratch;
+static int dev_scratch(int id, size_t bytes, void** out) {
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    for (auto& f : g_dev_scratch)
+        if (f.dev == dev && f.id == id) {
+            if (f.bytes < bytes) {
+                CB_CUDA(cudaDeviceSynchronize());
+                cudaFree(f.p);
+                f.p = nullptr; f.bytes = 0;
+                CB_CUDA(cudaMalloc(&f.p, bytes));
+                f.bytes = bytes;
+            }
+            *out = f.p;
+            return 0;
+        }
+    DevScratch f;
+    f.dev = dev; f.id = id; f.bytes = bytes; f.p = nullptr;
+    CB_CUDA(cudaMalloc(&f.p, bytes));
+    g_dev_scratch.push_back(f);
+    *out = f.p;
+    return 0;
+}
+
 // per-device scratch of the fill kernel (parked pair results, F3_NSLOTS rows of (F3_TILE - 1) nl doubles) and the slot
 // flags; grows with nl, never shrinks
 struct FillScratch { int dev; int nl; double* d; int* busy; };
@@ -1073,7 +1103,7 @@ static int fill21_launch(const double* tab, const double* chi, const double* b, 
     int* busy = nullptr;
     if (int rc = fill_scratch(nl, &scratch, &busy)) return rc;
     double* lx = nullptr;
-    CB_CUDA(cudaMallocAsync(&lx, sizeof(double) * (size_t)nl, st));
+    if (int rc = dev_scratch(1, sizeof(double) * (size_t)nl, (void**)&lx)) return rc;
     log10_table_kernel<<<ceil_div(nl, 256), 256, 0, st>>>(l0, l_step, nl, lx);
     count_launch();
     const size_t smem = sizeof(F3Smem);
@@ -1082,7 +1112,6 @@ static int fill21_launch(const double* tab, const double* chi, const double* b, 
                                                                  tile0, tile_step, lower_only, out_ptrs, l_owner, l_row, scratch, busy);
     count_launch();
     CB_LAUNCH_CHECK();
-    CB_CUDA(cudaFreeAsync(lx, st));
     return 0;
 }
 

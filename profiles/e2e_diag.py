@@ -4,7 +4,8 @@ import numpy as np, torch
 from cora_b200 import corr21cm, _dev, hputil, skysim
 _dev.bind_host_to_gpu(0)
 cr = corr21cm.Corr21cm(); cr.table()
-cr.nside, cr.frequencies, cr.oversample = 256, np.linspace(800., 400., 256, endpoint=False), 3
+NS, NC = int(os.environ.get("NSIDE", 256)), int(os.environ.get("NCHAN", 256))
+cr.nside, cr.frequencies, cr.oversample = NS, np.linspace(800., 400., NC, endpoint=False), 3
 orig_empty = torch.empty
 stamps = []
 def timed_empty(*a, **k):
@@ -16,9 +17,9 @@ for i in range(12):
     stamps.clear()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    cl = skysim.clarray(cr.angular_powerspectrum, 767, cr.frequencies, device_out=True)
+    cl = skysim.clarray(cr.angular_powerspectrum, 3 * NS - 1, cr.frequencies, device_out=True)
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    sky = skysim.mkfullsky(cl, 256, seed=i)
+    sky = skysim.mkfullsky(cl, NS, seed=i)
     t2 = time.perf_counter()
     del sky, cl
     t3 = time.perf_counter()
