@@ -276,8 +276,10 @@ class ShardedSky(object):
                               lower_only=lower_only)
         return out
 
-    def alm_local(self, cla, seed=0, gauss=None, roots=None):
-        """root + draw/apply for the local l's -> send buffer (complex128, one slab per destination)."""
+    def alm_local(self, cla, seed=0, gauss=None, roots=None, slab_tables=None):
+        """root + draw/apply for the local l's -> send buffer (complex128, one slab per destination).
+        ``slab_tables = (nu_base, nu_width, out)`` (device tables + output tensor) replaces the per-destination slab
+        layout, e.g. by the single ``[rows][nz]`` slab of the all-gather (``ShardPlan.gather_tables``)."""
         t = _dev.torch()
         lib = _lib.load()
         if roots is None:
@@ -287,7 +289,10 @@ class ShardedSky(object):
             root, used, _ = nputil.root_batched_device(cla, jitter_rel=1e-14, clip_rel=1e-16, out=outb, ws=rws)
         else:
             root, used = _dev.to_device(roots, t.float64), None
-        if self.size > 1:
+        nu_base, nu_width = self.nu_base, self.nu_width
+        if slab_tables is not None:
+            nu_base, nu_width, send = slab_tables
+        elif self.size > 1:
             send = self._persistent("send", lambda: _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128))
         lmax_loc = int(self.l_list.max())
         gptr, gld = self._draw_take(seed) if gauss is None else (None, 0)
@@ -312,8 +317,8 @@ class ShardedSky(object):
                       _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
             return panel
         _lib.call("cora_b200_draw_apply_slabs", _lib.ptr(root), _lib.ptr(self.l_list), _lib.ptr(used), self.nl, self.nz,
-                  self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(self.row0), _lib.ptr(self.nu_base),
-                  _lib.ptr(self.nu_width), _lib.ptr(send), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
+                  self.lmax, ctypes.c_ulonglong(int(seed)), gptr, gld, _lib.ptr(self.row0), _lib.ptr(nu_base),
+                  _lib.ptr(nu_width), _lib.ptr(send), _lib.ptr(ws), int(nbytes), _lib.stream_ptr())
         return send
 
     def alm_gathered(self, cla, seed=0, gauss=None, roots=None):
@@ -326,18 +331,12 @@ class ShardedSky(object):
         if self.size == 1:
             panel = self.alm_local(cla, seed=seed, gauss=gauss, roots=roots)
         else:
-            # one slab [rows_r][nz] instead of per-destination slabs: swap the slab tables for the call
+            # one slab [rows_r][nz] (every channel) instead of per-destination slabs
             base, width = self.plan.gather_tables()
-            keep = (self.nu_base, self.nu_width, self._buf.pop("send", None))
-            self.nu_base, self.nu_width = _dev.to_device(base, t.int64), _dev.to_device(width, t.int32)
-            try:
-                slab = self.alm_local(cla, seed=seed, gauss=gauss, roots=roots).clone() if self.nl else \
-                    _dev.empty((0,), t.complex128)
-            finally:
-                self.nu_base, self.nu_width = keep[0], keep[1]
-                self._buf.pop("send", None)
-                if keep[2] is not None:
-                    self._buf["send"] = keep[2]
+            slab = _dev.empty((int(self.plan.rows[self.rank]) * self.nz,), t.complex128)
+            if self.nl:
+                self.alm_local(cla, seed=seed, gauss=gauss, roots=roots,
+                               slab_tables=(_dev.to_device(base, t.int64), _dev.to_device(width, t.int32), slab))
             allb = allgather_alm(slab, self.plan, self.rank, self.group)
             panel = _dev.empty((nalm, self.nz), t.complex128)
             loff = _dev.to_device(self.plan.gather_l_offsets(), t.int64)

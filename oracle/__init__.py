@@ -16,7 +16,8 @@ algorithm, citing the reference ``file:line`` it follows.  Parity status:
   ``healpy>=1.17`` per ``pyproject.toml:30``), which is neither under /root/reference
   nor installable here, and the reference's tests hold no golden at that boundary:
   **parity unpinned**.  ``sht.py`` restates the published HEALPix RING synthesis and is
-  validated analytically (scipy ``sph_harm_y`` direct sums, closed forms).
+  validated analytically (scipy ``sph_harm_y`` direct sums, closed forms, and exact rational
+  evaluations of the spin-0 / spin-2 closed sums for every (l, m) up to l = 64).
 * forward SHT (``sht.py: map2alm / anafast``; ``healpy.map2alm``): **parity unpinned** for the
   same reason; pinned to the synthesis through the adjoint identity and a band-limited round trip.
 """

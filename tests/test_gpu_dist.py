@@ -108,8 +108,8 @@ def test_alms_allgather_virtual_ranks(size, partition):
     base, width = plan.gather_tables()
     for r in range(size):
         sh = cdist.ShardedSky(model, nside, freq, lmax=lmax, rank=r, size=size, partition=partition, exchange="collective")
-        sh.nu_base, sh.nu_width = _dev.to_device(base, torch.int64), _dev.to_device(width, torch.int32)
-        slab = sh.alm_local(sh.fill(), seed=9)
+        slab = torch.empty(int(plan.rows[r]) * nz, dtype=torch.complex128, device="cuda")
+        sh.alm_local(sh.fill(), seed=9, slab_tables=(_dev.to_device(base, torch.int64), _dev.to_device(width, torch.int32), slab))
         allb[r * n : r * n + slab.numel()] = slab
     panel = torch.empty((L * (L + 1) // 2, nz), dtype=torch.complex128, device="cuda")
     loff = _dev.to_device(plan.gather_l_offsets(), torch.int64)

@@ -303,3 +303,59 @@ def test_ring_subset_transforms_match_full():
     ad = osht.map2alm_adjoint(full, nside, lmax)
     for m, v in osht.map2alm_adjoint_ms(full, nside, lmax, [0, 5, 47]).items():
         np.testing.assert_array_equal(v, ad[:, osht.alm_index(lmax, m, m) : osht.alm_index(lmax, lmax, m) + 1])
+
+
+# ------------------------------------------------------------------ exact spin-2 known answers up to l = 64
+def _sylm_exact(s, l, m, half):
+    """_sY_lm(theta, 0) from Goldberg et al.'s closed sum in EXACT rational arithmetic.  ``half = (p, q, n)`` encodes the
+    half angle as cos(theta/2) = p / sqrt(n), sin(theta/2) = q / sqrt(n) (p^2 + q^2 = n): every term of the sum is then
+    the integer C(l-s, r) C(l+s, r+s-m) (-1)^(l-r-s) p^a q^b over n^l, so the alternating sum -- which loses all its
+    digits in floating point beyond l ~ 30 -- is exact; only the final square-root prefactor is rounded."""
+    from fractions import Fraction
+    from math import comb, factorial as f
+
+    p, q, n = half
+    tot = 0
+    for r in range(0, l - s + 1):
+        k = r + s - m
+        if k < 0 or k > l + s:
+            continue
+        a, b = 2 * r + s - m, 2 * l - 2 * r - s + m
+        tot += comb(l - s, r) * comb(l + s, k) * (-1) ** (l - r - s) * p**a * q**b
+    pref2 = Fraction(f(l + m) * f(l - m) * (2 * l + 1), f(l + s) * f(l - s))      # times 1 / (4 pi)
+    val = Fraction(tot, n**l)
+    return (-1.0) ** m * float(val) * np.sqrt(float(pref2) / (4 * np.pi)) if abs(val) < 1e300 else None
+
+
+@pytest.mark.parametrize("half", [(2, 1, 5), (2, 3, 13), (4, 3, 25), (1, 7, 50)])
+def test_spin2_functions_exact_known_answers_to_l64(half):
+    """X1 + X2 = _{+2}Y_lm(theta, 0) and X1 - X2 = _{-2}Y_lm(theta, 0) for every (l, m) up to l = 64,
+    against exact rational evaluations of the closed form -- independent of any recurrence."""
+    p, q, n = half
+    c = np.array([(p * p - q * q) / n])            # cos(theta) = cos^2 - sin^2 of the half angle
+    s = np.array([2.0 * p * q / n])
+    lmax = 64
+    worst = 0.0
+    for m in range(0, lmax + 1):
+        X1, X2 = sht._spin2_X(lmax, m, c, s)
+        for l in range(max(m, 2), lmax + 1):
+            yp = _sylm_exact(2, l, m, half)
+            ym = _sylm_exact(-2, l, m, half)
+            scale = max(abs(yp), abs(ym), 1e-3)
+            worst = max(worst, abs(X1[l - m, 0] + X2[l - m, 0] - yp) / scale, abs(X1[l - m, 0] - X2[l - m, 0] - ym) / scale)
+    assert worst < 1e-11, worst
+
+
+def test_scalar_lambda_exact_known_answers_to_l64():
+    """lambda_lm(theta) = _0Y_lm(theta, 0) against the same exact closed form (l up to 64, all m)."""
+    half = (2, 3, 13)
+    p, q, n = half
+    c = np.array([(p * p - q * q) / n])
+    s = np.array([2.0 * p * q / n])
+    worst = 0.0
+    for m in range(0, 65):
+        lam = sht.lambda_lm(64, m, c, s)
+        for l in range(m, 65):
+            y = _sylm_exact(0, l, m, half)
+            worst = max(worst, abs(lam[l - m, 0] - y) / max(abs(y), 1e-3))
+    assert worst < 1e-11, worst
