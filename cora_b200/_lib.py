@@ -72,6 +72,7 @@ SIGNATURES = {
     "cora_b200_diag_max": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "cora_b200_root_multi_workspace_bytes": (_ll, [_i, _i, _i]),
     "cora_b200_root_batched_multi": (_i, [_vp, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "cora_b200_alm_scale_l": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
     "cora_b200_set_legendre_ws": (_i, [_i]),
     "cora_b200_corr_bins": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "cora_b200_legendre_table": (_i, [_vp, _vp, _i, _i, _vp, _ll, _vp]),

@@ -66,9 +66,37 @@ __global__ void slabs_to_panel_kernel(const double2* __restrict__ recv, const lo
     }
 }
 
+// panel[idx(l, m)][chan0 + c] *= scale[l, c]: a per-(l, channel) factor on every a_lm (Gaussian beam of
+// healpy.smoothing, one width per channel).  grid (channel blocks, l), threads over (m, c).
+__global__ void alm_scale_l_kernel(double2* __restrict__ panel, long long stride, int chan0, int nchan, int lmax,
+                                   const double* __restrict__ scale) {
+    const int l = blockIdx.y;
+    const long long n = (long long)(l + 1) * nchan;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(e / nchan), c = (int)(e - (long long)m * nchan);
+        const long long idx = (long long)m * (2 * lmax + 1 - m) / 2 + l;
+        const double f = scale[(long long)l * nchan + c];
+        double2 v = panel[idx * stride + chan0 + c];
+        v.x *= f; v.y *= f;
+        panel[idx * stride + chan0 + c] = v;
+    }
+}
+
 }  // namespace cb
 
 using namespace cb;
+
+extern "C" int cora_b200_alm_scale_l(void* alm_panel, long long panel_stride, int chan0, int nchan, int lmax, const double* scale,
+                                     void* stream) {
+    CB_REQUIRE(alm_panel && scale && nchan >= 1 && lmax >= 0 && lmax + 1 <= 65535, 1, "alm_scale_l: bad arguments");
+    KTimer kt(K_LAYOUT, (cudaStream_t)stream);
+    const long long per_l = (long long)(lmax + 1) * nchan;
+    dim3 grid((unsigned)std::min<long long>(64, (per_l + 255) / 256), lmax + 1);
+    alm_scale_l_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((double2*)alm_panel, panel_stride, chan0, nchan, lmax, scale);
+    count_launch();
+    CB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int cora_b200_alm_slabs_to_panel(const void* recv, const long long* l_off, int lmax, int nchan, void* alm_panel,
                                             long long panel_stride, int chan0, void* stream) {

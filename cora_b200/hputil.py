@@ -453,3 +453,57 @@ def sphtrans_inv_complex(alm, nside):
     almr = _make_half_alm(alm)
     almi = 1.0j * (alm[:, : almr.shape[1]] - almr)
     return sphtrans_inv_real(almr, nside) + 1.0j * sphtrans_inv_real(almi, nside)
+
+
+# ------------------------------------------------------------------ smoothing and coordinate rotation
+def smoothing(hpmap, fwhm=0.0, sigma=None, iter=3, lmax=None):
+    """``healpy.smoothing`` with the defaults cora relies on (``cora/foreground/galaxy.py:101-104,165-185``): analysis
+    without ring weights and ``iter`` refinements up to ``lmax = 3 nside - 1``, multiplication by the Gaussian beam
+    ``exp(-l (l + 1) sigma^2 / 2)`` (``sigma = fwhm / sqrt(8 ln 2)``), synthesis.  ``hpmap``: ``[npix]`` or
+    ``[nmap, npix]``; ``fwhm`` / ``sigma`` in radians, scalars or one per map.  Both transforms and the beam run on the
+    GPU (``cora_b200_map2alm`` -> ``cora_b200_alm_scale_l`` -> ``cora_b200_alm2map``)."""
+    t = _dev.torch()
+    m = np.asarray(hpmap, dtype=np.float64)
+    single = m.ndim == 1
+    m2 = np.ascontiguousarray(m.reshape(-1, m.shape[-1]))
+    nmap, npix = m2.shape
+    nside = _nside_of(npix)
+    lmax = 3 * nside - 1 if lmax is None else int(lmax)
+    sig = np.broadcast_to(np.asarray(fwhm, dtype=np.float64) / np.sqrt(8.0 * np.log(2.0)) if sigma is None
+                          else np.asarray(sigma, dtype=np.float64), (nmap,))
+    ell = np.arange(lmax + 1, dtype=np.float64)
+    beam = np.exp(-0.5 * ell[:, None] * (ell[:, None] + 1.0) * sig[None, :] ** 2)           # [L, nmap]
+    panel = map2alm_device(_dev.to_device(m2, t.float64), nside, lmax, iter=iter)
+    _lib.call("cora_b200_alm_scale_l", _lib.ptr(panel), int(panel.shape[1]), 0, nmap, lmax,
+              _lib.ptr(_dev.to_device(np.ascontiguousarray(beam), t.float64)), _lib.stream_ptr())
+    out = _dev.to_host(alm2map_device(panel, nside, lmax, _lib.ALM_PANEL, int(panel.shape[1]), nmap))
+    return out[0] if single else out.reshape(m.shape)
+
+
+def coord_x2y(map, x, y):
+    """Rotate a map between coordinate systems (``hputil.py:534-566``): every output pixel takes the bilinear
+    interpolation of the input map at its own direction rotated by ``Rotator(coord=[y, x])``.  Works on a series of
+    maps (Healpix index last), in place like the reference.  'C' celestial, 'G' Galactic ('E' ecliptic is not
+    provided)."""
+    from . import healpix
+
+    if x not in ["C", "G", "E"] or y not in ["C", "G", "E"]:
+        raise Exception("Co-ordinate system invalid.")
+    npix = map.shape[-1]
+    angpos = ang_positions(_nside_of(npix))
+    theta, phi = healpix.rotate_angles(angpos[:, 0], angpos[:, 1], y, x)
+    pix, wgt = healpix.get_interp_weights(_nside_of(npix), theta, phi)
+    map_flat = map.reshape((-1, npix))
+    for i in range(map_flat.shape[0]):
+        map_flat[i] = np.sum(map_flat[i][pix] * wgt, axis=0)
+    return map_flat.reshape(map.shape)
+
+
+def coord_g2c(map_):
+    """Galactic -> celestial (``hputil.py:569-585``)."""
+    return coord_x2y(map_, "G", "C")
+
+
+def coord_c2g(map_):
+    """Celestial -> Galactic (``hputil.py:588-604``)."""
+    return coord_x2y(map_, "C", "G")

@@ -320,6 +320,12 @@ int cora_b200_draw_apply_peers(const double* root, const int* l_list_h, const in
                                long long gauss_ld, const void* nu_ptr, const int* nu_width, void* workspace,
                                long long ws_bytes, void* stream);
 
+/* alm_panel[idx(l, m)][chan0 + c] *= scale[l * nchan + c] (device float64[(lmax+1) * nchan]): a per-(l, channel) factor
+ * on every a_lm -- the Gaussian beam exp(-l (l+1) sigma^2 / 2) of healpy.smoothing as ConstrainedGalaxy calls it
+ * (cora/foreground/galaxy.py:165-185), between cora_b200_map2alm and cora_b200_alm2map.                          */
+int cora_b200_alm_scale_l(void* alm_panel, long long panel_stride, int chan0, int nchan, int lmax, const double* scale,
+                          void* stream);
+
 /* Which Legendre kernels the inverse SHT launches: bit 0 = warp-specialised scalar kernel, bit 1 = warp-specialised
  * spin-2 kernel (default 3, or the CORA_B200_LEGENDRE_WS environment variable at load); cleared bits select the
  * single-role kernel.  Returns the previous mask; mask < 0 only queries.  (A/B measurements and tests.)          */
