@@ -734,15 +734,43 @@ __global__ void __launch_bounds__(1024) lr_pchol_kernel(RootBlocks B, WaveCtx w)
         }
         __syncthreads();
     }
-    // ---- certificate: |A - L L^T| over the lower triangle; thread = column j, walks the rows i >= j
+    // ---- certificate: |A - L L^T| over the lower triangle, in 4 x 4 register blocks (bi >= bj): per k a thread loads 4
+    // values of column block bi (the same for its neighbours: broadcast) and 4 of bj (consecutive across threads) for 16
+    // FMAs.  (One thread per column walking the rows read two operands per FMA from L2 -- 500 MB per 1024^2 matrix,
+    // 3.3 ms per CTA, the largest part of the fallback.)
     const double bound = 4.0 * s_tau + 64.0 * 2.220446049250313e-16 * s_dmax;
     int bad = 0;
-    for (int j = tid; j < nz; j += blockDim.x) {
-        for (int i = j; i < nz; i++) {
-            double v = A[(long long)i * nz + j];
-            for (int kk = 0; kk < k; kk++) v = fma(-Lws[(long long)kk * nz + i], Lws[(long long)kk * nz + j], v);
-            bad |= !(fabs(v) <= bound);
+    const int nblk = (nz + 3) >> 2;
+    const long long ntile = (long long)nblk * (nblk + 1) / 2;
+    for (long long tix = tid; tix < ntile; tix += blockDim.x) {
+        // tile index -> (bi, bj <= bi), row-major over the lower triangle of blocks
+        int bi = (int)((sqrt(8.0 * (double)tix + 1.0) - 1.0) * 0.5);
+        while ((long long)(bi + 1) * (bi + 2) / 2 <= tix) bi++;
+        while ((long long)bi * (bi + 1) / 2 > tix) bi--;
+        const int bj = (int)(tix - (long long)bi * (bi + 1) / 2);
+        const int i0 = 4 * bi, j0 = 4 * bj;
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
+        for (int kk = 0; kk < k; kk++) {
+            const double* row = Lws + (long long)kk * nz;
+            double li[4], lj[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) { li[r] = (i0 + r < nz) ? row[i0 + r] : 0.0; lj[r] = (j0 + r < nz) ? row[j0 + r] : 0.0; }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = fma(li[r], lj[c], acc[r][c]);
         }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int i = i0 + r, j = j0 + c;
+                if (i < nz && j <= i) bad |= !(fabs(A[(long long)i * nz + j] - acc[r][c]) <= bound);
+            }
     }
     bad = __syncthreads_or(bad);
     if (tid == 0) {
