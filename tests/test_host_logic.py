@@ -188,3 +188,26 @@ def test_map_writer_layout_roundtrip(tmp_path):
     mapio.write_map(str(tmp_path / "i"), full, freq, include_pol=False)
     g, h = mapio.read_map(str(tmp_path / "i"))
     assert g.shape == (5, 1, npix) and h["pol"] == ["I"] and h["freq"]["width"][0] == 80.0
+
+
+def test_tabulated_correlation_host_semantics():
+    """TabulatedCorrelation called on the host is numpy.interp (clamped at both ends), linear in r or in ln r."""
+    from cora_b200 import corrfunc
+
+    r = np.array([0.5, 1.0, 2.0, 4.0])
+    xi = np.array([3.0, 2.0, 0.5, 0.25])
+    lin = corrfunc.TabulatedCorrelation(r, xi)
+    np.testing.assert_allclose(lin(np.array([0.0, 0.5, 0.75, 3.0, 9.0])), [3.0, 3.0, 2.5, 0.375, 0.25])
+    log = corrfunc.TabulatedCorrelation(r, xi, kind="log")
+    np.testing.assert_allclose(log(np.array([0.0, np.sqrt(2.0), 8.0])), [3.0, 1.25, 0.25])
+    assert lin(np.ones((2, 3, 4))).shape == (2, 3, 4)
+    with pytest.raises(ValueError):
+        corrfunc.TabulatedCorrelation(r[::-1], xi)
+    with pytest.raises(ValueError):
+        corrfunc.TabulatedCorrelation(r, xi, kind="cubic")
+    # cosine rule: the cancellation-free form equals the textbook one
+    mu, x = np.array([-0.3, 0.999999]), np.array([10.0, 10.5, 300.0])
+    got = corrfunc.cosine_rule(mu, x, x)
+    want = np.sqrt(x[None, :, None] ** 2 + x[None, None, :] ** 2 - 2 * x[None, :, None] * x[None, None, :] * mu[:, None, None])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-6)
+    assert np.all(np.diagonal(got, axis1=1, axis2=2)[1] < 0.5)
