@@ -780,7 +780,9 @@ __global__ void __launch_bounds__(1024) lr_pchol_kernel(RootBlocks B, WaveCtx w)
 }
 
 // step 2: orthogonalise the r columns of L (rows of L^T) -> u_k, lambda_k = |u_k|^2; largest + jitter -> eig_max
-__global__ void __launch_bounds__(1024) lr_jacobi_kernel(RootBlocks B, WaveCtx w, int max_sweeps) {
+constexpr int LJ_RMAX = 64;     // largest factor rank that is Gram-preconditioned (G and V in shared memory)
+constexpr int LJ_XC = 128;      // columns of L^T transformed per chunk
+__global__ void __launch_bounds__(1024) lr_jacobi_kernel(RootBlocks B, WaveCtx w, int max_sweeps, int precondition) {
     __shared__ int s_rot;
     __shared__ double s_red[32];
     int l, b;
@@ -791,8 +793,75 @@ __global__ void __launch_bounds__(1024) lr_jacobi_kernel(RootBlocks B, WaveCtx w
     double* lam = w.evals + (long long)blockIdx.x * nz;
     const double cmax = w.dmax[l] * w.jitter_rel;
     int sweep = 0;
-    if (r > 1) sweep = hestenes_sweeps(Lt, nullptr, r, nz, max_sweeps, &s_rot);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (r > 1 && r <= LJ_RMAX && precondition) {
+        // Gram preconditioning.  The one-sided Jacobi below streams the r rows (r x nz doubles, 480 KB for rank 60 at
+        // 1024 channels: L2, not shared memory) twice per pair and needs ~8-10 sweeps from the pivoted-Cholesky factor.
+        // The r x r Gram matrix G = L^T L fits shared memory: its eigenvectors W (one-sided Jacobi on G with accumulated
+        // rotations, all in shared memory) make the rows of W^T L^T orthogonal up to the accuracy G allows (it squares
+        // the condition number), after which the streaming Jacobi -- which restores the high relative accuracy --
+        // converges in one or two sweeps.
+        extern __shared__ __align__(16) double lj_smem[];
+        double* Gs = lj_smem;                   // [r][r]
+        double* Vs = Gs + LJ_RMAX * LJ_RMAX;    // [r][r]
+        double* Xs = Vs + LJ_RMAX * LJ_RMAX;    // [r][LJ_XC] column chunk of L^T
+        // (1) G = L^T L in 4 x 4 blocks of (p, q <= p): a warp streams 8 rows once for 16 dot products
+        const int nb4 = (r + 3) >> 2;
+        for (int tile = warp; tile < nb4 * (nb4 + 1) / 2; tile += nwarp) {
+            int bp = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+            while ((bp + 1) * (bp + 2) / 2 <= tile) bp++;
+            while (bp * (bp + 1) / 2 > tile) bp--;
+            const int bq = tile - bp * (bp + 1) / 2;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = 0.0;
+            for (int c = lane; c < nz; c += 32) {
+                double xp[4], xq[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    xp[a] = (4 * bp + a < r) ? Lt[(long long)(4 * bp + a) * nz + c] : 0.0;
+                    xq[a] = (4 * bq + a < r) ? Lt[(long long)(4 * bq + a) * nz + c] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = fma(xp[a], xq[b2], acc[a][b2]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2++) {
+                    const double v = warp_sum(acc[a][b2]);
+                    const int pp = 4 * bp + a, qq = 4 * bq + b2;
+                    if (lane == 0 && pp < r && qq < r) { Gs[pp * r + qq] = v; Gs[qq * r + pp] = v; }
+                }
+        }
+        for (int e = threadIdx.x; e < r * r; e += blockDim.x) Vs[e] = (e / r == e % r) ? 1.0 : 0.0;
+        __syncthreads();
+        // (2) rows of Vs <- eigenvectors of G
+        hestenes_sweeps(Gs, Vs, r, r, max_sweeps, &s_rot);
+        __syncthreads();
+        // (3) L^T <- V L^T, column chunk by column chunk (the chunk's old values of all rows are staged first)
+        for (int c0 = 0; c0 < nz; c0 += LJ_XC) {
+            const int nc = min(LJ_XC, nz - c0);
+            for (int e = threadIdx.x; e < r * LJ_XC; e += blockDim.x) {
+                const int pp = e / LJ_XC, cc = e - pp * LJ_XC;
+                Xs[e] = (cc < nc) ? Lt[(long long)pp * nz + c0 + cc] : 0.0;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < r * LJ_XC; e += blockDim.x) {
+                const int kk = e / LJ_XC, cc = e - kk * LJ_XC;
+                if (cc >= nc) continue;
+                double v = 0.0;
+                for (int pp = 0; pp < r; pp++) v = fma(Vs[kk * r + pp], Xs[pp * LJ_XC + cc], v);
+                Lt[(long long)kk * nz + c0 + cc] = v;
+            }
+            __syncthreads();
+        }
+    }
+    if (r > 1) sweep = hestenes_sweeps(Lt, nullptr, r, nz, max_sweeps, &s_rot);
     double mx = 0.0;
     for (int k = warp; k < r; k += nwarp) {
         double s = 0.0;
@@ -920,6 +989,8 @@ static long long root_fixed_bytes(int nb, int nl, int nz) {
 // CORA_B200_JACOBI_MAX_NZ overrides (e.g. a huge value forces the exact route everywhere).
 // 1: the first Cholesky kernel (separate read-modify-write / diagonal / row-solve phases), for A/B runs
 static const bool g_chol_v1 = [] { const char* e = getenv("CORA_B200_CHOL_V1"); return e && e[0] == '1'; }();
+// low-rank eigen route: Gram-precondition the one-sided Jacobi on the factor (CORA_B200_LR_PRECOND=0 turns it off)
+static const bool g_lr_precond = [] { const char* e = getenv("CORA_B200_LR_PRECOND"); return !(e && e[0] == '0'); }();
 // operand ring of the fused-tile Cholesky: 0 = 2 stages of 16 k, 1 = 3 stages of 8 k (deeper prefetch, more barriers)
 static const bool g_chol_deep = [] { const char* e = getenv("CORA_B200_CHOL_DEEP"); return e && e[0] == '1'; }();
 static int g_jacobi_max_nz = [] { const char* e = getenv("CORA_B200_JACOBI_MAX_NZ"); return e ? atoi(e) : 128; }();
@@ -1064,7 +1135,11 @@ extern "C" int cora_b200_root_batched_multi(const double* const* cl_blocks, int 
             const size_t smem = sizeof(double) * 2 * (size_t)nz;
             CB_CUDA(cudaFuncSetAttribute(lr_pchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             lr_pchol_kernel<<<nslots, nz >= 512 ? 1024 : 512, smem, st>>>(B, w);
-            lr_jacobi_kernel<<<nslots, 1024, 0, st>>>(B, w, 60);
+            {
+                const size_t sm_j = sizeof(double) * (2 * LJ_RMAX * LJ_RMAX + LJ_RMAX * LJ_XC);
+                CB_CUDA(cudaFuncSetAttribute(lr_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_j));
+                lr_jacobi_kernel<<<nslots, 1024, sm_j, st>>>(B, w, 60, g_lr_precond ? 1 : 0);
+            }
             lr_decide_kernel<<<ceil_div(nslots, 128), 128, 0, st>>>(B, w, nslots);
             count_launch(3);
         } else {
