@@ -223,3 +223,26 @@ def test_mpiarray_single_rank():
     assert np.array_equal(a.allgather(), np.arange(12.0).reshape(4, 3))
     assert a.redistribute(axis=1).axis == 1
     assert not mpiarray.is_distributed(np.zeros(3))
+
+
+@pytest.mark.parametrize("nz", [1, 7, 256, 1024])
+@pytest.mark.parametrize("size", [1, 2, 3, 8])
+def test_fill_tiles_are_dealt_interleaved_and_cover_everything(nz, size):
+    """The sharded 21cm fill deals its channel-pair tiles rank, rank + G, ... (dist.fill_tile_share): every tile of
+    cora_b200_cl_fill_21cm_ntiles(nz) exactly once over the ranks, shares equal to within one tile."""
+    from cora_b200 import _lib
+    from cora_b200 import dist as cdist
+
+    ntile = int(_lib.load().cora_b200_cl_fill_21cm_ntiles(nz))
+    assert ntile >= (nz * (nz + 1) // 2 + 3) // 4
+    seen = np.zeros(ntile, dtype=int)
+    counts = []
+    for r in range(size):
+        t0, n, step = cdist.fill_tile_share(ntile, r, size)
+        assert step == size
+        idx = t0 + step * np.arange(n)
+        assert n == 0 or idx.max() < ntile
+        seen[idx] += 1
+        counts.append(n)
+    assert np.all(seen == 1)
+    assert max(counts) - min(counts) <= 1
