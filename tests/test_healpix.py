@@ -133,3 +133,12 @@ def test_coord_rotation_of_a_dipole():
     assert np.max(np.abs(back[0] - gal[0])) < 1e-2
     with pytest.raises(Exception, match="Co-ordinate system invalid"):
         hputil.coord_x2y(gal, "G", "Q")
+
+
+def test_pix2ang_known_answers_from_healpy_docs():
+    # healpy.pix2ang / pix2vec docstring examples (nside 16, RING)
+    th, ph = hpx.pix2ang(16, np.array([1440, 427, 1520, 0, 3068]))
+    np.testing.assert_allclose(th, [1.52911759, 0.78550497, 1.57079633, 0.05103658, 3.09055608], atol=5e-9)
+    np.testing.assert_allclose(ph, [0.0, 0.78539816, 1.61988371, 0.78539816, 0.78539816], atol=5e-9)
+    v = hpx.ang2vec(*hpx.pix2ang(16, np.array([1504])))[0]
+    np.testing.assert_allclose(v, [0.99879545620517241, 0.049067674327418015, 0.0], atol=1e-15)
